@@ -1,0 +1,207 @@
+"""ctypes binding of the C ABI in include/garden_sceneprep.h (libgarden_sceneprep.so).
+
+This is the Python face of the product used by bench.py and tests/: it only marshals plain pointers and sizes.
+There is no fallback path: if the library is missing, or no sm_100 GPU is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from .layout import RECORD_DTYPE, VIEW_DTYPE
+
+LIB_PATH = Path(__file__).resolve().parent / "libgarden_sceneprep.so"
+
+GSP_OK, GSP_ERR_INVALID, GSP_ERR_CUDA, GSP_ERR_NOMEM, GSP_ERR_STATE, GSP_ERR_HIERARCHY = range(6)
+GSP_MAX_POOLS, GSP_MAX_VIEWS = 8, 16
+
+# every symbol include/garden_sceneprep.h declares: name -> (restype, argtypes)
+_u32, _i32, _u64, _vp = C.c_uint32, C.c_int, C.c_uint64, C.c_void_p
+_pp = C.POINTER(C.c_void_p)
+_pu32 = C.POINTER(C.c_uint32)
+SYMBOLS = {
+    "gsp_version": (C.c_char_p, []),
+    "gsp_create": (_i32, [_i32, _pp]),
+    "gsp_destroy": (None, [_vp]),
+    "gsp_last_error": (C.c_char_p, [_vp]),
+    "gsp_set_stream": (_i32, [_vp, _vp]),
+    "gsp_set_transforms": (_i32, [_vp, _vp, _u32, _u32]),
+    "gsp_update_transforms": (_i32, [_vp, _vp, _u32, _u32, _u32]),
+    "gsp_set_pool_count": (_i32, [_vp, _u32]),
+    "gsp_set_mesh_pool": (_i32, [_vp, _u32, _u32, _u32, _vp, _u32, _u32, _u32, _vp]),
+    "gsp_set_views": (_i32, [_vp, _u32, _vp, _vp]),
+    "gsp_run": (_i32, [_vp]),
+    "gsp_run_async": (_i32, [_vp]),
+    "gsp_sync": (_i32, [_vp]),
+    "gsp_unsorted_buffer_count": (_u32, [_vp, _u32]),
+    "gsp_sorted_buffer_count": (_u32, [_vp, _u32]),
+    "gsp_get_unsorted": (_i32, [_vp, _u32, _u32, _pp, _pu32, _pu32]),
+    "gsp_get_sorted_counts": (_i32, [_vp, _u32, _u32, _pu32, _pu32]),
+    "gsp_get_sorted": (_i32, [_vp, _u32, _i32, _pp, _pu32]),
+    "gsp_get_unsorted_device": (_i32, [_vp, _u32, _u32, _pp, _pu32, _pu32]),
+    "gsp_get_sorted_device": (_i32, [_vp, _u32, _i32, _pp, _pu32]),
+    "gsp_get_sorted_run_device": (_i32, [_vp, _u32, _i32, _u32, _pp, _pp, _pu32]),
+    "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),
+    "gsp_download_models": (_i32, [_vp, _u32, _vp]),
+    "gsp_last_launch_count": (_u32, [_vp]),
+    "gsp_last_visible_total": (_u64, [_vp]),
+    "gsp_merge_runs": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+class ScenePrepError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"gsp error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libgarden_sceneprep.so and binds every declared symbol. Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `python -m garden_b200.build` (or __graft_entry__.build()). "
+            "There is no CPU fallback for the scene-preparation path.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _ptr(a) -> int:
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+class ScenePrep:
+    """One gsp_context. Mirrors the call sequence of MeshRenderSystem (prepareSystems -> prepareMeshes per view)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        handle = C.c_void_p()
+        rc = self.lib.gsp_create(device, C.byref(handle))
+        if rc != GSP_OK:
+            raise ScenePrepError(rc, self.lib.gsp_last_error(None).decode())
+        self.h = handle
+        self.view_count = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gsp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != GSP_OK:
+            raise ScenePrepError(rc, self.lib.gsp_last_error(self.h).decode())
+
+    # ---- staging ----
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.gsp_set_stream(self.h, cuda_stream))
+
+    def set_transforms(self, aos, stride: int, occupancy: int):
+        self._check(self.lib.gsp_set_transforms(self.h, _ptr(aos), stride, occupancy))
+
+    def update_transforms(self, aos, stride: int, first: int, count: int):
+        self._check(self.lib.gsp_update_transforms(self.h, _ptr(aos), stride, first, count))
+
+    def set_pool_count(self, n: int):
+        self._check(self.lib.gsp_set_pool_count(self.h, n))
+
+    def set_mesh_pool(self, pool: int, render_type: int, aos, stride: int, occupancy: int, count: int | None = None,
+                      draw_ready: bool = True, ready_counts=None):
+        if count is None:
+            count = occupancy
+        if ready_counts is not None:
+            ready_counts = np.ascontiguousarray(ready_counts, dtype=np.uint8)
+            assert ready_counts.size >= occupancy
+        self._check(self.lib.gsp_set_mesh_pool(self.h, pool, render_type, 1 if draw_ready else 0, _ptr(aos), stride,
+                                               occupancy, count, _ptr(ready_counts)))
+
+    def set_views(self, views: np.ndarray, camera_pos):
+        views = np.ascontiguousarray(views, dtype=VIEW_DTYPE)
+        cam = np.ascontiguousarray(camera_pos, dtype=np.float32)
+        self._check(self.lib.gsp_set_views(self.h, views.size, views.ctypes.data, cam.ctypes.data))
+        self.view_count = views.size
+
+    # ---- frame ----
+    def run(self):
+        self._check(self.lib.gsp_run(self.h))
+
+    def run_async(self):
+        self._check(self.lib.gsp_run_async(self.h))
+
+    def sync(self):
+        self._check(self.lib.gsp_sync(self.h))
+
+    # ---- results ----
+    def unsorted_buffer_count(self, view: int) -> int:
+        return self.lib.gsp_unsorted_buffer_count(self.h, view)
+
+    def sorted_buffer_count(self, view: int) -> int:
+        return self.lib.gsp_sorted_buffer_count(self.h, view)
+
+    def _records(self, ptr: C.c_void_p, count: int, copy: bool) -> np.ndarray:
+        if count == 0 or not ptr.value:
+            return np.zeros(0, dtype=RECORD_DTYPE)
+        buf = (C.c_uint8 * (count * 64)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=RECORD_DTYPE, count=count)
+        return arr.copy() if copy else arr
+
+    def get_unsorted(self, view: int, buffer: int, copy: bool = True):
+        ptr, draw, inst = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self._check(self.lib.gsp_get_unsorted(self.h, view, buffer, C.byref(ptr), C.byref(draw), C.byref(inst)))
+        return self._records(ptr, draw.value, copy), draw.value, inst.value
+
+    def get_sorted_counts(self, view: int, buffer: int):
+        draw, inst = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.gsp_get_sorted_counts(self.h, view, buffer, C.byref(draw), C.byref(inst)))
+        return draw.value, inst.value
+
+    def get_sorted(self, view: int, which: int, copy: bool = True):
+        ptr, draw = C.c_void_p(), C.c_uint32()
+        self._check(self.lib.gsp_get_sorted(self.h, view, which, C.byref(ptr), C.byref(draw)))
+        return self._records(ptr, draw.value, copy), draw.value
+
+    def get_unsorted_device(self, view: int, buffer: int):
+        ptr, draw, inst = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self._check(self.lib.gsp_get_unsorted_device(self.h, view, buffer, C.byref(ptr), C.byref(draw), C.byref(inst)))
+        return ptr.value, draw.value, inst.value
+
+    def get_sorted_run_device(self, view: int, kind: int, buffer: int = 0):
+        keys, pays, count = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        self._check(self.lib.gsp_get_sorted_run_device(self.h, view, kind, buffer, C.byref(keys), C.byref(pays),
+                                                       C.byref(count)))
+        return keys.value, pays.value, count.value
+
+    def writeback_visible(self, pool: int, aos, stride: int):
+        self._check(self.lib.gsp_writeback_visible(self.h, pool, _ptr(aos), stride))
+
+    def download_models(self, pool: int, occupancy: int) -> np.ndarray:
+        out = np.zeros((occupancy, 12), dtype=np.float32)
+        self._check(self.lib.gsp_download_models(self.h, pool, out.ctypes.data))
+        return out
+
+    def last_launch_count(self) -> int:
+        return self.lib.gsp_last_launch_count(self.h)
+
+    def last_visible_total(self) -> int:
+        return self.lib.gsp_last_visible_total(self.h)

@@ -1,0 +1,755 @@
+// C ABI of libgarden_sceneprep.so (include/garden_sceneprep.h): context, staging uploads, frame orchestration, results.
+// Orchestration mirrors MeshRenderSystem::prepareMeshes (source/system/render/mesh.cpp:331-553) for all views of a frame.
+#include "sceneprep_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace gsp;
+
+struct gsp_context
+{
+	Context c;
+};
+
+static std::string gCreateError;
+
+#define GSP_CUDA(call)                                                                             \
+	do {                                                                                           \
+		cudaError_t err__ = (call);                                                                \
+		if (err__ != cudaSuccess) {                                                                \
+			c.error = std::string(#call) + ": " + cudaGetErrorString(err__);                       \
+			return GSP_ERR_CUDA;                                                                   \
+		}                                                                                          \
+	} while (0)
+
+static int fail(Context& c, int code, const char* message)
+{
+	c.error = message;
+	return code;
+}
+
+template<class T>
+static cudaError_t ensureDevice(T*& ptr, size_t& cap, size_t need, bool keep = false, cudaStream_t stream = nullptr)
+{
+	if (need <= cap && ptr)
+		return cudaSuccess;
+	size_t newCap = std::max(need, cap + cap / 2);
+	if (newCap == 0) newCap = 1;
+	T* fresh = nullptr;
+	cudaError_t err = cudaMalloc((void**)&fresh, newCap * sizeof(T));
+	if (err != cudaSuccess)
+		return err;
+	if (ptr)
+	{
+		if (keep && cap)
+			cudaMemcpyAsync(fresh, ptr, cap * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+		cudaStreamSynchronize(stream);
+		cudaFree(ptr);
+	}
+	ptr = fresh; cap = newCap;
+	return cudaSuccess;
+}
+template<class T>
+static cudaError_t ensureDevice32(T*& ptr, uint32_t& cap, size_t need)
+{
+	size_t cap64 = cap;
+	cudaError_t err = ensureDevice(ptr, cap64, need);
+	cap = (uint32_t)cap64;
+	return err;
+}
+
+extern "C"
+{
+
+const char* gsp_version(void) { return "garden_sceneprep 0.1 sm_100a"; }
+
+int gsp_create(int device, gsp_context** out)
+{
+	if (!out)
+		return GSP_ERR_INVALID;
+	*out = nullptr;
+	int deviceCount = 0;
+	cudaError_t err = cudaGetDeviceCount(&deviceCount);
+	if (err != cudaSuccess || deviceCount == 0)
+	{
+		gCreateError = std::string("no CUDA device available (") + cudaGetErrorString(err) +
+			"); this library has no CPU fallback";
+		return GSP_ERR_CUDA;
+	}
+	if (device < 0 || device >= deviceCount)
+	{
+		gCreateError = "device index out of range";
+		return GSP_ERR_INVALID;
+	}
+	cudaDeviceProp prop;
+	err = cudaGetDeviceProperties(&prop, device);
+	if (err != cudaSuccess || prop.major < 10)
+	{
+		gCreateError = "device is not sm_100 class (kernels are built for sm_100a only)";
+		return GSP_ERR_CUDA;
+	}
+	auto ctx = new (std::nothrow) gsp_context();
+	if (!ctx)
+		return GSP_ERR_NOMEM;
+	Context& c = ctx->c;
+	c.device = device;
+	memset(c.segOf, -1, sizeof(c.segOf));
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking) != cudaSuccess ||
+		cudaMalloc((void**)&c.dCounters, kCtrCount * sizeof(uint32_t)) != cudaSuccess ||
+		cudaMallocHost((void**)&c.hCounters, kCtrCount * sizeof(uint32_t)) != cudaSuccess)
+	{
+		gCreateError = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+		delete ctx;
+		return GSP_ERR_CUDA;
+	}
+	c.stream = c.ownStream;
+	c.dError = c.dCounters + kCtrError;
+	cudaMemset(c.dCounters, 0, kCtrCount * sizeof(uint32_t));
+	memset(c.hCounters, 0, kCtrCount * sizeof(uint32_t));
+	*out = ctx;
+	return GSP_OK;
+}
+
+void gsp_destroy(gsp_context* ctx)
+{
+	if (!ctx)
+		return;
+	Context& c = ctx->c;
+	cudaSetDevice(c.device);
+	cudaStreamSynchronize(c.stream);
+	auto& t = c.tf;
+	cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);
+	cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.entityToSlot);
+	for (auto& p : c.pools)
+	{
+		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus);
+	}
+	cudaFree(c.dSegments); cudaFree(c.keys[0]); cudaFree(c.keys[1]); cudaFree(c.payloads[0]); cudaFree(c.payloads[1]);
+	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortHist); cudaFree(c.sortStatus); cudaFree(c.sortTickets);
+	cudaFree(c.segTileOffset); cudaFree(c.dAosScratch);
+	cudaFreeHost(c.hCounters); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible);
+	cudaStreamDestroy(c.ownStream);
+	delete ctx;
+}
+
+const char* gsp_last_error(const gsp_context* ctx)
+{
+	return ctx ? ctx->c.error.c_str() : gCreateError.c_str();
+}
+
+int gsp_set_stream(gsp_context* ctx, void* cudaStream)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	GSP_CUDA(cudaSetDevice(c.device));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	c.stream = cudaStream ? (cudaStream_t)cudaStream : c.ownStream;
+	return GSP_OK;
+}
+
+//----------------------------------------------------------------------------------------------------------------------
+static int uploadAos(Context& c, const void* aos, size_t bytes)
+{
+	size_t cap = c.dAosScratchCap;
+	uint8_t* ptr = (uint8_t*)c.dAosScratch;
+	GSP_CUDA(ensureDevice(ptr, cap, bytes, false, c.stream));
+	c.dAosScratch = ptr; c.dAosScratchCap = cap;
+	GSP_CUDA(cudaMemcpyAsync(c.dAosScratch, aos, bytes, cudaMemcpyHostToDevice, c.stream));
+	return GSP_OK;
+}
+
+int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint32_t occupancy)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if ((!aos && occupancy) || stride < kTfMinStride || (stride & 3))
+		return fail(c, GSP_ERR_INVALID, "gsp_set_transforms: bad pointer or stride (need >= 80, multiple of 4)");
+	GSP_CUDA(cudaSetDevice(c.device));
+	auto& t = c.tf;
+	if (occupancy > t.capacity || !t.rot)
+	{
+		uint32_t cap = std::max<uint32_t>(occupancy, t.capacity + t.capacity / 2);
+		if (cap == 0) cap = 1;
+		GSP_CUDA(cudaStreamSynchronize(c.stream));
+		cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);
+		cudaFree(t.parentEntity); cudaFree(t.flags);
+		t.rot = nullptr; t.posSx = nullptr; t.sYZ = nullptr; t.parent = nullptr; t.entity = nullptr;
+		t.parentEntity = nullptr; t.flags = nullptr; t.capacity = 0;
+		GSP_CUDA(cudaMalloc((void**)&t.rot, (size_t)cap * sizeof(float4)));
+		GSP_CUDA(cudaMalloc((void**)&t.posSx, (size_t)cap * sizeof(float4)));
+		GSP_CUDA(cudaMalloc((void**)&t.sYZ, (size_t)cap * sizeof(float2)));
+		GSP_CUDA(cudaMalloc((void**)&t.parent, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.entity, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.parentEntity, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.flags, (size_t)cap));
+		t.capacity = cap;
+	}
+	t.occupancy = occupancy;
+	c.linkDirty = true; c.resultsValid = false;
+	if (occupancy == 0)
+		return GSP_OK;
+	int rc = uploadAos(c, aos, (size_t)stride * occupancy);
+	if (rc) return rc;
+	// entity -> slot map sized by the largest live entity id
+	uint32_t* dMax = c.dCounters + kCtrError + 1;
+	GSP_CUDA(cudaMemsetAsync(dMax, 0, sizeof(uint32_t), c.stream));
+	launchMaxEntity(c, c.dAosScratch, stride, occupancy, dMax);
+	uint32_t maxEntity = 0;
+	GSP_CUDA(cudaMemcpyAsync(&maxEntity, dMax, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(ensureDevice32(t.entityToSlot, t.entityCap, (size_t)maxEntity + 1));
+	GSP_CUDA(cudaMemsetAsync(t.entityToSlot, 0, (size_t)t.entityCap * sizeof(uint32_t), c.stream));
+	GSP_CUDA(cudaMemsetAsync(c.dError, 0, sizeof(uint32_t), c.stream));
+	launchStageTransforms(c, c.dAosScratch, stride, 0, occupancy, true);
+	uint32_t error = 0;
+	GSP_CUDA(cudaMemcpyAsync(&error, c.dError, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(cudaGetLastError());
+	if (error)
+		return fail(c, GSP_ERR_HIERARCHY, "gsp_set_transforms: a parent entity has no TransformComponent");
+	return GSP_OK;
+}
+
+int gsp_update_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint32_t first, uint32_t count)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if ((!aos && count) || stride < kTfMinStride || (stride & 3) || (uint64_t)first + count > c.tf.occupancy)
+		return fail(c, GSP_ERR_INVALID, "gsp_update_transforms: bad pointer, stride or range");
+	if (count == 0)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	// `aos` is the pool base (same pointer meaning as gsp_set_transforms); only the dirty range is uploaded.
+	int rc = uploadAos(c, (const uint8_t*)aos + (size_t)first * stride, (size_t)stride * count);
+	if (rc) return rc;
+	launchStageTransforms(c, c.dAosScratch, stride, first, count, false);
+	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the scratch buffer and the caller's memory are free again
+	GSP_CUDA(cudaGetLastError());
+	c.resultsValid = false;
+	return GSP_OK;
+}
+
+int gsp_set_pool_count(gsp_context* ctx, uint32_t poolCount)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (poolCount > (uint32_t)kMaxPools)
+		return fail(c, GSP_ERR_INVALID, "gsp_set_pool_count: too many pools");
+	for (uint32_t i = poolCount; i < (uint32_t)kMaxPools; i++)
+		c.pools[i].set = false;
+	c.poolCount = poolCount;
+	c.layoutDirty = true; c.resultsValid = false;
+	return GSP_OK;
+}
+
+int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint32_t drawReady, const void* aos,
+	uint32_t stride, uint32_t occupancy, uint32_t count, const uint8_t* readyCounts)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (pool >= (uint32_t)kMaxPools || renderType > GSP_RT_UI || (!aos && occupancy) || stride < kMcMinStride || (stride & 3) ||
+		occupancy > 0x0FFFFFFFu)
+		return fail(c, GSP_ERR_INVALID, "gsp_set_mesh_pool: bad pool index, render type, pointer, stride or occupancy");
+	GSP_CUDA(cudaSetDevice(c.device));
+	auto& p = c.pools[pool];
+	if (occupancy > p.capacity || !p.aabbA)
+	{
+		uint32_t cap = std::max<uint32_t>(occupancy, p.capacity + p.capacity / 2);
+		if (cap == 0) cap = 1;
+		GSP_CUDA(cudaStreamSynchronize(c.stream));
+		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus);
+		p.aabbA = nullptr; p.aabbB = nullptr; p.entity = nullptr; p.tslot = nullptr; p.flags = nullptr; p.ready = nullptr;
+		p.world = nullptr; p.visible = nullptr; p.cullStatus = nullptr; p.capacity = 0;
+		GSP_CUDA(cudaMalloc((void**)&p.aabbA, (size_t)cap * sizeof(float4)));
+		GSP_CUDA(cudaMalloc((void**)&p.aabbB, (size_t)cap * sizeof(float2)));
+		GSP_CUDA(cudaMalloc((void**)&p.entity, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&p.tslot, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&p.flags, (size_t)cap));
+		GSP_CUDA(cudaMalloc((void**)&p.ready, (size_t)cap));
+		GSP_CUDA(cudaMalloc((void**)&p.world, (size_t)cap * 3 * sizeof(float4)));
+		GSP_CUDA(cudaMalloc((void**)&p.visible, (size_t)cap));
+		p.cullTilesCap = (cap + kCullTile - 1) / kCullTile;
+		GSP_CUDA(cudaMalloc((void**)&p.cullStatus, (size_t)p.cullTilesCap * kMaxViews * sizeof(uint32_t)));
+		p.capacity = cap;
+	}
+	if (p.occupancy != occupancy || p.renderType != renderType || p.stride != stride || !p.set ||
+		(p.count == 0) != (count == 0) || p.drawReady != drawReady)
+		c.layoutDirty = true;
+	p.occupancy = occupancy; p.count = count; p.stride = stride; p.renderType = renderType; p.drawReady = drawReady;
+	p.hasReady = readyCounts != nullptr; p.set = true; p.visibleValid = false;
+	if (pool >= c.poolCount) { c.poolCount = pool + 1; c.layoutDirty = true; }
+	c.linkDirty = true; c.resultsValid = false;
+	if (occupancy == 0)
+		return GSP_OK;
+	int rc = uploadAos(c, aos, (size_t)stride * occupancy);
+	if (rc) return rc;
+	launchStagePool(c, pool, c.dAosScratch, stride, occupancy);
+	if (readyCounts)
+		GSP_CUDA(cudaMemcpyAsync(p.ready, readyCounts, occupancy, cudaMemcpyHostToDevice, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(cudaGetLastError());
+	return GSP_OK;
+}
+
+int gsp_set_views(gsp_context* ctx, uint32_t viewCount, const gsp_view* views, const float cameraPosition[3])
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (viewCount == 0 || viewCount > (uint32_t)kMaxViews || !views || !cameraPosition)
+		return fail(c, GSP_ERR_INVALID, "gsp_set_views: bad view count or null pointer");
+	for (uint32_t v = 0; v < viewCount; v++)
+	{
+		if (views[v].planeCount == 0 || views[v].planeCount > 6 || views[v].uiPlaneCount > 6)
+			return fail(c, GSP_ERR_INVALID, "gsp_set_views: plane count must be 1..6 (Frustum::setPlaneCount, frustum.hpp:71-76)");
+	}
+	bool shapeChanged = c.views.size() != viewCount;
+	for (uint32_t v = 0; v < viewCount && !shapeChanged; v++)
+		shapeChanged = (c.views[v].shadowPass < 0) != (views[v].shadowPass < 0) ||
+			(c.views[v].uiPlaneCount == 0) != (views[v].uiPlaneCount == 0);
+	c.views.assign(views, views + viewCount);
+	memcpy(c.cameraPos, cameraPosition, sizeof(c.cameraPos));
+	c.viewsSet = true; c.resultsValid = false;
+	if (shapeChanged)
+		c.layoutDirty = true;
+	return GSP_OK;
+}
+
+//----------------------------------------------------------------------------------------------------------------------
+// Buffer bookkeeping of prepareMeshes (mesh.cpp:341-375,408-423,476-483) for every view, plus arena allocation.
+static int rebuildLayout(Context& c)
+{
+	c.segments.clear();
+	memset(c.segOf, -1, sizeof(c.segOf));
+	memset(c.prevPool, -1, sizeof(c.prevPool));
+	memset(c.participates, 0, sizeof(c.participates));
+	memset(c.bufferIndexOf, 0, sizeof(c.bufferIndexOf));
+	uint64_t offset = 0;
+	for (uint32_t v = 0; v < (uint32_t)c.views.size(); v++)
+	{
+		const bool mainView = c.views[v].shadowPass < 0;
+		uint32_t unsortedIndex = 0, sortedIndex = 0;
+		int transSeg = -1, uiSeg = -1, lastTrans = -1, lastUi = -1;
+		for (uint32_t p = 0; p < c.poolCount; p++)
+		{
+			auto& pool = c.pools[p];
+			if (!pool.set)
+			{
+				c.error = "pool " + std::to_string(p) + " was declared by gsp_set_pool_count but never set";
+				return GSP_ERR_STATE;
+			}
+			const bool active = pool.count > 0 && pool.drawReady && pool.occupancy > 0; // mesh.cpp:426,482
+			if (pool.renderType == GSP_RT_TRANSLUCENT || pool.renderType == GSP_RT_UI)
+			{
+				const bool isUI = pool.renderType == GSP_RT_UI;
+				if (isUI && !mainView) // mesh.cpp:365,416-417
+					continue;
+				if (isUI && active && c.views[v].uiPlaneCount == 0)
+				{
+					c.error = "a UI mesh pool needs uiPlanes in main views (the reference dereferences uiFrustum, mesh.cpp:440)";
+					return GSP_ERR_INVALID;
+				}
+				c.bufferIndexOf[v][p] = sortedIndex++;
+				int& segIndex = isUI ? uiSeg : transSeg;
+				int& last = isUI ? lastUi : lastTrans;
+				if (segIndex < 0)
+				{
+					Segment s;
+					s.view = v; s.pool = p; s.kind = isUI ? 2 : 1; s.descending = 1; s.key2D = isUI ? 1 : 0;
+					s.sorted = 1; s.capacity = 0; s.lastPool = kNone;
+					segIndex = (int)c.segments.size();
+					c.segments.push_back(s);
+				}
+				c.segOf[v][p] = segIndex;
+				if (active)
+				{
+					c.participates[v][p] = true;
+					c.prevPool[v][p] = last;
+					last = (int)p;
+					c.segments[segIndex].capacity += pool.occupancy;
+					c.segments[segIndex].lastPool = p;
+				}
+			}
+			else
+			{
+				Segment s;
+				s.view = v; s.pool = p; s.kind = 0; s.listIndex = (int)unsortedIndex;
+				s.sorted = pool.renderType == GSP_RT_OIT ? 0 : 1; // mesh.cpp:273-277
+				s.capacity = active ? pool.occupancy : 0;
+				s.lastPool = active ? p : kNone;
+				c.bufferIndexOf[v][p] = unsortedIndex++;
+				c.segOf[v][p] = (int)c.segments.size();
+				c.participates[v][p] = active;
+				c.segments.push_back(s);
+			}
+		}
+		c.unsortedCount[v] = unsortedIndex; c.sortedCount[v] = sortedIndex;
+	}
+	// arena offsets (16-element aligned so that 64-byte records and vector loads stay aligned)
+	std::vector<SegmentDev> dev(c.segments.size());
+	std::vector<uint32_t> tileOffsets(c.segments.size() + 1, 0);
+	uint32_t tiles = 0;
+	for (size_t i = 0; i < c.segments.size(); i++)
+	{
+		auto& s = c.segments[i];
+		s.offset = (uint32_t)offset;
+		offset += (s.capacity + 15u) & ~15u;
+		if (offset > 0xFFFFFFF0ull)
+		{
+			c.error = "draw-list arena exceeds 2^32 elements";
+			return GSP_ERR_NOMEM;
+		}
+		dev[i].offset = s.offset; dev[i].capacity = s.capacity;
+		dev[i].countIndex = s.lastPool == kNone ? kNone : ctrPoolEnd(s.lastPool, s.view);
+		dev[i].sorted = s.sorted; dev[i].descending = s.descending; dev[i].key2D = s.key2D; dev[i].pad0 = dev[i].pad1 = 0;
+		tileOffsets[i] = tiles;
+		tiles += (s.capacity + kSortTile - 1) / kSortTile;
+	}
+	tileOffsets[c.segments.size()] = tiles;
+	c.arenaElems = (uint32_t)offset;
+	c.sortTilesTotal = tiles;
+
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	const size_t nseg = c.segments.size();
+	if (nseg > c.dSegmentsCap || !c.dSegments)
+	{
+		cudaFree(c.dSegments); cudaFree(c.sortHist); cudaFree(c.sortTickets); cudaFree(c.segTileOffset);
+		c.dSegments = nullptr; c.sortHist = nullptr; c.sortTickets = nullptr; c.segTileOffset = nullptr;
+		size_t cap = std::max<size_t>(nseg, 8);
+		GSP_CUDA(cudaMalloc((void**)&c.dSegments, cap * sizeof(SegmentDev)));
+		GSP_CUDA(cudaMalloc((void**)&c.sortHist, cap * 4 * 256 * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&c.sortTickets, cap * 4 * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&c.segTileOffset, (cap + 1) * sizeof(uint32_t)));
+		c.dSegmentsCap = (uint32_t)cap;
+	}
+	if (nseg)
+	{
+		GSP_CUDA(cudaMemcpy(c.dSegments, dev.data(), nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice));
+		GSP_CUDA(cudaMemcpy(c.segTileOffset, tileOffsets.data(), (nseg + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
+	if (c.arenaElems > c.arenaCap || !c.keys[0])
+	{
+		for (int i = 0; i < 2; i++)
+		{
+			cudaFree(c.keys[i]); cudaFree(c.payloads[i]);
+			c.keys[i] = nullptr; c.payloads[i] = nullptr;
+		}
+		cudaFree(c.records); c.records = nullptr;
+		size_t cap = std::max<size_t>(c.arenaElems, 16);
+		for (int i = 0; i < 2; i++)
+		{
+			GSP_CUDA(cudaMalloc((void**)&c.keys[i], cap * sizeof(uint32_t)));
+			GSP_CUDA(cudaMalloc((void**)&c.payloads[i], cap * sizeof(uint32_t)));
+		}
+		GSP_CUDA(cudaMalloc((void**)&c.records, cap * sizeof(gsp_record)));
+		c.arenaCap = (uint32_t)cap;
+	}
+	const size_t statusNeed = (size_t)tiles * 4 * 256;
+	if (statusNeed > c.sortStatusCap || !c.sortStatus)
+	{
+		cudaFree(c.sortStatus); c.sortStatus = nullptr;
+		size_t cap = std::max<size_t>(statusNeed, 1024);
+		GSP_CUDA(cudaMalloc((void**)&c.sortStatus, cap * sizeof(uint32_t)));
+		c.sortStatusCap = cap;
+	}
+	c.segDownloaded.assign(nseg, 0);
+	c.layoutDirty = false;
+	return GSP_OK;
+}
+
+int gsp_run_async(gsp_context* ctx)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (!c.viewsSet)
+		return fail(c, GSP_ERR_STATE, "gsp_run: gsp_set_views has not been called");
+	GSP_CUDA(cudaSetDevice(c.device));
+	if (c.layoutDirty)
+	{
+		int rc = rebuildLayout(c);
+		if (rc) return rc;
+	}
+	uint32_t launches = 0;
+	if (c.linkDirty)
+	{
+		launches += launchLink(c);
+		c.linkDirty = false;
+	}
+	GSP_CUDA(cudaMemsetAsync(c.dCounters, 0, kCtrCount * sizeof(uint32_t), c.stream));
+	for (uint32_t p = 0; p < c.poolCount; p++)
+		launches += launchCull(c, p);
+	launches += launchSort(c);
+	launches += launchEmit(c);
+	GSP_CUDA(cudaMemcpyAsync(c.hCounters, c.dCounters, kCtrCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaGetLastError());
+	c.launchCount = launches;
+	std::fill(c.segDownloaded.begin(), c.segDownloaded.end(), 0);
+	c.resultsValid = false;
+	return GSP_OK;
+}
+
+int gsp_sync(gsp_context* ctx)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	GSP_CUDA(cudaSetDevice(c.device));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(cudaGetLastError());
+	if (c.hCounters[kCtrError])
+		return fail(c, GSP_ERR_HIERARCHY, "gsp_run: transform hierarchy is cyclic or deeper than 4096");
+	c.resultsValid = true;
+	return GSP_OK;
+}
+
+int gsp_run(gsp_context* ctx)
+{
+	int rc = gsp_run_async(ctx);
+	return rc ? rc : gsp_sync(ctx);
+}
+
+//----------------------------------------------------------------------------------------------------------------------
+static int findSegment(Context& c, uint32_t view, int kind, uint32_t listIndex)
+{
+	for (size_t i = 0; i < c.segments.size(); i++)
+	{
+		auto& s = c.segments[i];
+		if (s.view == view && s.kind == kind && (kind != 0 || (uint32_t)s.listIndex == listIndex))
+			return (int)i;
+	}
+	return -1;
+}
+static uint32_t segmentCount(Context& c, const Segment& s)
+{
+	return s.lastPool == kNone ? 0 : c.hCounters[ctrPoolEnd(s.lastPool, s.view)];
+}
+static uint32_t poolDrawCount(Context& c, uint32_t view, uint32_t pool)
+{
+	if (!c.participates[view][pool])
+		return 0;
+	uint32_t end = c.hCounters[ctrPoolEnd(pool, view)];
+	int prev = c.prevPool[view][pool];
+	return end - (prev >= 0 ? c.hCounters[ctrPoolEnd((uint32_t)prev, view)] : 0);
+}
+static uint32_t poolInstanceCount(Context& c, uint32_t view, uint32_t pool)
+{
+	if (!c.participates[view][pool])
+		return 0;
+	return c.pools[pool].hasReady ? c.hCounters[ctrPoolInst(pool, view)] : poolDrawCount(c, view, pool);
+}
+
+static int checkResults(Context& c, uint32_t view)
+{
+	if (!c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	if (view >= c.views.size())
+		return fail(c, GSP_ERR_INVALID, "view index out of range");
+	return GSP_OK;
+}
+
+static int downloadSegment(Context& c, int seg, const gsp_record** records)
+{
+	const Segment& s = c.segments[seg];
+	if (c.hRecordsCap < c.arenaElems || !c.hRecords)
+	{
+		cudaFreeHost(c.hRecords); c.hRecords = nullptr; c.hRecordsCap = 0;
+		GSP_CUDA(cudaMallocHost((void**)&c.hRecords, std::max<size_t>(c.arenaElems, 16) * sizeof(gsp_record)));
+		c.hRecordsCap = std::max<size_t>(c.arenaElems, 16);
+		std::fill(c.segDownloaded.begin(), c.segDownloaded.end(), 0);
+	}
+	uint32_t count = segmentCount(c, s);
+	if (!c.segDownloaded[seg] && count)
+	{
+		GSP_CUDA(cudaMemcpyAsync(c.hRecords + s.offset, c.records + s.offset, (size_t)count * sizeof(gsp_record),
+			cudaMemcpyDeviceToHost, c.stream));
+		GSP_CUDA(cudaStreamSynchronize(c.stream));
+		c.segDownloaded[seg] = 1;
+	}
+	*records = c.hRecords + s.offset;
+	return GSP_OK;
+}
+
+uint32_t gsp_unsorted_buffer_count(const gsp_context* ctx, uint32_t view)
+{
+	return (ctx && view < ctx->c.views.size() && !ctx->c.layoutDirty) ? ctx->c.unsortedCount[view] : 0;
+}
+uint32_t gsp_sorted_buffer_count(const gsp_context* ctx, uint32_t view)
+{
+	return (ctx && view < ctx->c.views.size() && !ctx->c.layoutDirty) ? ctx->c.sortedCount[view] : 0;
+}
+
+static int getUnsorted(gsp_context* ctx, uint32_t view, uint32_t buffer, const gsp_record** records,
+	uint32_t* drawCount, uint32_t* instanceCount, bool device)
+{
+	if (!ctx || !records || !drawCount || !instanceCount)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	int rc = checkResults(c, view);
+	if (rc) return rc;
+	int seg = findSegment(c, view, 0, buffer);
+	if (seg < 0)
+		return fail(c, GSP_ERR_INVALID, "unsorted buffer index out of range");
+	const Segment& s = c.segments[seg];
+	*drawCount = segmentCount(c, s);
+	*instanceCount = poolInstanceCount(c, view, s.pool);
+	if (device)
+	{
+		*records = c.records + s.offset;
+		return GSP_OK;
+	}
+	GSP_CUDA(cudaSetDevice(c.device));
+	return downloadSegment(c, seg, records);
+}
+
+int gsp_get_unsorted(gsp_context* ctx, uint32_t view, uint32_t buffer, const gsp_record** records,
+	uint32_t* drawCount, uint32_t* instanceCount)
+{
+	return getUnsorted(ctx, view, buffer, records, drawCount, instanceCount, false);
+}
+int gsp_get_unsorted_device(gsp_context* ctx, uint32_t view, uint32_t buffer, const gsp_record** records,
+	uint32_t* drawCount, uint32_t* instanceCount)
+{
+	return getUnsorted(ctx, view, buffer, records, drawCount, instanceCount, true);
+}
+
+int gsp_get_sorted_counts(gsp_context* ctx, uint32_t view, uint32_t buffer, uint32_t* drawCount, uint32_t* instanceCount)
+{
+	if (!ctx || !drawCount || !instanceCount)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	int rc = checkResults(c, view);
+	if (rc) return rc;
+	for (uint32_t p = 0; p < c.poolCount; p++)
+	{
+		auto rt = c.pools[p].renderType;
+		if ((rt == GSP_RT_TRANSLUCENT || rt == GSP_RT_UI) && c.segOf[view][p] >= 0 && c.bufferIndexOf[view][p] == buffer)
+		{
+			*drawCount = poolDrawCount(c, view, p);
+			*instanceCount = poolInstanceCount(c, view, p);
+			return GSP_OK;
+		}
+	}
+	return fail(c, GSP_ERR_INVALID, "sorted buffer index out of range");
+}
+
+static int getSorted(gsp_context* ctx, uint32_t view, int which, const gsp_record** records, uint32_t* drawCount, bool device)
+{
+	if (!ctx || !records || !drawCount || (which != 0 && which != 1))
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	int rc = checkResults(c, view);
+	if (rc) return rc;
+	int seg = findSegment(c, view, which == 0 ? 1 : 2, 0);
+	if (seg < 0) // no translucent / UI system in this view: empty list (transDrawIndex == 0)
+	{
+		*records = nullptr; *drawCount = 0;
+		return GSP_OK;
+	}
+	const Segment& s = c.segments[seg];
+	*drawCount = segmentCount(c, s);
+	if (device)
+	{
+		*records = c.records + s.offset;
+		return GSP_OK;
+	}
+	GSP_CUDA(cudaSetDevice(c.device));
+	return downloadSegment(c, seg, records);
+}
+int gsp_get_sorted(gsp_context* ctx, uint32_t view, int which, const gsp_record** records, uint32_t* drawCount)
+{
+	return getSorted(ctx, view, which, records, drawCount, false);
+}
+int gsp_get_sorted_device(gsp_context* ctx, uint32_t view, int which, const gsp_record** records, uint32_t* drawCount)
+{
+	return getSorted(ctx, view, which, records, drawCount, true);
+}
+
+int gsp_get_sorted_run_device(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer,
+	const uint32_t** keys, const uint32_t** payloads, uint32_t* count)
+{
+	if (!ctx || !keys || !payloads || !count || listKind < 0 || listKind > 2)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	int rc = checkResults(c, view);
+	if (rc) return rc;
+	int seg = findSegment(c, view, listKind, buffer);
+	if (seg < 0)
+	{
+		*keys = nullptr; *payloads = nullptr; *count = 0;
+		return GSP_OK;
+	}
+	const Segment& s = c.segments[seg];
+	*keys = c.keys[0] + s.offset; *payloads = c.payloads[0] + s.offset; *count = segmentCount(c, s);
+	return GSP_OK;
+}
+
+int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (pool >= c.poolCount || !aos || stride < kMcMinStride)
+		return fail(c, GSP_ERR_INVALID, "gsp_writeback_visible: bad pool, pointer or stride");
+	if (!c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	auto& p = c.pools[pool];
+	if (!p.visibleValid || p.occupancy == 0)
+		return GSP_OK; // the reference does not touch isVisible of pools the main view skipped (mesh.cpp:426,482)
+	GSP_CUDA(cudaSetDevice(c.device));
+	if (c.hVisibleCap < p.occupancy || !c.hVisible)
+	{
+		cudaFreeHost(c.hVisible); c.hVisible = nullptr; c.hVisibleCap = 0;
+		GSP_CUDA(cudaMallocHost((void**)&c.hVisible, p.occupancy));
+		c.hVisibleCap = p.occupancy;
+	}
+	GSP_CUDA(cudaMemcpyAsync(c.hVisible, p.visible, p.occupancy, cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	uint8_t* dst = (uint8_t*)aos + kMcVisible;
+	for (uint32_t i = 0; i < p.occupancy; i++)
+		dst[(size_t)i * stride] = c.hVisible[i];
+	return GSP_OK;
+}
+
+int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (pool >= c.poolCount || !out)
+		return fail(c, GSP_ERR_INVALID, "gsp_download_models: bad pool or pointer");
+	if (!c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	auto& p = c.pools[pool];
+	if (p.occupancy == 0)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	GSP_CUDA(cudaMemcpyAsync(out, p.world, (size_t)p.occupancy * 12 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	return GSP_OK;
+}
+
+uint32_t gsp_last_launch_count(const gsp_context* ctx) { return ctx ? ctx->c.launchCount : 0; }
+
+uint64_t gsp_last_visible_total(gsp_context* ctx)
+{
+	if (!ctx || !ctx->c.resultsValid)
+		return 0;
+	Context& c = ctx->c;
+	uint64_t total = 0;
+	for (auto& s : c.segments)
+		total += segmentCount(c, s);
+	return total;
+}
+
+} // extern "C"

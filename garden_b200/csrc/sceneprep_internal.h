@@ -1,0 +1,174 @@
+// Internal declarations shared by the translation units of libgarden_sceneprep.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/garden_sceneprep.h"
+
+namespace gsp
+{
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kMaxPools = GSP_MAX_POOLS;
+constexpr int kMaxViews = GSP_MAX_VIEWS;
+constexpr uint32_t kMaxChainDepth = 4096; // guard against cyclic hierarchies
+
+// ---- AoS field offsets of the reference's components (verified with offsetof in oracle/ref_harness) ----
+// TransformComponent, include/garden/system/transform.hpp:31-60
+constexpr uint32_t kTfEntity = 0, kTfParent = 4, kTfPos = 16, kTfScale = 32, kTfRot = 48, kTfSelfActive = 72,
+	kTfAncestorsActive = 73, kTfWithAncestors = 74, kTfMinStride = 80;
+// MeshRenderComponent, include/garden/system/render/mesh.hpp:45-55
+constexpr uint32_t kMcEntity = 0, kMcEnabled = 14, kMcVisible = 15, kMcAabbMin = 16, kMcAabbMax = 32, kMcMinStride = 48;
+
+// transform flags (SoA)
+constexpr uint8_t kTfLive = 1, kTfActive = 2, kTfAncestors = 4;
+// mesh flags (SoA): static filter of mesh.cpp:140-147 (entity != 0 && isEnabled && !degenerate AABB)
+constexpr uint8_t kMfCandidate = 1;
+
+// ---- device SoA mirrors -------------------------------------------------------------------------------------------
+struct TransformsDev
+{
+	uint32_t occupancy = 0, capacity = 0;
+	float4* rot = nullptr;    // quaternion xyzw
+	float4* posSx = nullptr;  // position xyz, scale x
+	float2* sYZ = nullptr;    // scale y, z
+	uint32_t* parent = nullptr; // parent transform slot or kNone
+	uint32_t* entity = nullptr; // owner entity id (0 = free slot)
+	uint32_t* parentEntity = nullptr;
+	uint8_t* flags = nullptr;
+	uint32_t* entityToSlot = nullptr; // entity id -> slot + 1
+	uint32_t entityCap = 0;
+};
+
+struct PoolDev
+{
+	uint32_t occupancy = 0, capacity = 0, count = 0, stride = 0, renderType = 0, drawReady = 0;
+	bool hasReady = false, set = false;
+	float4* aabbA = nullptr;  // min xyz, max x
+	float2* aabbB = nullptr;  // max y, z
+	uint32_t* entity = nullptr;
+	uint32_t* tslot = nullptr; // transform slot or kNone (resolved by the link kernel)
+	uint8_t* flags = nullptr;
+	uint8_t* ready = nullptr;
+	float4* world = nullptr;   // 3 x float4 per slot = float4x3 world matrix (c0..c3 lanes xyz), written for visible slots
+	uint8_t* visible = nullptr; // isVisible of the last main view, per slot
+	uint32_t* cullStatus = nullptr; // [tiles][kMaxViews] decoupled look-back words
+	uint32_t cullTiles = 0, cullTilesCap = 0;
+	bool visibleValid = false;
+};
+
+// Per-view constants handed to the cull kernel by value (__grid_constant__).
+struct ViewConst
+{
+	float planes[6][4];
+	float cameraOffset[4];
+	uint32_t planeCount;
+	uint32_t enabled;   // pool participates in this view
+	uint32_t writeVisible; // this is the last main view: store isVisible
+	uint32_t pad;
+};
+struct CullParams
+{
+	ViewConst views[kMaxViews];
+	float cam[4];          // camera position subtracted from c3 (zero for UI pools, mesh.cpp:441)
+	uint32_t viewCount;
+	uint32_t occupancy;
+	uint32_t poolIndex;    // goes into payload bits 28..31
+	uint32_t key2D;        // UI: key = model.c3.z + 1.0f (mesh.cpp:250)
+	uint32_t descending;   // translucent / UI lists sort descending (mesh.hpp:204)
+	uint32_t hasReady;
+	uint32_t anyWriteVisible;
+	uint32_t pad;
+};
+
+// A segment = one output list of one view: (view, canonical pool). Unsorted buffers own a segment each;
+// all translucent pools of a view share one, all UI pools share one.
+struct Segment
+{
+	uint32_t offset = 0;    // element offset into the key/payload/record arenas
+	uint32_t capacity = 0;
+	uint32_t view = 0, pool = 0; // canonical (first) pool
+	uint32_t lastPool = 0;  // last pool appending to it (its poolEnd is the final count)
+	uint32_t sorted = 1;    // 0 for OIT buffers (mesh.cpp:273-277)
+	uint32_t descending = 0, key2D = 0, stride = 0;
+	int kind = 0;           // 0 unsorted, 1 translucent, 2 ui
+	int listIndex = 0;      // unsorted buffer index within the view
+};
+
+struct SegmentDev // device-visible part
+{
+	uint32_t offset, capacity, countIndex /* index into poolEnd of lastPool,view */, sorted;
+	uint32_t descending, key2D, pad0, pad1;
+};
+
+struct Context
+{
+	int device = 0;
+	cudaStream_t ownStream = nullptr, stream = nullptr;
+	std::string error;
+
+	TransformsDev tf;
+	PoolDev pools[kMaxPools];
+	uint32_t poolCount = 0;
+
+	std::vector<gsp_view> views;
+	float cameraPos[3] = {0, 0, 0};
+	bool viewsSet = false, linkDirty = true, layoutDirty = true, resultsValid = false;
+
+	// segments
+	std::vector<Segment> segments;
+	int segOf[kMaxViews][kMaxPools]; // view,pool -> segment index or -1
+	int prevPool[kMaxViews][kMaxPools]; // previous pool appending to the same list (-1 = first)
+	bool participates[kMaxViews][kMaxPools]; // pool is processed in this view (count > 0 && isDrawReady, mesh.cpp:426,482)
+	uint32_t bufferIndexOf[kMaxViews][kMaxPools]; // unsorted / sorted buffer index of the pool in the view
+	uint32_t unsortedCount[kMaxViews], sortedCount[kMaxViews];
+	SegmentDev* dSegments = nullptr; uint32_t dSegmentsCap = 0;
+	uint32_t arenaElems = 0, arenaCap = 0;
+	uint32_t* keys[2] = {nullptr, nullptr};
+	uint32_t* payloads[2] = {nullptr, nullptr};
+	gsp_record* records = nullptr; size_t recordsCap = 0;
+
+	// per-frame device counters: [0, P*V) poolEnd, [P*V, 2*P*V) poolInst, then tickets, then error flag
+	uint32_t* dCounters = nullptr;
+	uint32_t* hCounters = nullptr; // pinned
+	// sort scratch
+	uint32_t* sortHist = nullptr;   // [segments][4][256]
+	uint32_t* sortStatus = nullptr; // [segments][tiles][256] per pass (re-zeroed by the prepare kernel)
+	uint32_t* sortTickets = nullptr; // [segments][4]
+	uint32_t* segTileOffset = nullptr; // device: prefix of tiles per segment (capacity based)
+	uint32_t sortTilesTotal = 0, sortScratchSegs = 0;
+	size_t sortStatusCap = 0;
+
+	// host staging
+	void* dAosScratch = nullptr; size_t dAosScratchCap = 0;
+	gsp_record* hRecords = nullptr; size_t hRecordsCap = 0; // pinned download area (arena-shaped)
+	std::vector<uint8_t> segDownloaded;
+	uint8_t* hVisible = nullptr; size_t hVisibleCap = 0;
+	uint32_t launchCount = 0;
+	uint32_t* dError = nullptr;
+};
+
+// counters layout helpers
+__host__ __device__ inline uint32_t ctrPoolEnd(uint32_t pool, uint32_t view) { return pool * kMaxViews + view; }
+__host__ __device__ inline uint32_t ctrPoolInst(uint32_t pool, uint32_t view) { return kMaxPools * kMaxViews + pool * kMaxViews + view; }
+constexpr uint32_t kCtrCullTicket = 2 * kMaxPools * kMaxViews; // + pool
+constexpr uint32_t kCtrError = kCtrCullTicket + kMaxPools;
+constexpr uint32_t kCtrCount = kCtrError + 8;
+
+constexpr uint32_t kCullTile = 256;       // slots per cull tile (= threads per block)
+constexpr uint32_t kSortItems = 16;       // keys per thread in the radix sort
+constexpr uint32_t kSortThreads = 256;
+constexpr uint32_t kSortTile = kSortItems * kSortThreads;
+
+// ---- kernel launchers (each returns the number of kernels it launched, or throws nothing; errors via cudaGetLastError) ----
+uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full);
+uint32_t launchMaxEntity(Context& c, const void* dAos, uint32_t stride, uint32_t count, uint32_t* dMax);
+uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy);
+uint32_t launchLink(Context& c);
+uint32_t launchCull(Context& c, uint32_t pool);
+uint32_t launchSort(Context& c);
+uint32_t launchEmit(Context& c);
+
+} // namespace gsp

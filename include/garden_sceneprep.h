@@ -1,0 +1,147 @@
+/* garden_sceneprep.h — C ABI of the B200 scene-preparation library (libgarden_sceneprep.so).
+ *
+ * Drop-in boundary for ONE path of cfnptr/garden: the body of
+ *     MeshRenderSystem::prepareMeshes(const Frustum&, const Frustum*, f32x4 cameraOffset, int8 shadowPass)
+ *     (reference: source/system/render/mesh.cpp:331-553, callers mesh.cpp:815,869,902)
+ * and everything it calls per component (TransformComponent::calcModel, isBehindFrustum, the distance key, the thread-local
+ * compaction and the std::sort of the draw lists), hoisted so that all views of a frame run in one call.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary; no exceptions (status codes + gsp_last_error).
+ * One caller thread per context; calls are synchronous from the caller's view unless stated otherwise.
+ * There is NO CPU fallback: every entry point that computes fails with GSP_ERR_CUDA if no sm_100 device is usable.
+ *
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef GARDEN_SCENEPREP_H
+#define GARDEN_SCENEPREP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSP_MAX_POOLS 8   /* mesh systems per context (IMeshRenderSystem group members) */
+#define GSP_MAX_VIEWS 16  /* views per frame (main camera + shadow passes + probes) */
+
+typedef enum gsp_status
+{
+	GSP_OK = 0,
+	GSP_ERR_INVALID = 1,  /* bad argument */
+	GSP_ERR_CUDA = 2,     /* CUDA runtime / device error (see gsp_last_error) */
+	GSP_ERR_NOMEM = 3,    /* host or device allocation failed */
+	GSP_ERR_STATE = 4,    /* call sequence error (e.g. gsp_run before gsp_set_views) */
+	GSP_ERR_HIERARCHY = 5 /* a parent entity has no TransformComponent or the chain is cyclic
+	                         (the reference throws EcsmError from Manager::get, ecsm.hpp:863-873) */
+} gsp_status;
+
+/* MeshRenderType — include/garden/system/render/mesh.hpp:30-40 (same numeric values). */
+typedef enum gsp_render_type
+{
+	GSP_RT_COLOR = 0, GSP_RT_OPAQUE = 1, GSP_RT_TRANSLUCENT = 2, GSP_RT_OIT = 3,
+	GSP_RT_REFRACTED = 4, GSP_RT_TRANS_DEPTH = 5, GSP_RT_UI = 6
+} gsp_render_type;
+
+/* Draw-list record: byte-identical to MeshRenderSystem::UnsortedMesh / SortedMesh
+ * (include/garden/system/render/mesh.hpp:191-205): 64 bytes, bakedModel = float4x3 column-major (c0..c3, lanes xyz).
+ * bufferIndex is only meaningful in the translucent / UI lists (SortedMesh); it is 0 in unsorted buffers. */
+typedef struct gsp_record
+{
+	uint64_t componentOffset; /* slot * componentStride, mesh.cpp:170,248 */
+	float bakedModel[12];
+	float distanceSq;
+	uint32_t bufferIndex;
+} gsp_record;
+
+/* One view = one reference prepareMeshes() call. Planes are what math::Frustum holds after Frustum(viewProj)
+ * (libraries/math/include/math/frustum.hpp:51-61): normal xyz + distance, unnormalised, computed by the caller. */
+typedef struct gsp_view
+{
+	float planes[6][4];
+	uint32_t planeCount;     /* Frustum::getPlaneCount(), 1..6 */
+	float uiPlanes[6][4];    /* the `uiFrustum` argument; used for UI mesh systems in the main view only */
+	uint32_t uiPlaneCount;   /* 0 = nullptr */
+	float cameraOffset[4];   /* the `cameraOffset` argument (zero for the main view, csm.cpp:304 for a cascade) */
+	int32_t shadowPass;      /* the `shadowPass` argument: < 0 main view (writes isVisible), >= 0 shadow pass */
+} gsp_view;
+
+typedef struct gsp_context gsp_context;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`. Replaces MeshRenderSystem's constructor-time state (mesh.cpp:31-36).
+ * Buffers of MeshRenderType::OIT systems are filled but left unsorted, as in sortMeshes (mesh.cpp:273-277). */
+int gsp_create(int device, gsp_context** out);
+void gsp_destroy(gsp_context* ctx);
+/* Last error message of this context (never NULL). With ctx == NULL: the message of the last failed gsp_create. */
+const char* gsp_last_error(const gsp_context* ctx);
+/* All work of this context is enqueued on `cudaStream` (a cudaStream_t; NULL = the context's own stream). */
+int gsp_set_stream(gsp_context* ctx, void* cudaStream);
+
+/* ---- component staging (AoS ECS pools -> SoA in HBM) ------------------------------------------------------------ */
+/* Replaces the per-entity Manager::tryGet<TransformComponent>() + field reads (mesh.cpp:149; ecsm.hpp:898-905).
+ * `aos` = LinearPool<TransformComponent>::getData() (linear-pool.hpp:717), `stride` = sizeof(TransformComponent) = 80
+ * (include/garden/system/transform.hpp:31-60), `occupancy` = getOccupancy() (linear-pool.hpp:734).
+ * The memory is copied during the call (pageable or pinned host memory both work). */
+int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint32_t occupancy);
+/* Dirty range: re-stages position/rotation/scale/active flags of slots [first, first+count); `aos` is the pool base
+ * (same pointer meaning as gsp_set_transforms), only the bytes of the range are read and uploaded. The hierarchy
+ * (entity and parent fields) must be unchanged since the last gsp_set_transforms. The ECS has no dirty tracking
+ * (transform.hpp:74-104 are plain stores), so the range comes from the caller. */
+int gsp_update_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint32_t first, uint32_t count);
+/* Declares how many mesh systems the frame has (meshSystems.size() after prepareSystems, mesh.cpp:69-108). */
+int gsp_set_pool_count(gsp_context* ctx, uint32_t poolCount);
+/* Replaces reading IMeshRenderSystem::{getMeshRenderType,getMeshComponentPool,getMeshComponentSize,isDrawReady}
+ * (mesh.hpp:60-147) inside prepareMeshes. `pool` is the index in meshSystems order. `count` = getCount()
+ * (linear-pool.hpp:729). `readyCounts` (nullable, `occupancy` bytes) carries the result of a system's
+ * getReadyMeshesAsync override beyond the frustum test (e.g. sprite.cpp:90-97): ready instance count per slot. */
+int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint32_t drawReady, const void* aos,
+	uint32_t stride, uint32_t occupancy, uint32_t count, const uint8_t* readyCounts);
+
+/* ---- per frame ---------------------------------------------------------------------------------------------------- */
+/* cameraPosition = CommonConstants::cameraPos (mesh.cpp:401), shared by every view of the frame. */
+int gsp_set_views(gsp_context* ctx, uint32_t viewCount, const gsp_view* views, const float cameraPosition[3]);
+/* Runs the whole frame on the device: world matrices, culling for every view, keys, compaction, sort, record
+ * emission. Results stay in HBM until fetched. Returns after the work has been enqueued AND completed. */
+int gsp_run(gsp_context* ctx);
+/* Same, but only enqueues (no host synchronisation); pair with gsp_sync. Used for device-side timing. */
+int gsp_run_async(gsp_context* ctx);
+int gsp_sync(gsp_context* ctx);
+
+/* ---- results (replace reading unsortedBuffers / transSortedMeshes / uiSortedMeshes, mesh.cpp:556-770) ------------ */
+uint32_t gsp_unsorted_buffer_count(const gsp_context* ctx, uint32_t view);
+uint32_t gsp_sorted_buffer_count(const gsp_context* ctx, uint32_t view);
+/* unsortedBuffers[buffer]->{combinedMeshes, drawCount, instanceCount}. `records` receives a pointer to pinned host
+ * memory owned by the library, valid until the next gsp_run / gsp_destroy; the list is downloaded on first request. */
+int gsp_get_unsorted(gsp_context* ctx, uint32_t view, uint32_t buffer, const gsp_record** records,
+	uint32_t* drawCount, uint32_t* instanceCount);
+/* sortedBuffers[buffer]->{drawCount, instanceCount} */
+int gsp_get_sorted_counts(gsp_context* ctx, uint32_t view, uint32_t buffer, uint32_t* drawCount, uint32_t* instanceCount);
+/* which = 0: transSortedMeshes / transDrawIndex, which = 1: uiSortedMeshes / uiDrawIndex */
+int gsp_get_sorted(gsp_context* ctx, uint32_t view, int which, const gsp_record** records, uint32_t* drawCount);
+/* Device-resident variants (no copy): `records` receives a device pointer (for CUDA/Vulkan interop consumers). */
+int gsp_get_unsorted_device(gsp_context* ctx, uint32_t view, uint32_t buffer, const gsp_record** records,
+	uint32_t* drawCount, uint32_t* instanceCount);
+int gsp_get_sorted_device(gsp_context* ctx, uint32_t view, int which, const gsp_record** records, uint32_t* drawCount);
+/* Sorted (key, payload) runs of one list on the device, before record emission: keys are the radix keys
+ * (ascending order == draw order), payload = pool << 28 | slot. Used by the multi-GPU gather + merge. */
+int gsp_get_sorted_run_device(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer,
+	const uint32_t** keys, const uint32_t** payloads, uint32_t* count);
+/* Stores MeshRenderComponent::isVisible (offset 15) for every slot of `pool` exactly as the reference's main-view pass
+ * does (mesh.cpp:144-146,152-153,161-167). No-op for pools the main view did not process. */
+int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride);
+/* World matrices (TransformComponent::calcModel(cameraPosition), transform.hpp:197-214) of pool slots as float4x3,
+ * valid for slots that were visible in at least one view of the last frame. `out` = occupancy * 12 floats on the host. */
+int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out);
+
+/* ---- introspection for benchmarks --------------------------------------------------------------------------------- */
+/* Number of CUDA kernels the last gsp_run launched. */
+uint32_t gsp_last_launch_count(const gsp_context* ctx);
+/* Sum over views and lists of drawCount for the last frame (needs results to be complete). */
+uint64_t gsp_last_visible_total(gsp_context* ctx);
+/* Library version string, e.g. "garden_sceneprep 0.1 sm_100a". */
+const char* gsp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GARDEN_SCENEPREP_H */
