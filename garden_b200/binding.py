@@ -45,9 +45,10 @@ SYMBOLS = {
     "gsp_get_sorted_run_device": (_i32, [_vp, _u32, _i32, _u32, _pp, _pp, _pu32]),
     "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),
     "gsp_download_models": (_i32, [_vp, _u32, _vp]),
+    "gsp_set_profiling": (_i32, [_vp, _i32]),
+    "gsp_get_phase_times": (_i32, [_vp, _vp]),
     "gsp_last_launch_count": (_u32, [_vp]),
     "gsp_last_visible_total": (_u64, [_vp]),
-    "gsp_merge_runs": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -199,6 +200,14 @@ class ScenePrep:
         out = np.zeros((occupancy, 12), dtype=np.float32)
         self._check(self.lib.gsp_download_models(self.h, pool, out.ctypes.data))
         return out
+
+    def set_profiling(self, enabled: bool):
+        self._check(self.lib.gsp_set_profiling(self.h, 1 if enabled else 0))
+
+    def phase_times(self) -> np.ndarray:
+        ms = np.zeros(5, dtype=np.float32)
+        self._check(self.lib.gsp_get_phase_times(self.h, ms.ctypes.data))
+        return ms
 
     def last_launch_count(self) -> int:
         return self.lib.gsp_last_launch_count(self.h)

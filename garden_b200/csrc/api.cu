@@ -132,6 +132,9 @@ void gsp_destroy(gsp_context* ctx)
 	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortHist); cudaFree(c.sortStatus); cudaFree(c.sortTickets);
 	cudaFree(c.segTileOffset); cudaFree(c.dAosScratch);
 	cudaFreeHost(c.hCounters); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible);
+	if (c.phaseEventsCreated)
+		for (auto& e : c.phaseEvents)
+			cudaEventDestroy(e);
 	cudaStreamDestroy(c.ownStream);
 	delete ctx;
 }
@@ -481,16 +484,29 @@ int gsp_run_async(gsp_context* ctx)
 		if (rc) return rc;
 	}
 	uint32_t launches = 0;
+	const bool prof = c.profiling;
+	if (prof && !c.phaseEventsCreated)
+	{
+		for (auto& e : c.phaseEvents)
+			GSP_CUDA(cudaEventCreate(&e));
+		c.phaseEventsCreated = true;
+	}
+	if (prof) cudaEventRecord(c.phaseEvents[0], c.stream);
 	if (c.linkDirty)
 	{
 		launches += launchLink(c);
 		c.linkDirty = false;
 	}
+	if (prof) cudaEventRecord(c.phaseEvents[1], c.stream);
 	GSP_CUDA(cudaMemsetAsync(c.dCounters, 0, kCtrCount * sizeof(uint32_t), c.stream));
 	for (uint32_t p = 0; p < c.poolCount; p++)
 		launches += launchCull(c, p);
-	launches += launchSort(c);
+	if (prof) cudaEventRecord(c.phaseEvents[2], c.stream);
+	launches += launchSort(c, prof ? c.phaseEvents[3] : nullptr);
+	if (prof) cudaEventRecord(c.phaseEvents[4], c.stream);
 	launches += launchEmit(c);
+	if (prof) cudaEventRecord(c.phaseEvents[5], c.stream);
+	c.phaseTimesValid = prof;
 	GSP_CUDA(cudaMemcpyAsync(c.hCounters, c.dCounters, kCtrCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaGetLastError());
 	c.launchCount = launches;
@@ -736,6 +752,29 @@ int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out)
 	GSP_CUDA(cudaSetDevice(c.device));
 	GSP_CUDA(cudaMemcpyAsync(out, p.world, (size_t)p.occupancy * 12 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	return GSP_OK;
+}
+
+int gsp_set_profiling(gsp_context* ctx, int enabled)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	ctx->c.profiling = enabled != 0;
+	return GSP_OK;
+}
+
+int gsp_get_phase_times(gsp_context* ctx, float* ms)
+{
+	if (!ctx || !ms)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	for (int i = 0; i < GSP_PHASE_COUNT; i++)
+		ms[i] = 0.0f;
+	if (!c.phaseTimesValid || !c.resultsValid)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	for (int i = 0; i < GSP_PHASE_COUNT; i++)
+		GSP_CUDA(cudaEventElapsedTime(&ms[i], c.phaseEvents[i], c.phaseEvents[i + 1]));
 	return GSP_OK;
 }
 

@@ -147,6 +147,9 @@ struct Context
 	std::vector<uint8_t> segDownloaded;
 	uint8_t* hVisible = nullptr; size_t hVisibleCap = 0;
 	uint32_t launchCount = 0;
+	bool profiling = false;
+	cudaEvent_t phaseEvents[8] = {};
+	bool phaseEventsCreated = false, phaseTimesValid = false;
 	uint32_t* dError = nullptr;
 };
 
@@ -168,7 +171,7 @@ uint32_t launchMaxEntity(Context& c, const void* dAos, uint32_t stride, uint32_t
 uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy);
 uint32_t launchLink(Context& c);
 uint32_t launchCull(Context& c, uint32_t pool);
-uint32_t launchSort(Context& c);
+uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);
 
 } // namespace gsp

@@ -227,11 +227,14 @@ __global__ void __launch_bounds__(kSortThreads) kSortPass(const __grid_constant_
 	}
 }
 
-uint32_t launchSort(Context& c)
+uint32_t launchSort(Context& c, cudaEvent_t afterHistogram)
 {
 	const uint32_t nseg = (uint32_t)c.segments.size();
 	if (nseg == 0)
+	{
+		if (afterHistogram) cudaEventRecord(afterHistogram, c.stream);
 		return 0;
+	}
 	uint32_t maxTiles = 0;
 	bool anySorted = false;
 	for (auto& s : c.segments)
@@ -241,7 +244,10 @@ uint32_t launchSort(Context& c)
 		maxTiles = max(maxTiles, (s.capacity + kSortTile - 1) / kSortTile);
 	}
 	if (!anySorted || maxTiles == 0)
+	{
+		if (afterHistogram) cudaEventRecord(afterHistogram, c.stream);
 		return 0;
+	}
 	SortArgs A;
 	A.segments = c.dSegments; A.counters = c.dCounters; A.hist = c.sortHist; A.status = c.sortStatus;
 	A.tickets = c.sortTickets; A.segTileOffset = c.segTileOffset; A.tilesTotal = c.sortTilesTotal;
@@ -249,6 +255,7 @@ uint32_t launchSort(Context& c)
 	cudaMemsetAsync(c.sortTickets, 0, (size_t)nseg * kPasses * sizeof(uint32_t), c.stream);
 	dim3 grid(maxTiles, nseg);
 	kSortHistogram<<<grid, kSortThreads, 0, c.stream>>>(A, c.keys[0]);
+	if (afterHistogram) cudaEventRecord(afterHistogram, c.stream);
 	uint32_t launches = 1;
 	for (uint32_t pass = 0; pass < kPasses; pass++)
 	{

@@ -134,6 +134,13 @@ int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t s
 int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out);
 
 /* ---- introspection for benchmarks --------------------------------------------------------------------------------- */
+/* Per-phase device timing with CUDA events recorded on the context's stream around each kernel group of gsp_run.
+ * Phases: 0 link (entity -> transform slot, only after structural changes), 1 cull+compact (all pools),
+ * 2 sort histogram, 3 sort passes, 4 record emission. */
+#define GSP_PHASE_COUNT 5
+int gsp_set_profiling(gsp_context* ctx, int enabled);
+/* Milliseconds of each phase of the last completed gsp_run (zeros when profiling is off). `ms` = GSP_PHASE_COUNT floats. */
+int gsp_get_phase_times(gsp_context* ctx, float* ms);
 /* Number of CUDA kernels the last gsp_run launched. */
 uint32_t gsp_last_launch_count(const gsp_context* ctx);
 /* Sum over views and lists of drawCount for the last frame (needs results to be complete). */
