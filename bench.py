@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the scene-preparation hot path (transform -> cull -> key -> compact -> sort -> draw records).
+
+  python bench.py --gpus N --steps K --warmup W                 the B200 path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W   the reference's own CPU thread-pool path
+
+One JSON line on stdout (rank 0). A "step" is one frame = all views of one scene state. Metric: entities
+transformed+culled+sorted per second (BASELINE.json). `value` is device-resident (SoA already in HBM, lists left in HBM),
+`e2e` goes through the C ABI with host buffers (AoS upload, list download, isVisible write-back) every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from garden_b200 import scenes, views as V  # noqa: E402
+
+METRIC = "entities transformed+culled+sorted/s"
+UNIT = "entities/s"
+# algorithmic bytes per frame B = 75*N + 132*SumVis
+BYTES_PER_ENTITY = 75
+BYTES_PER_VISIBLE = 132
+WORKLOADS = {
+    # name -> (config, default N, description)
+    "C4": ("C4", 16_000_000, "16M instances, depth-8 hierarchy, camera + 4 CSM cascades"),
+    "C2": ("C2", 1_000_000, "1M entities, depth-4 hierarchy, camera + 4 CSM cascades"),
+    "C3": ("C3", 4_000_000, "4M entities, depth-8, opaque + translucent, 1 view"),
+}
+
+
+def frame_views(workload: str):
+    if workload == "C3":
+        return V.perspective_views([(0.6, -0.05)], 1.2, 16 / 9, 0.01)[0]
+    return V.camera_and_cascades(0.6, -0.12, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))[0]
+
+
+def camera_pos():
+    return np.array([12.5, 3.0, -7.25], dtype=np.float32)
+
+
+def load_peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows = []
+        self.proc = None
+        self.device_index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_like(arr: np.ndarray):
+    """Copies `arr` into pinned host memory (torch allocator) and returns (numpy view, owner tensor)."""
+    import torch
+    t = torch.empty(arr.nbytes, dtype=torch.uint8, pin_memory=True)
+    view = t.numpy().view(arr.dtype).reshape(arr.shape)
+    view[...] = arr
+    return view, t
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_engine_run(workload: str, sample_n: int, steps: int, warmup: int, seed: int):
+    """Times the reference's own prepareMeshes (oracle/_ref stock build; falls back to the C port) on `sample_n`
+    entities of the workload. Returns dict(value, ms_per_step, cores, kind, sample, visible)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import reflib
+    cfg = WORKLOADS[workload][0]
+    scene = scenes.config_scene(cfg, n=sample_n, seed=seed)
+    scene.camera_pos = camera_pos()
+    views = frame_views(workload)
+    if reflib.ref_available("stock"):
+        with reflib.RefEngine("stock", threads=-1) as ref:
+            ref.load_scene(scene)
+            threads = ref.thread_count
+            ref.time_frames(views, max(warmup, 1))
+            ms, vis = ref.time_frames(views, steps)
+        kind = "reference"
+        cores = threads
+    else:
+        from common import OracleRun, aos_inputs
+        t, pools = aos_inputs(scene)
+        rts = [p.render_type for p in scene.pools]
+        ms = []
+        vis = [0]
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orun = OracleRun((t, t.dtype.itemsize, t.size), [(m, m.dtype.itemsize, m.size) for m in pools], rts, views,
+                             scene.camera_pos)
+            if i >= warmup:
+                ms.append((time.perf_counter() - t0) * 1e3)
+            vis = [sum(u[1] for vw in orun.views for u in vw["unsorted"]) + sum(vw["trans"][1] for vw in orun.views)]
+        ms = np.array(ms)
+        kind, cores = "port", 1
+    mean_ms = float(np.mean(ms))
+    return {"value": sample_n / (mean_ms * 1e-3), "ms_per_step": mean_ms, "best_ms": float(np.min(ms)), "cores": int(cores),
+            "kind": kind, "visible": int(vis[-1]),
+            "sample": f"{sample_n} entities of workload {workload} (same generator, same {views.size} views), "
+                      f"{len(ms)} frames, mean"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = reference_engine_run(args.workload, args.ref_sample, args.steps, args.warmup, args.seed)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][2]}", "entities_per_step": args.ref_sample,
+                   "views": int(frame_views(args.workload).size), "visible_total": res["visible"],
+                   "note": "reference CPU thread-pool path on host cores; each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from garden_b200.binding import ScenePrep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the scene-preparation path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, default_n, desc = WORKLOADS[args.workload]
+    n = args.entities or default_n
+    # weak scaling: every GPU owns an N-entity shard (contiguous entity range of a world-size * N scene)
+    scene = scenes.config_scene(cfg, n=n, seed=args.seed + 7919 * rank)
+    scene.camera_pos = camera_pos()
+    views = frame_views(args.workload)
+    t_np, pools_np = scenes.build_aos(scene)
+    rts = [p.render_type for p in scene.pools]
+    t_pin, _t_owner = pinned_like(t_np)
+    pool_pins = [pinned_like(m) for m in pools_np]
+    del t_np, pools_np
+
+    stream = torch.cuda.current_stream()
+    sp = ScenePrep(local_rank)
+    sp.set_stream(stream.cuda_stream)
+
+    def stage():
+        sp.set_transforms(t_pin, t_pin.dtype.itemsize, t_pin.size)
+        sp.set_pool_count(len(pool_pins))
+        for k, (m, _) in enumerate(pool_pins):
+            sp.set_mesh_pool(k, rts[k], m, m.dtype.itemsize, m.size)
+        sp.set_views(views, scene.camera_pos)
+
+    stage()
+    merger = None
+    if world > 1:
+        from garden_b200.dist import RunMerger
+        merger = RunMerger(sp, views.size, len(pool_pins), rts)
+
+    def frame():
+        sp.run_async()
+        if merger is not None:
+            merger.gather_and_merge()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        frame()
+    sp.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        frame()
+    ev1.record(stream)
+    sp.sync()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = sp.last_launch_count() + (merger.launches_per_frame if merger else 0)
+    visible_total = sp.last_visible_total()
+
+    # ---- per-kernel-group timing (CUDA events on the same stream, inside the library) ----
+    sp.set_profiling(True)
+    phase = np.zeros(5)
+    prof_steps = max(3, min(args.steps, 10))
+    for _ in range(prof_steps):
+        sp.run()
+        phase += sp.phase_times()
+    phase /= prof_steps
+    sp.set_profiling(False)
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    records_bytes = 0
+
+    def e2e_frame():
+        nonlocal records_bytes
+        stage()
+        sp.run()
+        total = 0
+        for v in range(views.size):
+            for b in range(sp.unsorted_buffer_count(v)):
+                rec, draw, _ = sp.get_unsorted(v, b, copy=False)
+                total += draw
+            rec, draw = sp.get_sorted(v, 0, copy=False)
+            total += draw
+        for k, (m, _) in enumerate(pool_pins):
+            sp.writeback_visible(k, m, m.dtype.itemsize)
+        records_bytes = total * 64
+        return total
+
+    e2e_frame()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_frame()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = t_pin.nbytes + sum(m.nbytes for m, _ in pool_pins) + views.nbytes
+    d2h = records_bytes + sum(m.size for m, _ in pool_pins)
+
+    # ---- reduce over ranks: max time, summed work ----
+    stats = torch.tensor([elapsed_ms, e2e_s, float(visible_total)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        elapsed_ms, e2e_s, visible_sum = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        visible_sum = float(visible_total)
+    ms_per_step = elapsed_ms / args.steps
+    total_entities = n * world
+    value = total_entities / (ms_per_step * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        alg_bytes = BYTES_PER_ENTITY * n + BYTES_PER_VISIBLE * visible_total  # per GPU
+        names = ["link", "cull+compact (kCull)", "sort histogram (kSortHistogram)", "sort passes (kSortPass x4)",
+                 "record emission (kEmit)"]
+        kernel_bytes = [0, 75 * n + 8 * visible_total, 4 * visible_total, 64 * visible_total, (8 + 48 + 64) * visible_total]
+        frame_ms = float(phase.sum())
+        kernels = []
+        for i in range(1, 5):
+            ms = float(phase[i])
+            gbs = kernel_bytes[i] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            kernels.append({"name": names[i], "ms": round(ms, 4), "share": round(ms / frame_ms, 3) if frame_ms else 0,
+                            "bytes": int(kernel_bytes[i]), "GBps": round(gbs, 1), "frac": round(gbs / peak, 3)})
+        dom = max(range(len(kernels)), key=lambda i: kernels[i]["ms"])
+        frame_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": kernels[dom]["name"], "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "frame": {"algorithmic_bytes": int(alg_bytes), "achieved": round(frame_gbs, 1), "frac": round(frame_gbs / peak, 3),
+                      "formula": "75*N + 132*SumVis (SURVEY.md 8d), per GPU, over the timed ms_per_step"},
+            "kernels": kernels,
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "entities_per_gpu": n, "entities_total": total_entities,
+                       "views": int(views.size), "visible_total": int(visible_sum),
+                       "l2": "inputs larger than L2 (%.2f GB of SoA streams per frame vs 126 MB L2)" % (75 * n / 1e9),
+                       "sharding": "contiguous entity ranges per GPU, all views per GPU" if world > 1 else "single GPU"},
+            "roofline": roofline,
+            "e2e": {"value": total_entities / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "full AoS pool upload (ECS has no dirty tracking) + run + all draw lists to host + isVisible write-back"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = reference_engine_run(args.workload, args.ref_sample, args.ref_steps, 1, args.seed)
+            line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                                    "sample": res["sample"], "ms_per_step": res["ms_per_step"]}
+        print(json.dumps(line), flush=True)
+    sp.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--entities", type=int, default=0, help="override N per GPU (default: the workload's N)")
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-sample", type=int, default=1_000_000, help="entities in the CPU reference sample")
+    ap.add_argument("--ref-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,7 +126,7 @@ void gsp_destroy(gsp_context* ctx)
 	for (auto& p : c.pools)
 	{
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
-		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus); cudaFree(p.visBits);
 	}
 	cudaFree(c.dSegments); cudaFree(c.keys[0]); cudaFree(c.keys[1]); cudaFree(c.payloads[0]); cudaFree(c.payloads[1]);
 	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortHist); cudaFree(c.sortStatus); cudaFree(c.sortTickets);
@@ -270,7 +270,8 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		if (cap == 0) cap = 1;
 		GSP_CUDA(cudaStreamSynchronize(c.stream));
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
-		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus); cudaFree(p.visBits);
+		p.visBits = nullptr;
 		p.aabbA = nullptr; p.aabbB = nullptr; p.entity = nullptr; p.tslot = nullptr; p.flags = nullptr; p.ready = nullptr;
 		p.world = nullptr; p.visible = nullptr; p.cullStatus = nullptr; p.capacity = 0;
 		GSP_CUDA(cudaMalloc((void**)&p.aabbA, (size_t)cap * sizeof(float4)));
@@ -283,6 +284,7 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		GSP_CUDA(cudaMalloc((void**)&p.visible, (size_t)cap));
 		p.cullTilesCap = (cap + kCullTile - 1) / kCullTile;
 		GSP_CUDA(cudaMalloc((void**)&p.cullStatus, (size_t)p.cullTilesCap * kMaxViews * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&p.visBits, (size_t)p.cullTilesCap * kMaxViews * (kCullTile / 32) * sizeof(uint32_t)));
 		p.capacity = cap;
 	}
 	if (p.occupancy != occupancy || p.renderType != renderType || p.stride != stride || !p.set ||

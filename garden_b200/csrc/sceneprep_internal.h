@@ -54,7 +54,8 @@ struct PoolDev
 	uint8_t* ready = nullptr;
 	float4* world = nullptr;   // 3 x float4 per slot = float4x3 world matrix (c0..c3 lanes xyz), written for visible slots
 	uint8_t* visible = nullptr; // isVisible of the last main view, per slot
-	uint32_t* cullStatus = nullptr; // [tiles][kMaxViews] decoupled look-back words
+	uint32_t* cullStatus = nullptr; // [kMaxViews][tiles] visible count per tile and view, scanned in place to list offsets
+	uint32_t* visBits = nullptr;    // [kMaxViews][tiles * 8] visibility ballot words
 	uint32_t cullTiles = 0, cullTilesCap = 0;
 	bool visibleValid = false;
 };
@@ -63,11 +64,12 @@ struct PoolDev
 struct ViewConst
 {
 	float planes[6][4];
+	float planeL2[6];    // |n|_2, rounded up
+	float planeL1[6];    // |n|_1 * band scale
+	float planeAbsD[6];  // |d| * band scale
 	float cameraOffset[4];
 	uint32_t planeCount;
 	uint32_t enabled;   // pool participates in this view
-	uint32_t writeVisible; // this is the last main view: store isVisible
-	uint32_t pad;
 };
 struct CullParams
 {
