@@ -31,7 +31,7 @@ struct CullArgs
 	float4* __restrict__ world;
 	uint8_t* __restrict__ visible;
 	uint32_t* __restrict__ visBits;  // [kMaxViews][tiles * 8] one ballot word per warp and view: visibility bit per slot
-	uint32_t* __restrict__ tileCount; // [kMaxViews][tiles] visible slots per tile and view; scanned in place to list offsets
+	uint32_t* __restrict__ chunkCount; // [kMaxViews][chunks] visible slots per chunk and view; scanned in place to list offsets
 	uint32_t* __restrict__ counters;
 	uint32_t* __restrict__ keys;
 	uint32_t* __restrict__ payloads;
@@ -39,8 +39,11 @@ struct CullArgs
 	uint32_t baseCounter[kMaxViews]; // counter index holding the list length before this pool (kNone = 0)
 	uint32_t visibleView;            // view whose result is stored to isVisible (kNone = none)
 	uint32_t tiles;
+	uint32_t chunks;
 };
 
+constexpr uint32_t kChunkTiles = 32;                               // tiles per compaction chunk
+constexpr uint32_t kChunkWords = kChunkTiles * (kCullTile / 32);   // ballot words per chunk = threads of kScatter
 constexpr uint32_t kFlagAggregate = 1u << 30, kFlagInclusive = 2u << 30, kValueMask = (1u << 30) - 1;
 
 __device__ __forceinline__ uint32_t ldVolatile(const uint32_t* p)
@@ -59,18 +62,23 @@ __device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v)
 // the ancestors' LOCAL matrices — are shared. Each tile computes the local matrix of every transform it touches once
 // (bit-identical to recomputing it) and parks it in a direct-mapped cache keyed by transform slot;
 // ancestors outside the tile (or evicted by a conflicting slot) are recomputed from the SoA streams.
-constexpr uint32_t kCacheSize = 512, kCacheMask = kCacheSize - 1, kHalo = 16;
+constexpr uint32_t kCacheSize = 320, kHalo = 16; // >= tile + halo distinct slots; index = slot % kCacheSize
+constexpr uint32_t kDepthBins = 32;
 
 struct CullShared
 {
-	float L[12][kCacheSize];   // component-major: consecutive slots hit consecutive banks
-	uint32_t tag[kCacheSize];  // transform slot held by the entry (kNone = empty)
-	uint32_t par[kCacheSize];  // its parent slot
-	uint32_t warpCount[kMaxViews][kCullTile / 32];
-	uint32_t base[kMaxViews];
-	uint32_t inst[kMaxViews];
+	float4 L[kCacheSize][3];    // float4x3 per entry, 48-byte stride: 128-bit shared loads/stores are conflict-free
+	uint32_t tag[kCacheSize];   // transform slot held by the entry (kNone = empty)
+	uint32_t par[kCacheSize];   // its parent slot
+	float aabb[6][kCullTile];   // per owner slot: min xyz, max xyz
+	uint32_t ownTs[kCullTile];  // per owner slot: transform slot (kNone = not a candidate)
+	uint16_t perm[kCullTile];   // work item -> owner slot, grouped by chain depth so a warp walks chains of equal length
+	uint16_t maskOf[kCullTile]; // per owner slot: visibility bit per view
+	uint8_t ownWalk[kCullTile]; // per owner slot: walks its parent chain (candidate && modelWithAncestors)
+	uint32_t hist[kDepthBins];
+	uint32_t binStart[kDepthBins];
 	uint32_t total[kMaxViews];
-	uint32_t tile;
+	uint32_t inst[kMaxViews];
 	uint32_t minSlot;
 };
 
@@ -84,24 +92,52 @@ __device__ __forceinline__ Mat43 loadLocal43(const CullArgs& a, uint32_t t)
 
 __device__ __forceinline__ void cacheInsert(CullShared& sh, uint32_t t, uint32_t parent, const Mat43& L)
 {
-	const uint32_t e = t & kCacheMask;
+	const uint32_t e = t % kCacheSize;
 	// claim the entry first: two slots of one tile may collide, and only the winner may write the payload
 	if (atomicCAS(&sh.tag[e], kNone, t) != kNone)
 		return;
-	#pragma unroll
-	for (int i = 0; i < 4; i++)
-		#pragma unroll
-		for (int l = 0; l < 3; l++)
-			sh.L[i * 3 + l][e] = L.c[i][l];
+	sh.L[e][0] = make_float4(L.c[0][0], L.c[0][1], L.c[0][2], L.c[1][0]);
+	sh.L[e][1] = make_float4(L.c[1][1], L.c[1][2], L.c[2][0], L.c[2][1]);
+	sh.L[e][2] = make_float4(L.c[2][2], L.c[3][0], L.c[3][1], L.c[3][2]);
 	sh.par[e] = parent;
+}
+
+// Local matrix + parent link of transform slot t: from the cache when it holds t, else recomputed from the SoA streams.
+__device__ __forceinline__ Mat43 fetchLocal(const CullShared& sh, const CullArgs& a, uint32_t t, uint32_t& parent)
+{
+	const uint32_t e = t % kCacheSize;
+	Mat43 L;
+	if (sh.tag[e] == t)
+	{
+		const float4 a0 = sh.L[e][0], a1 = sh.L[e][1], a2 = sh.L[e][2];
+		L.c[0][0] = a0.x; L.c[0][1] = a0.y; L.c[0][2] = a0.z; L.c[1][0] = a0.w;
+		L.c[1][1] = a1.x; L.c[1][2] = a1.y; L.c[2][0] = a1.z; L.c[2][1] = a1.w;
+		L.c[2][2] = a2.x; L.c[3][0] = a2.y; L.c[3][1] = a2.z; L.c[3][2] = a2.w;
+		parent = sh.par[e];
+	}
+	else
+	{
+		L = loadLocal43(a, t);
+		parent = a.tParent[t];
+	}
+	return L;
 }
 
 // Conservative half-width of the band around a plane inside which the exact 8-corner test decides:
 // computed plane distances differ from real arithmetic by a few ulp of the magnitudes involved (|n|_1 * A + |d|, A bounding
-// every |corner lane| and every intermediate of the corner transform); 2^-16 of that leaves a factor > 30 of head room.
-constexpr float kBandScale = 1.0f / 65536.0f;
+// every |corner lane| and every intermediate of the corner transform); 2 * 2^-16 of that leaves a factor > 30 of head room.
+// With |n|_1 <= sqrt(3) |n|_2 the band folds into the sphere radius: reach = |n|_2 * (radius + kBandR * A) + kBandD * |d|.
+constexpr float kBandR = 1.7321f / 32768.0f, kBandD = 1.0f / 32768.0f;
 
-__global__ void __launch_bounds__(kCullTile, 3) kCull(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+// Threads per block and slots per thread: a tile of kCullTile slots is handled by kCullThreads threads, kCullItems each.
+// Work items are sorted by chain length into groups of 32 (deepest first); warp w takes groups w and (last - w), so every
+// warp walks chains of uniform length AND all warps of the block carry the same total work.
+constexpr uint32_t kCullThreads = 128, kCullItems = kCullTile / kCullThreads, kCullWarps = kCullThreads / 32;
+constexpr uint32_t kCullGroups = kCullTile / 32;
+static_assert(kCullItems == 2, "the snake assignment below pairs group g with group (last - g)");
+
+template<uint32_t kViews>
+__global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
 {
 	__shared__ CullShared sh;
 
@@ -113,63 +149,110 @@ __global__ void __launch_bounds__(kCullTile, 3) kCull(const __grid_constant__ Cu
 		sh.inst[threadIdx.x] = 0;
 		sh.total[threadIdx.x] = 0;
 	}
-	for (uint32_t i = threadIdx.x; i < kCacheSize; i += kCullTile)
+	if (threadIdx.x < kDepthBins)
+		sh.hist[threadIdx.x] = 0;
+	for (uint32_t i = threadIdx.x; i < kCacheSize; i += kCullThreads)
 		sh.tag[i] = kNone;
 	__syncthreads();
 	const uint32_t tile = blockIdx.x;
-	const uint32_t slot = tile * kCullTile + threadIdx.x;
 
-	// ---- filter (mesh.cpp:140-155) ----
-	const bool inRange = slot < P.occupancy;
-	bool cand = inRange && (A.mflags[slot] & kMfCandidate);
-	uint32_t ts = inRange ? A.tslot[slot] : kNone;
-	// flags, TRS and parent link depend only on `ts`: issue all the loads together (one latency, not four)
-	uint8_t tf = 0;
-	float4 tq = make_float4(0.f, 0.f, 0.f, 1.f), tp = make_float4(0.f, 0.f, 0.f, 1.f);
-	float2 tsyz = make_float2(1.f, 1.f);
-	uint32_t parentLink = kNone;
-	if (ts != kNone)
+	// ---- filter (mesh.cpp:140-155) + phase 1: local matrix of the own transform into the cache ----
+	uint32_t depthKey[kCullItems], rankInBin[kCullItems];
+	#pragma unroll
+	for (uint32_t r = 0; r < kCullItems; r++)
 	{
-		tf = A.tFlags[ts]; tq = A.tRot[ts]; tp = A.tPosSx[ts]; tsyz = A.tSYZ[ts]; parentLink = A.tParent[ts];
-	}
-	const bool liveTransform = (tf & kTfLive) != 0;
-	cand = cand && liveTransform && (tf & kTfActive);
-
-	// ---- phase 1: local matrix of the own transform (and of a short halo before the tile) into the cache ----
-	Mat43 M;
-	uint32_t parent = kNone;
-	if (liveTransform)
-	{
-		M = localModel43(tp.x, tp.y, tp.z, tq.x, tq.y, tq.z, tq.w, tp.w, tsyz.x, tsyz.y);
-		parent = parentLink;
-		cacheInsert(sh, ts, parent, M);
-		atomicMin(&sh.minSlot, ts);
+		const uint32_t own = threadIdx.x + r * kCullThreads;
+		const uint32_t slot = tile * kCullTile + own;
+		const bool inRange = slot < P.occupancy;
+		bool cand = inRange && (A.mflags[slot] & kMfCandidate);
+		const uint32_t ts = inRange ? A.tslot[slot] : kNone;
+		// flags, TRS and parent link depend only on `ts`: issue all the loads together (one latency, not four)
+		uint8_t tf = 0;
+		float4 tq = make_float4(0.f, 0.f, 0.f, 1.f), tp = make_float4(0.f, 0.f, 0.f, 1.f);
+		float2 tsyz = make_float2(1.f, 1.f);
+		uint32_t parentLink = kNone;
+		if (ts != kNone)
+		{
+			tf = A.tFlags[ts]; tq = A.tRot[ts]; tp = A.tPosSx[ts]; tsyz = A.tSYZ[ts]; parentLink = A.tParent[ts];
+		}
+		if (inRange)
+		{
+			const float4 ba = A.aabbA[slot];
+			const float2 bb = A.aabbB[slot];
+			sh.aabb[0][own] = ba.x; sh.aabb[1][own] = ba.y; sh.aabb[2][own] = ba.z;
+			sh.aabb[3][own] = ba.w; sh.aabb[4][own] = bb.x; sh.aabb[5][own] = bb.y;
+		}
+		const bool liveTransform = (tf & kTfLive) != 0;
+		cand = cand && liveTransform && (tf & kTfActive);
+		if (liveTransform)
+		{
+			Mat43 L = localModel43(tp.x, tp.y, tp.z, tq.x, tq.y, tq.z, tq.w, tp.w, tsyz.x, tsyz.y);
+			cacheInsert(sh, ts, parentLink, L);
+			atomicMin(&sh.minSlot, ts);
+		}
+		// chain length (capped) sorts the tile's work; modelWithAncestors == false means no walk at all (transform.hpp:200)
+		const bool walk = cand && (tf & kTfAncestors);
+		depthKey[r] = walk ? (uint32_t)(tf >> kTfDepthShift) : 0u;
+		sh.ownTs[own] = cand ? ts : kNone;
+		sh.ownWalk[own] = walk ? 1 : 0;
+		rankInBin[r] = atomicAdd(&sh.hist[depthKey[r]], 1u);
 	}
 	__syncthreads();
-	if (threadIdx.x < kHalo)
+	if (warp == 0 && lane < kHalo)
 	{
 		// chains that start in the previous tile: their ancestors sit right before the tile's lowest transform slot
 		const uint32_t first = sh.minSlot;
-		if (first != kNone && first >= threadIdx.x + 1)
+		if (first != kNone && first >= lane + 1)
 		{
-			const uint32_t h = first - 1 - threadIdx.x;
-			if (sh.tag[h & kCacheMask] == kNone && (A.tFlags[h] & kTfLive))  // (racing claims are settled by the CAS)
+			const uint32_t h = first - 1 - lane;
+			if (sh.tag[h % kCacheSize] == kNone && (A.tFlags[h] & kTfLive)) // (racing claims are settled by the CAS)
 			{
 				Mat43 H = loadLocal43(A, h);
 				cacheInsert(sh, h, A.tParent[h], H);
 			}
 		}
 	}
+	if (warp == 1) // exclusive scan of the depth histogram, deepest chains first
+	{
+		const uint32_t c = sh.hist[kDepthBins - 1 - lane];
+		uint32_t inc = c;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc += t;
+		}
+		sh.binStart[kDepthBins - 1 - lane] = inc - c;
+	}
+	__syncthreads();
+	#pragma unroll
+	for (uint32_t r = 0; r < kCullItems; r++)
+		sh.perm[sh.binStart[depthKey[r]] + rankInBin[r]] = (uint16_t)(threadIdx.x + r * kCullThreads);
 	__syncthreads();
 
-	uint32_t mask = 0;
-	uint32_t readyCount = 1;
-	if (cand)
+	// ---- phases 2 + 3 run per WORK ITEM ----
+	#pragma unroll 1
+	for (uint32_t r = 0; r < kCullItems; r++)
 	{
+		const uint32_t group = r == 0 ? warp : kCullGroups - 1 - warp;
+		const uint32_t owner = sh.perm[group * 32 + lane];
+		const uint32_t wslot = tile * kCullTile + owner;
+		const uint32_t wts = sh.ownTs[owner];
+		const bool work = wts != kNone;
+		uint32_t mask = 0;
+
 		// ---- phase 2: world matrix, leaf-first chain product (transform.hpp:199-211) ----
-		if (tf & kTfAncestors)
+		Mat43 M;
+		#pragma unroll
+		for (int i = 0; i < 4; i++)
+			for (int l = 0; l < 3; l++)
+				M.c[i][l] = (i == l) ? 1.0f : 0.0f;
+		if (work)
 		{
-			uint32_t p = parent;
+			uint32_t p;
+			M = fetchLocal(sh, A, wts, p);
+			if (!sh.ownWalk[owner])
+				p = kNone;
 			uint32_t depth = 0;
 			while (p != kNone)
 			{
@@ -178,23 +261,8 @@ __global__ void __launch_bounds__(kCullTile, 3) kCull(const __grid_constant__ Cu
 					atomicExch(&A.counters[kCtrError], (uint32_t)GSP_ERR_HIERARCHY);
 					break;
 				}
-				const uint32_t e = p & kCacheMask;
-				Mat43 L;
 				uint32_t next;
-				if (sh.tag[e] == p)
-				{
-					#pragma unroll
-					for (int i = 0; i < 4; i++)
-						#pragma unroll
-						for (int l = 0; l < 3; l++)
-							L.c[i][l] = sh.L[i * 3 + l][e];
-					next = sh.par[e];
-				}
-				else
-				{
-					L = loadLocal43(A, p);
-					next = A.tParent[p];
-				}
+				const Mat43 L = fetchLocal(sh, A, p, next);
 				M = matMul43(L, M);
 				p = next;
 			}
@@ -204,9 +272,13 @@ __global__ void __launch_bounds__(kCullTile, 3) kCull(const __grid_constant__ Cu
 		M.c[3][1] = __fadd_rn(M.c[3][1], -P.cam[1]);
 		M.c[3][2] = __fadd_rn(M.c[3][2], -P.cam[2]);
 
-		const float4 ba = A.aabbA[slot];
-		const float2 bb = A.aabbB[slot];
-		const float mn[3] = {ba.x, ba.y, ba.z}, mx[3] = {ba.w, bb.x, bb.y};
+		float mn[3], mx[3];
+		#pragma unroll
+		for (int k = 0; k < 3; k++)
+		{
+			mn[k] = sh.aabb[k][owner];
+			mx[k] = sh.aabb[3 + k][owner];
+		}
 
 		// ---- phase 3a: conservative bounds of the transformed box (any rounding is fine here, the band absorbs it) ----
 		float ctr[3], ext[3], amax[3];
@@ -234,113 +306,200 @@ __global__ void __launch_bounds__(kCullTile, 3) kCull(const __grid_constant__ Cu
 			float len2 = fmaf(M.c[i][0], M.c[i][0], fmaf(M.c[i][1], M.c[i][1], M.c[i][2] * M.c[i][2]));
 			rr = fmaf(len2, ext[i] * ext[i], rr);
 		}
-		const float radius = sqrtf(3.0f * rr) * 1.0001f;
-
-		// corners for the exact test are produced lazily, once
-		float vx[8], vy[8], vz[8];
-		bool haveCorners = false;
+		const float reachR = fmaf(magnitude, kBandR, sqrtf(3.0f * rr) * 1.0001f);
 
 		// ---- phase 3b: plane tests per view (aabb.hpp:452-462): culled if some plane has all 8 corners at d < 0 ----
-		for (uint32_t v = 0; v < P.viewCount; v++)
+		// Branch-free classification of all six planes against the bounding sphere; only straddling planes (or NaNs) fall
+		// through to the reference's exact 8-corner arithmetic, so the boolean result is identical by construction.
+		// The view loop is fully unrolled so that every plane constant is a direct constant-bank operand.
+		uint32_t exactViews = 0; // views that need the exact test
+		#pragma unroll
+		for (uint32_t v = 0; v < kViews; v++)
 		{
-			const ViewConst& V = P.views[v];
-			if (!V.enabled)
-				continue;
-			bool culled = false;
-			for (uint32_t i = 0; i < V.planeCount; i++)
+			if (v < P.viewCount) // warp-uniform
 			{
-				const float nx = V.planes[i][0], ny = V.planes[i][1], nz = V.planes[i][2], nd = V.planes[i][3];
-				const float dc = fmaf(nx, cw[0], fmaf(ny, cw[1], fmaf(nz, cw[2], nd)));
-				const float band = fmaf(V.planeL1[i], magnitude, V.planeAbsD[i]); // already scaled by 2 * kBandScale
-				const float reach = fmaf(radius, V.planeL2[i], band);
-				if (dc > reach)
-					continue;          // every corner is certainly in front: the plane cannot cull
-				if (dc < -reach)
+				const ViewConst& V = P.views[v];
+				bool behindAny = false, uncertainAny = false;
+				#pragma unroll
+				for (int i = 0; i < 6; i++) // planes past planeCount are neutral (always "in front")
 				{
-					culled = true;     // every corner is certainly behind (all eight d < 0)
-					break;
+					const float dc = fmaf(V.planes[i][0], cw[0], fmaf(V.planes[i][1], cw[1], fmaf(V.planes[i][2], cw[2], V.planes[i][3])));
+					const float reach = fmaf(V.planeL2[i], reachR, V.planeAbsD[i]);
+					const bool certain = fabsf(dc) > reach;   // all eight corners certainly on one side (NaN: not certain)
+					behindAny = behindAny || (certain && dc < 0.0f); // certainly all at d < 0: the plane culls
+					uncertainAny = uncertainAny || !certain;
 				}
-				// straddling (or NaN): the reference's exact arithmetic decides
-				if (!haveCorners)
+				if (!behindAny && V.enabled)
 				{
+					if (!uncertainAny)
+						mask |= 1u << v;
+					else
+						exactViews |= 1u << v;
+				}
+			}
+		}
+		if (!work)
+		{
+			mask = 0; exactViews = 0;
+		}
+		if (exactViews) // rare: the box straddles a plane
+		{
+			float vx[8], vy[8], vz[8];
+			#pragma unroll
+			for (int k = 0; k < 8; k++)
+				transformCorner43(M, (k & 4) ? mx[0] : mn[0], (k & 2) ? mx[1] : mn[1], (k & 1) ? mx[2] : mn[2], vx[k], vy[k], vz[k]);
+			while (exactViews)
+			{
+				const uint32_t v = __ffs(exactViews) - 1;
+				exactViews &= exactViews - 1;
+				const ViewConst& V = P.views[v];
+				bool culled = false;
+				for (uint32_t i = 0; i < V.planeCount && !culled; i++)
+				{
+					const float nx = V.planes[i][0], ny = V.planes[i][1], nz = V.planes[i][2], nd = V.planes[i][3];
+					// planes the sphere test already proved "in front" cannot cull; no plane of this view is "certainly behind"
+					const float dc = fmaf(nx, cw[0], fmaf(ny, cw[1], fmaf(nz, cw[2], nd)));
+					if (dc > fmaf(V.planeL2[i], reachR, V.planeAbsD[i]))
+						continue;
+					bool allBehind = true;
 					#pragma unroll
 					for (int k = 0; k < 8; k++)
-						transformCorner43(M, (k & 4) ? mx[0] : mn[0], (k & 2) ? mx[1] : mn[1], (k & 1) ? mx[2] : mn[2],
-							vx[k], vy[k], vz[k]);
-					haveCorners = true;
+						allBehind = allBehind && (planeDistance(nx, ny, nz, nd, vx[k], vy[k], vz[k]) < 0.0f);
+					culled = allBehind;
 				}
-				bool allBehind = true;
-				#pragma unroll
-				for (int k = 0; k < 8; k++)
-					allBehind = allBehind && (planeDistance(nx, ny, nz, nd, vx[k], vy[k], vz[k]) < 0.0f);
-				if (allBehind) { culled = true; break; }
+				if (!culled)
+					mask |= 1u << v;
 			}
-			if (!culled)
-				mask |= 1u << v;
 		}
-		if (P.hasReady) // a getReadyMeshesAsync override's extra predicate (e.g. sprite.cpp:90-97)
+		uint32_t readyCount = 1;
+		if (P.hasReady && mask) // a getReadyMeshesAsync override's extra predicate (e.g. sprite.cpp:90-97)
 		{
-			readyCount = A.ready[slot];
+			readyCount = A.ready[wslot];
 			if (readyCount == 0) mask = 0;
 		}
 		if (mask) // bakedModel = (float4x3)model (mesh.cpp:171,249)
 		{
-			float4* w = A.world + (size_t)slot * 3;
+			float4* w = A.world + (size_t)wslot * 3;
 			w[0] = make_float4(M.c[0][0], M.c[0][1], M.c[0][2], M.c[1][0]);
 			w[1] = make_float4(M.c[1][1], M.c[1][2], M.c[2][0], M.c[2][1]);
 			w[2] = make_float4(M.c[2][2], M.c[3][0], M.c[3][1], M.c[3][2]);
+			if (P.hasReady)
+			{
+				for (uint32_t v = 0; v < P.viewCount; v++)
+					if ((mask >> v) & 1u)
+						atomicAdd(&sh.inst[v], readyCount);
+			}
 		}
+		sh.maskOf[owner] = (uint16_t)mask;
 	}
-	// isVisible of the (last) main view, written for every slot like mesh.cpp:144-146,152-153,161-167
-	if (A.visibleView != kNone && inRange)
-		A.visible[slot] = (uint8_t)((mask >> A.visibleView) & 1u);
+	__syncthreads();
 
-	// ---- visibility bits: one ballot word per warp and view, plus the tile's visible count per view ----
-	// (no inter-tile dependency in this kernel: list positions are assigned by kScanTiles + kScatter below)
-	for (uint32_t v = 0; v < P.viewCount; v++)
+	// ---- back to slot order: isVisible, one ballot word per 32 slots and view, the tile's visible count per view ----
+	// (no inter-tile dependency in this kernel: list positions are assigned by kScanChunks + kScatter below)
+	#pragma unroll
+	for (uint32_t r = 0; r < kCullItems; r++)
 	{
-		const uint32_t b = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
-		if (lane == 0)
-		{
-			A.visBits[((size_t)v * A.tiles + tile) * (kCullTile / 32) + warp] = b;
-			if (b)
-				atomicAdd(&sh.total[v], (uint32_t)__popc(b));
-		}
-	}
-	if (P.hasReady)
-	{
+		const uint32_t own = threadIdx.x + r * kCullThreads;
+		const uint32_t slot = tile * kCullTile + own;
+		const uint32_t mask = sh.maskOf[own];
+		// isVisible of the (last) main view, written for every slot like mesh.cpp:144-146,152-153,161-167
+		if (A.visibleView != kNone && slot < P.occupancy)
+			A.visible[slot] = (uint8_t)((mask >> A.visibleView) & 1u);
+		uint32_t mine = 0; // lane v keeps the ballot word of view v
 		for (uint32_t v = 0; v < P.viewCount; v++)
-			if ((mask >> v) & 1u)
-				atomicAdd(&sh.inst[v], readyCount);
+		{
+			const uint32_t b = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
+			if (lane == v) mine = b;
+		}
+		if (lane < P.viewCount)
+		{
+			A.visBits[((size_t)lane * A.tiles + tile) * (kCullTile / 32) + (own >> 5)] = mine;
+			if (mine)
+				atomicAdd(&sh.total[lane], (uint32_t)__popc(mine));
+		}
 	}
 	__syncthreads();
 	if (threadIdx.x < P.viewCount)
 	{
 		const uint32_t v = threadIdx.x;
-		A.tileCount[(size_t)v * A.tiles + tile] = sh.total[v];
+		if (sh.total[v]) // visible slots per chunk of kChunkTiles tiles: the only cross-tile quantity the compaction needs
+			atomicAdd(&A.chunkCount[(size_t)v * A.chunks + tile / kChunkTiles], sh.total[v]);
 		if (P.hasReady && sh.inst[v])
 			atomicAdd(&A.counters[ctrPoolInst(P.poolIndex, v)], sh.inst[v]);
 	}
 }
 
-// Exclusive scan of the per-tile visible counts of one view (one block per view) -> list offset of every tile.
+// Exclusive scan of the per-chunk visible counts of one view (one block per view) -> list offset of every chunk.
 // Also publishes the list length after this pool (poolEnd), which is the draw count the host reads back.
 constexpr uint32_t kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) kScanTiles(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+__global__ void __launch_bounds__(kScanThreads) kScanChunks(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
 {
 	const uint32_t v = blockIdx.x;
 	if (!P.views[v].enabled)
 		return;
 	__shared__ uint32_t sWarp[kScanThreads / 32];
-	uint32_t* counts = A.tileCount + (size_t)v * A.tiles;
-	const uint32_t per = (A.tiles + kScanThreads - 1) / kScanThreads;
-	const uint32_t begin = min(threadIdx.x * per, A.tiles), end = min(begin + per, A.tiles);
-	uint32_t sum = 0;
-	for (uint32_t i = begin; i < end; i++)
-		sum += counts[i];
-	// block exclusive scan of the per-thread sums
+	__shared__ uint32_t sCarry;
+	uint32_t* counts = A.chunkCount + (size_t)v * A.chunks;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t inc = sum;
+	if (threadIdx.x == 0)
+		sCarry = A.baseCounter[v] != kNone ? A.counters[A.baseCounter[v]] : 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < A.chunks; base += kScanThreads)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t c = i < A.chunks ? counts[i] : 0;
+		uint32_t inc = c;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc += t;
+		}
+		if (lane == 31)
+			sWarp[warp] = inc;
+		__syncthreads();
+		if (warp == 0)
+		{
+			uint32_t w = sWarp[lane], winc = w;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+				if (lane >= (uint32_t)o) winc += t;
+			}
+			sWarp[lane] = winc - w;
+		}
+		__syncthreads();
+		const uint32_t carry = sCarry;
+		const uint32_t exclusive = carry + sWarp[warp] + inc - c;
+		if (i < A.chunks)
+			counts[i] = exclusive;
+		__syncthreads();
+		if (threadIdx.x == kScanThreads - 1)
+			sCarry = exclusive + c;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		A.counters[ctrPoolEnd(P.poolIndex, v)] = sCarry;
+}
+
+// Compaction + key. One block per (chunk, view): thread i owns ballot word i of the chunk (32 slots); a block scan of
+// the popcounts gives each word its list offset, then every set bit becomes one (key, payload) entry. Lists come out in
+// slot order, so the stable radix sort breaks ties by slot.
+__global__ void __launch_bounds__(kChunkWords) kScatter(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+{
+	const uint32_t v = blockIdx.y;
+	const ViewConst& V = P.views[v];
+	if (!V.enabled)
+		return;
+	__shared__ uint32_t sWarp[kChunkWords / 32];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t chunk = blockIdx.x;
+	const uint32_t wordIndex = chunk * kChunkWords + threadIdx.x;
+	const uint32_t words = A.tiles * (kCullTile / 32);
+	uint32_t word = wordIndex < words ? A.visBits[(size_t)v * words + wordIndex] : 0;
+	const uint32_t cnt = __popc(word);
+	uint32_t inc = cnt;
 	#pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
 	{
@@ -350,77 +509,31 @@ __global__ void __launch_bounds__(kScanThreads) kScanTiles(const __grid_constant
 	if (lane == 31)
 		sWarp[warp] = inc;
 	__syncthreads();
-	if (warp == 0)
+	uint32_t before = 0;
+	#pragma unroll
+	for (uint32_t w = 0; w < kChunkWords / 32; w++)
+		if (w < warp) before += sWarp[w];
+	uint32_t pos = A.chunkCount[(size_t)v * A.chunks + chunk] + before + inc - cnt;
+	uint32_t* keys = A.keys + A.segOffset[v];
+	uint32_t* pays = A.payloads + A.segOffset[v];
+	const float ox = V.cameraOffset[0], oy = V.cameraOffset[1], oz = V.cameraOffset[2];
+	while (word)
 	{
-		uint32_t w = sWarp[lane];
-		uint32_t winc = w;
-		#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-			if (lane >= (uint32_t)o) winc += t;
-		}
-		sWarp[lane] = winc - w;
-	}
-	__syncthreads();
-	const uint32_t listBase = A.baseCounter[v] != kNone ? A.counters[A.baseCounter[v]] : 0;
-	uint32_t running = listBase + sWarp[warp] + inc - sum;
-	for (uint32_t i = begin; i < end; i++)
-	{
-		const uint32_t c = counts[i];
-		counts[i] = running;
-		running += c;
-	}
-	if (threadIdx.x == kScanThreads - 1)
-		A.counters[ctrPoolEnd(P.poolIndex, v)] = running;
-}
-
-// Compaction + key: every visible (slot, view) pair gets its position from the tile offset, the popcounts of the
-// preceding warps' ballot words and its rank inside its own word -> lists come out in slot order (stable tie-break).
-__global__ void __launch_bounds__(kCullTile) kScatter(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
-{
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t tile = blockIdx.x;
-	const uint32_t slot = tile * kCullTile + threadIdx.x;
-	const uint32_t payload = (P.poolIndex << 28) | slot;
-	bool loaded = false;
-	float c3x = 0.0f, c3y = 0.0f, c3z = 0.0f;
-	for (uint32_t v = 0; v < P.viewCount; v++)
-	{
-		const ViewConst& V = P.views[v];
-		if (!V.enabled)
-			continue;
-		uint32_t w = 0;
-		if (lane < kCullTile / 32)
-			w = A.visBits[((size_t)v * A.tiles + tile) * (kCullTile / 32) + lane];
-		const uint32_t mine = __shfl_sync(0xffffffffu, w, warp);
-		if (mine == 0)
-			continue; // warp-uniform
-		uint32_t before = lane < warp ? __popc(w) : 0;
-		#pragma unroll
-		for (int o = 4; o > 0; o >>= 1)
-			before += __shfl_xor_sync(0xffffffffu, before, o);
-		before = __shfl_sync(0xffffffffu, before, 0);
-		if (!((mine >> lane) & 1u))
-			continue;
-		if (!loaded)
-		{
-			const float4 w2 = A.world[(size_t)slot * 3 + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
-			c3x = w2.y; c3y = w2.z; c3z = w2.w;
-			loaded = true;
-		}
-		const uint32_t pos = A.tileCount[(size_t)v * A.tiles + tile] + before + __popc(mine & ((1u << lane) - 1u));
+		const uint32_t bit = __ffs(word) - 1;
+		word &= word - 1;
+		const uint32_t slot = wordIndex * 32 + bit;
+		const float4 w2 = A.world[(size_t)slot * 3 + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
 		float key;
 		if (P.key2D)
-			key = __fadd_rn(c3z, 1.0f); // mesh.cpp:250
+			key = __fadd_rn(w2.w, 1.0f); // mesh.cpp:250
 		else
-			key = lengthSq3(__fadd_rn(c3x, V.cameraOffset[0]), __fadd_rn(c3y, V.cameraOffset[1]),
-				__fadd_rn(c3z, V.cameraOffset[2])); // mesh.cpp:172,251
+			key = lengthSq3(__fadd_rn(w2.y, ox), __fadd_rn(w2.z, oy), __fadd_rn(w2.w, oz)); // mesh.cpp:172,251
 		uint32_t k = floatToOrdered(key);
 		if (P.descending)
 			k = ~k;
-		A.keys[A.segOffset[v] + pos] = k;
-		A.payloads[A.segOffset[v] + pos] = payload;
+		keys[pos] = k;
+		pays[pos] = (P.poolIndex << 28) | slot;
+		pos++;
 	}
 }
 
@@ -449,11 +562,16 @@ uint32_t launchCull(Context& c, uint32_t pool)
 		V.planeCount = isUI ? gv.uiPlaneCount : gv.planeCount;
 		for (uint32_t i = 0; i < 6; i++)
 		{
-			const float* pl = V.planes[i];
+			float* pl = V.planes[i];
+			if (i >= V.planeCount) // neutral plane: always classified "in front", never examined by the exact test
+			{
+				pl[0] = pl[1] = pl[2] = 0.0f; pl[3] = 1.0f;
+				V.planeL2[i] = 0.0f; V.planeAbsD[i] = 0.0f;
+				continue;
+			}
 			// rounded up a little: these only widen the band in which the exact test is used
 			V.planeL2[i] = sqrtf(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2]) * 1.0001f;
-			V.planeL1[i] = (fabsf(pl[0]) + fabsf(pl[1]) + fabsf(pl[2])) * (2.0f * kBandScale);
-			V.planeAbsD[i] = fabsf(pl[3]) * (2.0f * kBandScale);
+			V.planeAbsD[i] = fabsf(pl[3]) * kBandD * 1.0001f;
 		}
 		memcpy(V.cameraOffset, gv.cameraOffset, sizeof(V.cameraOffset));
 		A.segOffset[v] = c.segments[seg].offset;
@@ -476,14 +594,33 @@ uint32_t launchCull(Context& c, uint32_t pool)
 	A.tRot = c.tf.rot; A.tPosSx = c.tf.posSx; A.tSYZ = c.tf.sYZ; A.tParent = c.tf.parent; A.tFlags = c.tf.flags;
 	A.aabbA = p.aabbA; A.aabbB = p.aabbB; A.tslot = p.tslot; A.mflags = p.flags; A.ready = p.ready;
 	A.world = p.world; A.visible = p.visible;
-	A.visBits = p.visBits; A.tileCount = p.cullStatus; A.counters = c.dCounters;
+	A.visBits = p.visBits; A.chunkCount = p.cullStatus; A.counters = c.dCounters;
 	A.keys = c.keys[0]; A.payloads = c.payloads[0];
 	A.tiles = (p.occupancy + kCullTile - 1) / kCullTile;
+	A.chunks = (A.tiles + kChunkTiles - 1) / kChunkTiles;
 	p.visibleValid = A.visibleView != kNone;
 
-	kCull<<<A.tiles, kCullTile, 0, c.stream>>>(P, A);
-	kScanTiles<<<P.viewCount, kScanThreads, 0, c.stream>>>(P, A);
-	kScatter<<<A.tiles, kCullTile, 0, c.stream>>>(P, A);
+	static bool carveoutSet = false;
+	if (!carveoutSet) // 4 resident blocks x 37 KB of shared memory need the large carve-out
+	{
+		cudaFuncSetAttribute(kCull<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(kCull<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(kCull<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(kCull<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(kCull<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(kCull<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		carveoutSet = true;
+	}
+	cudaMemsetAsync(p.cullStatus, 0, (size_t)A.chunks * kMaxViews * sizeof(uint32_t), c.stream);
+	// the view loop is unrolled at compile time (plane constants become direct constant-bank operands)
+	if (P.viewCount <= 1) kCull<1><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	else if (P.viewCount <= 2) kCull<2><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	else if (P.viewCount <= 4) kCull<4><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	else if (P.viewCount <= 6) kCull<6><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	else if (P.viewCount <= 8) kCull<8><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	else kCull<16><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	kScanChunks<<<P.viewCount, kScanThreads, 0, c.stream>>>(P, A);
+	kScatter<<<dim3(A.chunks, P.viewCount), kChunkWords, 0, c.stream>>>(P, A);
 	return 3;
 }
 

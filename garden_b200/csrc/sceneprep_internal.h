@@ -24,6 +24,7 @@ constexpr uint32_t kMcEntity = 0, kMcEnabled = 14, kMcVisible = 15, kMcAabbMin =
 
 // transform flags (SoA)
 constexpr uint8_t kTfLive = 1, kTfActive = 2, kTfAncestors = 4;
+constexpr uint32_t kTfDepthShift = 3; // bits 3..7: chain length capped at 31 (work-balancing hint only)
 // mesh flags (SoA): static filter of mesh.cpp:140-147 (entity != 0 && isEnabled && !degenerate AABB)
 constexpr uint8_t kMfCandidate = 1;
 
@@ -65,7 +66,6 @@ struct ViewConst
 {
 	float planes[6][4];
 	float planeL2[6];    // |n|_2, rounded up
-	float planeL1[6];    // |n|_1 * band scale
 	float planeAbsD[6];  // |d| * band scale
 	float cameraOffset[4];
 	uint32_t planeCount;

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(256) kStageTransforms(const uint8_t* __restric
 	if (e) f |= kTfLive;
 	if ((w & 0xffu) && (w & 0xff00u)) f |= kTfActive;   // isActive(), transform.hpp:110
 	if (w & 0xff0000u) f |= kTfAncestors;                // modelWithAncestors, transform.hpp:60,200
-	flags[slot] = f;
+	// bits 3..7 hold the chain length (kComputeDepth); a TRS-only update keeps them
+	flags[slot] = full ? f : (uint8_t)(f | (flags[slot] & ~((1u << kTfDepthShift) - 1u)));
 	if (full)
 	{
 		entity[slot] = e;
@@ -72,6 +73,23 @@ __global__ void __launch_bounds__(256) kResolveParents(uint32_t count, const uin
 		else atomicExch(error, (uint32_t)GSP_ERR_HIERARCHY);
 	}
 	parent[i] = p;
+}
+
+// Chain length of every transform (number of ancestors, capped at 31) into flag bits 3..7. The cull kernel only uses it
+// to group work of equal chain length into the same warp; correctness never depends on it.
+__global__ void __launch_bounds__(256) kComputeDepth(uint32_t count, const uint32_t* __restrict__ parent, uint8_t* __restrict__ flags)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	uint32_t depth = 0;
+	uint32_t p = parent[i];
+	while (p != kNone && depth < 31)
+	{
+		depth++;
+		p = parent[p];
+	}
+	flags[i] = (uint8_t)((flags[i] & ((1u << kTfDepthShift) - 1u)) | (depth << kTfDepthShift));
 }
 
 // One thread per mesh-component slot: AABB, owner entity and the static part of the filter at mesh.cpp:140-147.
@@ -120,7 +138,8 @@ uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, ui
 	{
 		kResolveParents<<<blocksFor(count, 256), 256, 0, c.stream>>>(count, t.parentEntity, t.entityToSlot, t.entityCap,
 			t.parent, c.dError);
-		n++;
+		kComputeDepth<<<blocksFor(count, 256), 256, 0, c.stream>>>(count, t.parent, t.flags);
+		n += 2;
 	}
 	return n;
 }
