@@ -10,6 +10,7 @@
 // then reads a tile once, ranks it in shared memory, resolves the tile's global digit offsets with a decoupled look-back
 // over the preceding tiles and scatters. Per element traffic: 4 B (histogram) + 4 x (8 B read + 8 B write).
 #include "sceneprep_internal.h"
+#include <algorithm>
 
 namespace gsp
 {
@@ -27,6 +28,7 @@ struct SortArgs
 	uint32_t* __restrict__ tickets;        // [segment][pass]
 	const uint32_t* __restrict__ segTileOffset; // first status tile of each segment
 	uint32_t tilesTotal;                   // status tiles per pass
+	uint32_t segmentCountTotal;            // number of segments
 };
 
 __device__ __forceinline__ uint32_t segmentCount(const SortArgs& a, const SegmentDev& s)
@@ -39,9 +41,11 @@ __device__ __forceinline__ uint32_t ldRelaxed(const uint32_t* p)
 	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v)
+// The status word is the only thing a successor tile reads from this tile, so a relaxed store is enough. (A release
+// store would first drain this thread's scattered output stores of the previous tile and delay the publication.)
+__device__ __forceinline__ void stRelaxed(uint32_t* p, uint32_t v)
 {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
 // Up-front histogram of all 4 digits; also clears the look-back status words of the tile for all 4 passes.
@@ -104,126 +108,186 @@ __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* sWa
 	return offset + inc - v;
 }
 
-__global__ void __launch_bounds__(kSortThreads) kSortPass(const __grid_constant__ SortArgs A, uint32_t pass,
+constexpr uint32_t kLookbackBatch = 8; // predecessor tiles inspected per step (independent loads in flight)
+
+__global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_constant__ SortArgs A, uint32_t pass,
 	const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ payIn,
 	uint32_t* __restrict__ keysOut, uint32_t* __restrict__ payOut)
 {
-	const SegmentDev seg = A.segments[blockIdx.y];
-	const uint32_t count = segmentCount(A, seg);
-	if (!seg.sorted || blockIdx.x * kSortTile >= count)
-		return;
-
 	__shared__ uint32_t sKeys[kSortTile];
 	__shared__ uint32_t sPay[kSortTile];
 	__shared__ uint32_t sWarpHist[kWarps][kRadix];
 	__shared__ uint32_t sBinStart[kRadix];  // tile-local exclusive start of each digit
 	__shared__ int32_t sGlobal[kRadix];     // global position = sGlobal[d] + local index
 	__shared__ uint32_t sWarpTotals[kWarps];
-	__shared__ uint32_t sTile;
+	__shared__ uint32_t sSegTileEnd[kMaxViews * kMaxPools]; // inclusive prefix of tiles over the segments
+	__shared__ uint32_t sWork[2];           // claimed (segment, tile)
 
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t shift = pass * kRadixBits;
+	const uint32_t d = threadIdx.x; // the digit this thread owns in the per-digit phases
+
+	// Tiles of ALL segments form one ticket space (segment lengths differ by orders of magnitude between a near cascade and
+	// the main view, so per-segment grids would leave most blocks idle). Tickets are claimed in order => within a segment
+	// tiles start in order and the look-back never waits on a tile that has not been claimed.
 	if (threadIdx.x == 0)
-		sTile = atomicAdd(&A.tickets[blockIdx.y * kPasses + pass], 1u);
-	for (uint32_t i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads)
-		(&sWarpHist[0][0])[i] = 0;
-	__syncthreads();
-	const uint32_t tile = sTile;
-	const uint32_t base = tile * kSortTile;
-	const uint32_t n = min(kSortTile, count - base);
-	const uint32_t* kin = keysIn + seg.offset + base;
-	const uint32_t* pin = payIn + seg.offset + base;
-
-	// ---- load (warp-striped: tile order = warp, item, lane) and rank within the warp, in order ----
-	uint32_t key[kSortItems], pay[kSortItems], rank[kSortItems];
-	#pragma unroll
-	for (uint32_t i = 0; i < kSortItems; i++)
 	{
-		uint32_t idx = warp * (kSortItems * 32) + i * 32 + lane;
-		key[i] = idx < n ? kin[idx] : 0xFFFFFFFFu; // padding ranks after every real key of the tile
-		pay[i] = idx < n ? pin[idx] : 0u;
-	}
-	#pragma unroll
-	for (uint32_t i = 0; i < kSortItems; i++)
-	{
-		const uint32_t d = (key[i] >> shift) & (kRadix - 1);
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
-		const uint32_t leader = __ffs(peers) - 1;
-		uint32_t pre = 0;
-		if (lane == leader)
+		uint32_t running = 0;
+		for (uint32_t i = 0; i < A.segmentCountTotal; i++)
 		{
-			pre = sWarpHist[warp][d];
-			sWarpHist[warp][d] = pre + __popc(peers);
+			const SegmentDev sg = A.segments[i];
+			const uint32_t c = sg.sorted ? segmentCount(A, sg) : 0u;
+			running += (c + kSortTile - 1) / kSortTile;
+			sSegTileEnd[i] = running;
 		}
-		pre = __shfl_sync(0xffffffffu, pre, leader);
-		rank[i] = pre + __popc(peers & ((1u << lane) - 1u));
-		__syncwarp();
 	}
 	__syncthreads();
+	const uint32_t totalTiles = sSegTileEnd[A.segmentCountTotal - 1];
 
-	// ---- per digit (thread d owns digit d): warp offsets, tile count, global offset by look-back ----
-	const uint32_t d = threadIdx.x;
-	uint32_t tileCount = 0;
-	#pragma unroll
-	for (uint32_t w = 0; w < kWarps; w++)
+	while (true)
 	{
-		uint32_t c = sWarpHist[w][d];
-		sWarpHist[w][d] = tileCount;
-		tileCount += c;
-	}
-	const uint32_t binStart = blockExclusiveScan(tileCount, sWarpTotals);
-	// global exclusive start of digit d in this pass = exclusive scan of the segment histogram
-	const uint32_t histD = A.hist[((size_t)blockIdx.y * kPasses + pass) * kRadix + d];
-	const uint32_t digitBase = blockExclusiveScan(histD, sWarpTotals);
-
-	// padding keys (digit 255 in every pass) are excluded from what is published to other tiles
-	uint32_t realCount = tileCount;
-	if (d == kRadix - 1)
-		realCount -= kSortTile - n;
-	uint32_t* st = A.status + ((size_t)pass * A.tilesTotal + A.segTileOffset[blockIdx.y] + tile) * kRadix + d;
-	uint32_t exclusive = 0;
-	if (tile == 0)
-		stRelease(st, kFlagInclusive | realCount);
-	else
-	{
-		stRelease(st, kFlagAggregate | realCount);
-		int32_t t = (int32_t)tile - 1;
-		while (true)
+		__syncthreads();
+		if (threadIdx.x == 0)
 		{
-			const uint32_t* ps = st - (size_t)(tile - (uint32_t)t) * kRadix;
-			uint32_t s;
-			do { s = ldRelaxed(ps); } while ((s & ~kValueMask) == 0);
-			exclusive += s & kValueMask;
-			if (s & kFlagInclusive)
-				break;
-			t--;
+			const uint32_t g = atomicAdd(&A.tickets[pass], 1u);
+			uint32_t sgi = 0;
+			if (g < totalTiles)
+				while (sSegTileEnd[sgi] <= g) sgi++;
+			sWork[0] = g < totalTiles ? sgi : kNone;
+			sWork[1] = g - (sgi ? sSegTileEnd[sgi - 1] : 0u);
 		}
-		stRelease(st, kFlagInclusive | (exclusive + realCount));
-	}
-	sBinStart[d] = binStart;
-	sGlobal[d] = (int32_t)(digitBase + exclusive) - (int32_t)binStart;
-	__syncthreads();
+		for (uint32_t i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads)
+			(&sWarpHist[0][0])[i] = 0;
+		__syncthreads();
+		const uint32_t segIndex = sWork[0];
+		if (segIndex == kNone)
+			break;
+		const uint32_t tile = sWork[1];
+		const SegmentDev seg = A.segments[segIndex];
+		const uint32_t count = segmentCount(A, seg);
+		uint32_t* statusBase = A.status + ((size_t)pass * A.tilesTotal + A.segTileOffset[segIndex]) * kRadix + d;
+		// global exclusive start of digit d in this pass = exclusive scan of the segment histogram
+		const uint32_t histD = A.hist[((size_t)segIndex * kPasses + pass) * kRadix + d];
+		const uint32_t base = tile * kSortTile;
+		const uint32_t n = min(kSortTile, count - base);
+		const uint32_t* kin = keysIn + seg.offset + base;
+		const uint32_t* pin = payIn + seg.offset + base;
 
-	// ---- scatter into shared memory in digit order, then write runs out ----
-	#pragma unroll
-	for (uint32_t i = 0; i < kSortItems; i++)
-	{
-		const uint32_t dg = (key[i] >> shift) & (kRadix - 1);
-		const uint32_t local = sBinStart[dg] + sWarpHist[warp][dg] + rank[i];
-		sKeys[local] = key[i];
-		sPay[local] = pay[i];
-	}
-	__syncthreads();
-	uint32_t* kout = keysOut + seg.offset;
-	uint32_t* pout = payOut + seg.offset;
-	#pragma unroll 4
-	for (uint32_t j = threadIdx.x; j < n; j += kSortThreads)
-	{
-		const uint32_t k = sKeys[j];
-		const uint32_t dg = (k >> shift) & (kRadix - 1);
-		const uint32_t pos = (uint32_t)(sGlobal[dg] + (int32_t)j);
-		kout[pos] = k;
-		pout[pos] = sPay[j];
+		// ---- load (warp-striped: tile order = warp, item, lane) and rank within the warp, in order ----
+		uint32_t key[kSortItems], pay[kSortItems], rank[kSortItems];
+		#pragma unroll
+		for (uint32_t i = 0; i < kSortItems; i++)
+		{
+			uint32_t idx = warp * (kSortItems * 32) + i * 32 + lane;
+			key[i] = idx < n ? kin[idx] : 0xFFFFFFFFu; // padding ranks after every real key of the tile
+			pay[i] = idx < n ? pin[idx] : 0u;
+		}
+		// lanes holding the same digit ("peers"): eight ballots, one per digit bit (cheaper than match.any here, and all
+		// sixteen items' masks are independent, so they pipeline)
+		uint32_t peerMask[kSortItems];
+		#pragma unroll
+		for (uint32_t i = 0; i < kSortItems; i++)
+		{
+			const uint32_t dg = (key[i] >> shift) & (kRadix - 1);
+			uint32_t peers = 0xffffffffu;
+			#pragma unroll
+			for (uint32_t b = 0; b < kRadixBits; b++)
+			{
+				const uint32_t vote = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
+				peers &= ((dg >> b) & 1u) ? vote : ~vote;
+			}
+			peerMask[i] = peers;
+		}
+		#pragma unroll
+		for (uint32_t i = 0; i < kSortItems; i++)
+		{
+			const uint32_t dg = (key[i] >> shift) & (kRadix - 1);
+			const uint32_t peers = peerMask[i];
+			const uint32_t leader = __ffs(peers) - 1;
+			uint32_t pre = 0;
+			if (lane == leader)
+			{
+				pre = sWarpHist[warp][dg];
+				sWarpHist[warp][dg] = pre + __popc(peers);
+			}
+			pre = __shfl_sync(0xffffffffu, pre, leader);
+			rank[i] = pre + __popc(peers & ((1u << lane) - 1u));
+			__syncwarp();
+		}
+		__syncthreads();
+
+		// ---- per digit (thread d owns digit d): warp offsets, tile count, global offset by look-back ----
+		uint32_t tileCount = 0;
+		#pragma unroll
+		for (uint32_t w = 0; w < kWarps; w++)
+		{
+			uint32_t c = sWarpHist[w][d];
+			sWarpHist[w][d] = tileCount;
+			tileCount += c;
+		}
+		// padding keys (digit 255 in every pass) are excluded from what is published to other tiles
+		uint32_t realCount = tileCount;
+		if (d == kRadix - 1)
+			realCount -= kSortTile - n;
+		uint32_t* st = statusBase + (size_t)tile * kRadix;
+		stRelaxed(st, (tile == 0 ? kFlagInclusive : kFlagAggregate) | realCount);
+		const uint32_t binStart = blockExclusiveScan(tileCount, sWarpTotals);
+		const uint32_t digitBase = blockExclusiveScan(histD, sWarpTotals);
+
+		uint32_t exclusive = 0;
+		if (tile != 0)
+		{
+			int32_t t = (int32_t)tile - 1;
+			bool done = false;
+			while (!done)
+			{
+				uint32_t sv[kLookbackBatch];
+				#pragma unroll
+				for (uint32_t j = 0; j < kLookbackBatch; j++)
+				{
+					const int32_t idx = t - (int32_t)j;
+					sv[j] = idx >= 0 ? ldRelaxed(statusBase + (size_t)idx * kRadix) : kFlagInclusive;
+				}
+				#pragma unroll
+				for (uint32_t j = 0; j < kLookbackBatch; j++)
+				{
+					if (!done)
+					{
+						while ((sv[j] & ~kValueMask) == 0)
+							sv[j] = ldRelaxed(statusBase + (size_t)(t - (int32_t)j) * kRadix);
+						exclusive += sv[j] & kValueMask;
+						done = (sv[j] & kFlagInclusive) != 0;
+					}
+				}
+				t -= (int32_t)kLookbackBatch;
+			}
+			stRelaxed(st, kFlagInclusive | (exclusive + realCount));
+		}
+		sBinStart[d] = binStart;
+		sGlobal[d] = (int32_t)(digitBase + exclusive) - (int32_t)binStart;
+		__syncthreads();
+
+		// ---- scatter into shared memory in digit order, then write runs out ----
+		#pragma unroll
+		for (uint32_t i = 0; i < kSortItems; i++)
+		{
+			const uint32_t dg = (key[i] >> shift) & (kRadix - 1);
+			const uint32_t local = sBinStart[dg] + sWarpHist[warp][dg] + rank[i];
+			sKeys[local] = key[i];
+			sPay[local] = pay[i];
+		}
+		__syncthreads();
+		uint32_t* kout = keysOut + seg.offset;
+		uint32_t* pout = payOut + seg.offset;
+		#pragma unroll 4
+		for (uint32_t j = threadIdx.x; j < n; j += kSortThreads)
+		{
+			const uint32_t k = sKeys[j];
+			const uint32_t dg = (k >> shift) & (kRadix - 1);
+			const uint32_t pos = (uint32_t)(sGlobal[dg] + (int32_t)j);
+			kout[pos] = k;
+			pout[pos] = sPay[j];
+		}
 	}
 }
 
@@ -251,16 +315,22 @@ uint32_t launchSort(Context& c, cudaEvent_t afterHistogram)
 	SortArgs A;
 	A.segments = c.dSegments; A.counters = c.dCounters; A.hist = c.sortHist; A.status = c.sortStatus;
 	A.tickets = c.sortTickets; A.segTileOffset = c.segTileOffset; A.tilesTotal = c.sortTilesTotal;
+	A.segmentCountTotal = nseg;
 	cudaMemsetAsync(c.sortHist, 0, (size_t)nseg * kPasses * kRadix * sizeof(uint32_t), c.stream);
 	cudaMemsetAsync(c.sortTickets, 0, (size_t)nseg * kPasses * sizeof(uint32_t), c.stream);
 	dim3 grid(maxTiles, nseg);
+	// sort passes are persistent (tiles claimed by ticket): 3 resident blocks per SM, split over the segments
+	uint32_t totalCapTiles = 0;
+	for (auto& sgm : c.segments)
+		if (sgm.sorted) totalCapTiles += (sgm.capacity + kSortTile - 1) / kSortTile;
+	dim3 passGrid(std::min<uint32_t>(totalCapTiles, 148u * 3u));
 	kSortHistogram<<<grid, kSortThreads, 0, c.stream>>>(A, c.keys[0]);
 	if (afterHistogram) cudaEventRecord(afterHistogram, c.stream);
 	uint32_t launches = 1;
 	for (uint32_t pass = 0; pass < kPasses; pass++)
 	{
 		const uint32_t in = pass & 1, out = in ^ 1;
-		kSortPass<<<grid, kSortThreads, 0, c.stream>>>(A, pass, c.keys[in], c.payloads[in], c.keys[out], c.payloads[out]);
+		kSortPass<<<passGrid, kSortThreads, 0, c.stream>>>(A, pass, c.keys[in], c.payloads[in], c.keys[out], c.payloads[out]);
 		launches++;
 	}
 	return launches; // 4 passes: sorted data ends in buffer 0
