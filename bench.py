@@ -61,7 +61,7 @@ def load_peaks():
 
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device_index)],
+                                          "-lms", "20", "-i", str(self.device_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -81,15 +81,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout: float = 5.0):
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin: float = 0.0, t_end: float = 1e300):
+        """Summary of the samples whose arrival time lies inside [t_begin, t_end] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for row in self.rows:
+        inside = [row for t, row in self.rows if t_begin <= t <= t_end + 0.03]
+        for row in inside:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 9:
                 continue
@@ -202,7 +209,9 @@ def run_b200_arm(args):
     pool_pins = [pinned_like(m) for m in pools_np]
     del t_np, pools_np
 
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the library enqueues on it and torch.cuda.Event records on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sp = ScenePrep(local_rank)
     sp.set_stream(stream.cuda_stream)
 
@@ -217,7 +226,7 @@ def run_b200_arm(args):
     merger = None
     if world > 1:
         from garden_b200.dist import RunMerger
-        merger = RunMerger(sp, views.size, len(pool_pins), rts)
+        merger = RunMerger(sp)
 
     def frame():
         sp.run_async()
@@ -237,22 +246,25 @@ def run_b200_arm(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         frame()
     ev1.record(stream)
     sp.sync()
     barrier()
+    t_end = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches_per_step = sp.last_launch_count() + (merger.launches_per_frame if merger else 0)
     visible_total = sp.last_visible_total()
 
     # ---- per-kernel-group timing (CUDA events on the same stream, inside the library) ----
     sp.set_profiling(True)
-    phase = np.zeros(5)
+    phase = np.zeros(6)
     prof_steps = max(3, min(args.steps, 10))
     for _ in range(prof_steps):
         sp.run()
@@ -305,12 +317,14 @@ def run_b200_arm(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         alg_bytes = BYTES_PER_ENTITY * n + BYTES_PER_VISIBLE * visible_total  # per GPU
-        names = ["link", "cull+compact (kCull)", "sort histogram (kSortHistogram)", "sort passes (kSortPass x4)",
-                 "record emission (kEmit)"]
-        kernel_bytes = [0, 75 * n + 8 * visible_total, 4 * visible_total, 64 * visible_total, (8 + 48 + 64) * visible_total]
+        names = ["link", "world matrices + culling (kCull)", "compaction + keys (kScanChunks + kScatter)",
+                 "sort histogram (kSortHistogram)", "sort passes (kSortPass x4)", "record emission (kEmit)"]
+        # algorithmic bytes attributed to each kernel group; they add up to 75*N + 132*SumVis:
+        # inputs + isVisible | nothing counted (fusable) | 4 B key read | 4 x (8 read + 8 write) | 64 B record write
+        kernel_bytes = [0, 75 * n, 0, 4 * visible_total, 64 * visible_total, 64 * visible_total]
         frame_ms = float(phase.sum())
         kernels = []
-        for i in range(1, 5):
+        for i in range(1, 6):
             ms = float(phase[i])
             gbs = kernel_bytes[i] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             kernels.append({"name": names[i], "ms": round(ms, 4), "share": round(ms / frame_ms, 3) if frame_ms else 0,
@@ -353,7 +367,7 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))

@@ -43,6 +43,10 @@ SYMBOLS = {
     "gsp_get_unsorted_device": (_i32, [_vp, _u32, _u32, _pp, _pu32, _pu32]),
     "gsp_get_sorted_device": (_i32, [_vp, _u32, _i32, _pp, _pu32]),
     "gsp_get_sorted_run_device": (_i32, [_vp, _u32, _i32, _u32, _pp, _pp, _pu32]),
+    "gsp_list_count": (_u32, [_vp]),
+    "gsp_get_list_counts": (_i32, [_vp, _vp, _u32]),
+    "gsp_export_runs": (_i32, [_vp, _vp, _vp, _u32]),
+    "gsp_merge_gathered": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),
     "gsp_download_models": (_i32, [_vp, _u32, _vp]),
     "gsp_set_profiling": (_i32, [_vp, _i32]),
@@ -193,6 +197,18 @@ class ScenePrep:
                                                        C.byref(count)))
         return keys.value, pays.value, count.value
 
+    def list_count(self) -> int:
+        return self.lib.gsp_list_count(self.h)
+
+    def list_counts(self) -> np.ndarray:
+        n = self.list_count()
+        counts = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.lib.gsp_get_list_counts(self.h, counts.ctypes.data, counts.size))
+        return counts[:n]
+
+    def export_runs(self, d_keys: int, d_payloads: int, capacity: int):
+        self._check(self.lib.gsp_export_runs(self.h, d_keys, d_payloads, capacity))
+
     def writeback_visible(self, pool: int, aos, stride: int):
         self._check(self.lib.gsp_writeback_visible(self.h, pool, _ptr(aos), stride))
 
@@ -205,7 +221,7 @@ class ScenePrep:
         self._check(self.lib.gsp_set_profiling(self.h, 1 if enabled else 0))
 
     def phase_times(self) -> np.ndarray:
-        ms = np.zeros(5, dtype=np.float32)
+        ms = np.zeros(6, dtype=np.float32)
         self._check(self.lib.gsp_get_phase_times(self.h, ms.ctypes.data))
         return ms
 

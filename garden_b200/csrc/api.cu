@@ -133,8 +133,13 @@ void gsp_destroy(gsp_context* ctx)
 	cudaFree(c.segTileOffset); cudaFree(c.dAosScratch);
 	cudaFreeHost(c.hCounters); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible);
 	if (c.phaseEventsCreated)
+	{
 		for (auto& e : c.phaseEvents)
 			cudaEventDestroy(e);
+		for (auto& pe : c.poolEvents)
+			for (auto& e : pe)
+				cudaEventDestroy(e);
+	}
 	cudaStreamDestroy(c.ownStream);
 	delete ctx;
 }
@@ -491,6 +496,9 @@ int gsp_run_async(gsp_context* ctx)
 	{
 		for (auto& e : c.phaseEvents)
 			GSP_CUDA(cudaEventCreate(&e));
+		for (auto& pe : c.poolEvents)
+			for (auto& e : pe)
+				GSP_CUDA(cudaEventCreate(&e));
 		c.phaseEventsCreated = true;
 	}
 	if (prof) cudaEventRecord(c.phaseEvents[0], c.stream);
@@ -502,12 +510,11 @@ int gsp_run_async(gsp_context* ctx)
 	if (prof) cudaEventRecord(c.phaseEvents[1], c.stream);
 	GSP_CUDA(cudaMemsetAsync(c.dCounters, 0, kCtrCount * sizeof(uint32_t), c.stream));
 	for (uint32_t p = 0; p < c.poolCount; p++)
-		launches += launchCull(c, p);
-	if (prof) cudaEventRecord(c.phaseEvents[2], c.stream);
-	launches += launchSort(c, prof ? c.phaseEvents[3] : nullptr);
-	if (prof) cudaEventRecord(c.phaseEvents[4], c.stream);
+		launches += launchCull(c, p, prof ? c.poolEvents[p][0] : nullptr, prof ? c.poolEvents[p][1] : nullptr);
+	launches += launchSort(c, prof ? c.phaseEvents[2] : nullptr);
+	if (prof) cudaEventRecord(c.phaseEvents[3], c.stream);
 	launches += launchEmit(c);
-	if (prof) cudaEventRecord(c.phaseEvents[5], c.stream);
+	if (prof) cudaEventRecord(c.phaseEvents[4], c.stream);
 	c.phaseTimesValid = prof;
 	GSP_CUDA(cudaMemcpyAsync(c.hCounters, c.dCounters, kCtrCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaGetLastError());
@@ -712,6 +719,49 @@ int gsp_get_sorted_run_device(gsp_context* ctx, uint32_t view, int listKind, uin
 	return GSP_OK;
 }
 
+uint32_t gsp_list_count(const gsp_context* ctx)
+{
+	return (ctx && !ctx->c.layoutDirty) ? (uint32_t)ctx->c.segments.size() : 0;
+}
+
+int gsp_get_list_counts(gsp_context* ctx, uint32_t* counts, uint32_t capacity)
+{
+	if (!ctx || !counts)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (!c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	if (capacity < c.segments.size())
+		return fail(c, GSP_ERR_INVALID, "gsp_get_list_counts: capacity too small");
+	for (size_t i = 0; i < c.segments.size(); i++)
+		counts[i] = segmentCount(c, c.segments[i]);
+	return GSP_OK;
+}
+
+int gsp_export_runs(gsp_context* ctx, uint32_t* dKeys, uint32_t* dPayloads, uint32_t capacity)
+{
+	if (!ctx || !dKeys || !dPayloads)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (!c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	GSP_CUDA(cudaSetDevice(c.device));
+	uint64_t offset = 0;
+	for (auto& s : c.segments)
+	{
+		const uint32_t n = segmentCount(c, s);
+		if (offset + n > capacity)
+			return fail(c, GSP_ERR_INVALID, "gsp_export_runs: destination too small");
+		if (n)
+		{
+			GSP_CUDA(cudaMemcpyAsync(dKeys + offset, c.keys[0] + s.offset, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+			GSP_CUDA(cudaMemcpyAsync(dPayloads + offset, c.payloads[0] + s.offset, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+		}
+		offset += n;
+	}
+	return GSP_OK;
+}
+
 int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride)
 {
 	if (!ctx)
@@ -775,8 +825,22 @@ int gsp_get_phase_times(gsp_context* ctx, float* ms)
 	if (!c.phaseTimesValid || !c.resultsValid)
 		return GSP_OK;
 	GSP_CUDA(cudaSetDevice(c.device));
-	for (int i = 0; i < GSP_PHASE_COUNT; i++)
-		GSP_CUDA(cudaEventElapsedTime(&ms[i], c.phaseEvents[i], c.phaseEvents[i + 1]));
+	// link | per pool: cull, then scan + scatter | sort histogram | sort passes | emission
+	GSP_CUDA(cudaEventElapsedTime(&ms[0], c.phaseEvents[0], c.phaseEvents[1]));
+	cudaEvent_t prev = c.phaseEvents[1];
+	for (uint32_t p = 0; p < c.poolCount; p++)
+	{
+		if (!c.poolLaunched[p])
+			continue;
+		float a = 0.0f, b = 0.0f;
+		GSP_CUDA(cudaEventElapsedTime(&a, prev, c.poolEvents[p][0]));
+		GSP_CUDA(cudaEventElapsedTime(&b, c.poolEvents[p][0], c.poolEvents[p][1]));
+		ms[1] += a; ms[2] += b;
+		prev = c.poolEvents[p][1];
+	}
+	GSP_CUDA(cudaEventElapsedTime(&ms[3], prev, c.phaseEvents[2]));
+	GSP_CUDA(cudaEventElapsedTime(&ms[4], c.phaseEvents[2], c.phaseEvents[3]));
+	GSP_CUDA(cudaEventElapsedTime(&ms[5], c.phaseEvents[3], c.phaseEvents[4]));
 	return GSP_OK;
 }
 

@@ -537,9 +537,10 @@ __global__ void __launch_bounds__(kChunkWords) kScatter(const __grid_constant__ 
 	}
 }
 
-uint32_t launchCull(Context& c, uint32_t pool)
+uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter)
 {
 	auto& p = c.pools[pool];
+	c.poolLaunched[pool] = false;
 	if (!p.set || p.occupancy == 0)
 		return 0;
 	CullParams P = {};
@@ -619,8 +620,11 @@ uint32_t launchCull(Context& c, uint32_t pool)
 	else if (P.viewCount <= 6) kCull<6><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
 	else if (P.viewCount <= 8) kCull<8><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
 	else kCull<16><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	if (afterCull) cudaEventRecord(afterCull, c.stream);
 	kScanChunks<<<P.viewCount, kScanThreads, 0, c.stream>>>(P, A);
 	kScatter<<<dim3(A.chunks, P.viewCount), kChunkWords, 0, c.stream>>>(P, A);
+	if (afterScatter) cudaEventRecord(afterScatter, c.stream);
+	c.poolLaunched[pool] = true;
 	return 3;
 }
 

@@ -151,6 +151,8 @@ struct Context
 	uint32_t launchCount = 0;
 	bool profiling = false;
 	cudaEvent_t phaseEvents[8] = {};
+	cudaEvent_t poolEvents[kMaxPools][2] = {};
+	bool poolLaunched[kMaxPools] = {};
 	bool phaseEventsCreated = false, phaseTimesValid = false;
 	uint32_t* dError = nullptr;
 };
@@ -172,7 +174,7 @@ uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, ui
 uint32_t launchMaxEntity(Context& c, const void* dAos, uint32_t stride, uint32_t count, uint32_t* dMax);
 uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy);
 uint32_t launchLink(Context& c);
-uint32_t launchCull(Context& c, uint32_t pool);
+uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter);
 uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);
 

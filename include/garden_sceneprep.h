@@ -126,6 +126,24 @@ int gsp_get_sorted_device(gsp_context* ctx, uint32_t view, int which, const gsp_
  * (ascending order == draw order), payload = pool << 28 | slot. Used by the multi-GPU gather + merge. */
 int gsp_get_sorted_run_device(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer,
 	const uint32_t** keys, const uint32_t** payloads, uint32_t* count);
+/* ---- multi-GPU exchange (no reference counterpart: one process, one std::sort per list) ---------------------------- */
+/* Number of draw lists of the frame, in (view, meshSystems order) with the shared translucent / UI lists counted once. */
+uint32_t gsp_list_count(const gsp_context* ctx);
+/* Length of every list of the last completed frame (`capacity` >= gsp_list_count entries). */
+int gsp_get_list_counts(gsp_context* ctx, uint32_t* counts, uint32_t capacity);
+/* Packs the sorted (key, payload) runs of all lists back to back into caller-provided DEVICE buffers (the send buffers of
+ * the NCCL all-gather). Enqueued on the context's stream. */
+int gsp_export_runs(gsp_context* ctx, uint32_t* dKeys, uint32_t* dPayloads, uint32_t capacity);
+/* K-way merge after the all-gather: this rank merges ITS key range of every list out of the `ranks` gathered runs
+ * (splitters = quantiles of rank 0's run, identical on every rank). All pointers are device pointers.
+ *   dKeys/dPayloads: gathered buffers, rank r's block at r * rankStride; dOffsets/dCounts: [ranks][lists];
+ *   dBounds: [lists][ranks][2] scratch; dSliceInfo: [lists][2] out = (global position of my slice, slice length);
+ *   dOutKeys/dOutPayloads/dOutRanks: my slices, list l at dOutOffsets[l]. Ties resolve to (rank, payload) order. */
+int gsp_merge_gathered(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t rankStride,
+	const uint32_t* dKeys, const uint32_t* dPayloads, const uint32_t* dOffsets, const uint32_t* dCounts, uint32_t maxRunLength,
+	uint32_t* dBounds, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads, uint8_t* dOutRanks,
+	const uint32_t* dOutOffsets);
+
 /* Stores MeshRenderComponent::isVisible (offset 15) for every slot of `pool` exactly as the reference's main-view pass
  * does (mesh.cpp:144-146,152-153,161-167). No-op for pools the main view did not process. */
 int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride);
@@ -135,9 +153,9 @@ int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out);
 
 /* ---- introspection for benchmarks --------------------------------------------------------------------------------- */
 /* Per-phase device timing with CUDA events recorded on the context's stream around each kernel group of gsp_run.
- * Phases: 0 link (entity -> transform slot, only after structural changes), 1 cull+compact (all pools),
- * 2 sort histogram, 3 sort passes, 4 record emission. */
-#define GSP_PHASE_COUNT 5
+ * Phases: 0 link (entity -> transform slot, only after structural changes), 1 world matrices + culling (kCull, all pools),
+ * 2 compaction + keys (kScanChunks + kScatter), 3 sort histogram, 4 sort passes, 5 record emission. */
+#define GSP_PHASE_COUNT 6
 int gsp_set_profiling(gsp_context* ctx, int enabled);
 /* Milliseconds of each phase of the last completed gsp_run (zeros when profiling is off). `ms` = GSP_PHASE_COUNT floats. */
 int gsp_get_phase_times(gsp_context* ctx, float* ms);
