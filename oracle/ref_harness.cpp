@@ -279,9 +279,14 @@ void ref_destroy_entities(uint32_t count, const uint32_t* entityIndex)
 			transformView->setParent({});
 		manager->destroy(entity);
 	}
-	manager->disposeGarbageComponents();
-	manager->disposeSystemComponents();
-	manager->disposeEntities();
+	// same order as Manager::update (libraries/ecsm/source/ecsm.cpp:591-593); repeated until the pools are quiescent,
+	// because disposing an entity only queues its components for the next system dispose
+	for (int pass = 0; pass < 2; pass++)
+	{
+		manager->disposeGarbageComponents();
+		manager->disposeEntities();
+		manager->disposeSystemComponents();
+	}
 }
 
 void ref_transform_pool(const void** data, uint32_t* stride, uint32_t* occupancy)

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Generates the golden vectors in tests/golden/*.npz by running the REFERENCE ITSELF (oracle/_ref/libgarden_ref_parity.so:
+the unmodified cfnptr/garden translation units built by oracle/Makefile with -O3 -DNDEBUG -march=haswell -ffp-contract=off).
+
+Run here (needs /root/reference for the _ref build):   python tests/golden/make_golden.py
+The reference's own tests hold no vectors for this path (calcModel / Frustum / isBehindFrustum / key / sort are
+"parity unpinned" upstream), so these files are the pin: inputs are the raw bytes of the reference's live ECS pools
+(LinearPool<TransformComponent>, LinearPool<mesh component>) after building the scene through createEntity / add<> /
+setParent / setActive / destroy, outputs are the reference's draw lists per view in canonical order
+(key, then bufferIndex, then componentOffset; OIT buffers by componentOffset), its counts and MeshRenderComponent::isVisible.
+
+Two fields the path never reads are zeroed in the stored input bytes so the files are reproducible: TransformComponent::uid
+(random, transform.hpp:37) and TransformComponent::childs (a heap pointer, transform.hpp:56).
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import reflib  # noqa: E402
+from common import canonical, canonical_oit, ref_frame  # noqa: E402
+from edge_scenes import few_planes_views, mixed_scene, mixed_views  # noqa: E402
+from garden_b200 import scenes, views as V  # noqa: E402
+from garden_b200.layout import RT_OIT, RT_TRANSLUCENT, RT_UI  # noqa: E402
+
+
+def cases():
+    s = scenes.config_scene("C1")
+    yield "c1_flat_10k", s, V.perspective_views([(0.4, -0.05)], 1.2, 16 / 9, 0.01)[0], None
+    s = scenes.config_scene("C2", n=3000)
+    s.camera_pos = np.array([5.0, 2.0, -3.0], np.float32)
+    yield "c2_depth4_5views", s, V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))[0], None
+    s = scenes.config_scene("C3", n=3000)
+    for k, p in enumerate(s.pools):
+        p.stride = 48 + 16 * (k % 3)
+    yield "c3_depth8_opaque_translucent", s, V.perspective_views([(1.1, 0.05)], 1.3, 16 / 9, 0.01)[0], None
+    yield "mixed_all_branches", mixed_scene(seed=7, n=2000), mixed_views(), None
+    s = mixed_scene(seed=11, n=1500, with_ui=False)
+    leaves = np.ones(s.entity_count, bool)
+    leaves[s.parent[s.parent >= 0]] = False
+    yield "freed_slots_few_planes", s, few_planes_views(), np.nonzero(leaves)[0][::7].astype(np.uint32)
+
+
+def main():
+    if not reflib.ref_available("parity"):
+        raise SystemExit("oracle/_ref/libgarden_ref_parity.so is missing: run `make -C oracle ref` where /root/reference exists")
+    for name, scene, views, victims in cases():
+        rts = [p.render_type for p in scene.pools]
+        unsorted_types = [rt for rt in rts if rt not in (RT_TRANSLUCENT, RT_UI)]
+        with reflib.RefEngine("parity", threads=-1) as ref:
+            ref.load_scene(scene)
+            if victims is not None:
+                ref.destroy_entities(victims)
+            out = {}
+            taddr, tstride, tocc = ref.transform_pool()
+            tbytes = ref.transform_bytes().reshape(tocc, tstride).copy()
+            tbytes[:, 8:16] = 0    # uid
+            tbytes[:, 64:72] = 0   # childs
+            out["transforms"] = tbytes
+            meta = []
+            for k in range(len(scene.pools)):
+                addr, stride, occ, count = ref.mesh_pool(k)
+                mb = ref.pool_bytes(k).reshape(occ, stride).copy() if occ else np.zeros((0, stride), np.uint8)
+                mb[:, 15] = 0  # isVisible is an output
+                out[f"pool{k}"] = mb
+                rc = ref.pool_ready_counts(k)
+                out[f"ready{k}"] = np.zeros(0, np.uint8) if rc is None else np.pad(rc, (0, max(0, occ - rc.size)), constant_values=1)[:occ]
+                meta.append([rts[k], stride, occ, count, 1 if scene.pools[k].draw_ready else 0, 0 if rc is None else 1])
+            out["pool_meta"] = np.array(meta, dtype=np.uint32)
+            out["views"] = views
+            out["camera_pos"] = np.asarray(scene.camera_pos, np.float32)
+            frame = ref_frame(ref, views)
+            total = 0
+            for v, res in enumerate(frame):
+                for b, (rec, draw, inst) in enumerate(res["unsorted"]):
+                    rec = canonical_oit(rec) if unsorted_types[b] == RT_OIT else canonical(rec, False)
+                    out[f"v{v}_unsorted{b}"] = rec
+                    out[f"v{v}_unsorted{b}_counts"] = np.array([draw, inst], np.uint32)
+                    total += draw
+                out[f"v{v}_sorted_counts"] = np.array(res["sorted_counts"], np.uint32).reshape(-1, 2)
+                out[f"v{v}_trans"] = canonical(res["trans"][0], True)
+                out[f"v{v}_ui"] = canonical(res["ui"][0], True)
+                total += res["trans"][1] + res["ui"][1]
+                if "visible" in res:
+                    for k, vis in enumerate(res["visible"]):
+                        out[f"v{v}_visible{k}"] = vis
+        path = HERE / f"{name}.npz"
+        np.savez_compressed(path, **out)
+        print(f"{name}: {scene.entity_count} entities, {views.size} views, {total} records -> {path.stat().st_size / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

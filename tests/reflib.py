@@ -6,7 +6,10 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
+import shutil
 import subprocess
+import tempfile
 from pathlib import Path
 
 import numpy as np
@@ -44,7 +47,15 @@ class RefEngine:
 
     def __init__(self, kind: str = "parity", threads: int = -1, use_oit: bool = False):
         path = REF_PARITY if kind == "parity" else REF_STOCK
-        self.lib = C.CDLL(str(path))
+        # mpmt's setMainThread() aborts when called twice in one process image (file-static flag in
+        # libraries/logy/libraries/mpmt/source/thread.c:178-194), so every engine instance loads a private copy of the
+        # library: a dlopen of a distinct file gets fresh statics.
+        with tempfile.NamedTemporaryFile(prefix="garden_ref_", suffix=".so", delete=False) as tmp:
+            shutil.copyfile(path, tmp.name)
+        try:
+            self.lib = C.CDLL(tmp.name)
+        finally:
+            os.unlink(tmp.name)
         L = self.lib
         L.ref_init.argtypes = [_i32, _i32]
         L.ref_add_pool.argtypes = [_i32]

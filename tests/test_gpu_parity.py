@@ -46,3 +46,227 @@ def test_depth8_opaque_and_translucent(oracle_built, sceneprep_lib):
     scene = scenes.config_scene("C3", n=150_000)
     views, _ = V.perspective_views([(1.1, 0.05)], 1.3, 16 / 9, 0.01)
     _run_both(scene, views, strides=[48, 64])
+
+
+# ---- every branch of the filters and buckets (tests/edge_scenes.py) -------------------------------------------------
+def test_mixed_scene_all_branches(oracle_built, sceneprep_lib):
+    from edge_scenes import mixed_scene, mixed_views
+    scene = mixed_scene(seed=21, n=60_000, box_half=120.0)
+    views = mixed_views(yaw=1.3)
+    ready = [p.ready for p in scene.pools]
+    sp, orun, t, pools = _run_both(scene, views, ready=ready)
+    main = orun.views[-1]
+    assert main["ui"][1] > 0 and main["trans"][1] > 0
+    # isVisible write-back (main view only, mesh.cpp:144-146,152-153,161-167) against the oracle's per-slot result
+    for k, m in enumerate(pools):
+        raw = m.view(np.uint8).reshape(-1, m.dtype.itemsize)
+        raw[:, 15] = 0xFF
+        sp.writeback_visible(k, m, m.dtype.itemsize)
+        want = main["visible"][k]
+        assert np.array_equal(raw[:, 15], want), f"pool {k}: isVisible differs"
+    sp.close()
+
+
+def test_few_planes_and_freed_slots(oracle_built, sceneprep_lib):
+    from edge_scenes import few_planes_views, mixed_scene
+    scene = mixed_scene(seed=22, n=20_000, with_ui=False, box_half=80.0)
+    t, pools = aos_inputs(scene)
+    # free slots: default-constructed components (entity == 0) in the middle of the pools (linear-pool.hpp)
+    leaves = np.ones(scene.entity_count, bool)
+    leaves[scene.parent[scene.parent >= 0]] = False
+    dead = set((np.nonzero(leaves)[0][::5] + 1).tolist())
+    for arr in [t] + pools:
+        kill = np.isin(arr["entity"], list(dead))
+        raw = arr.view(np.uint8).reshape(-1, arr.dtype.itemsize)
+        raw[kill] = 0
+    from garden_b200.binding import ScenePrep
+    views = few_planes_views()
+    rts = [p.render_type for p in scene.pools]
+    ready = [p.ready for p in scene.pools]
+    orun = OracleRun((t, t.dtype.itemsize, t.size), [(m, m.dtype.itemsize, m.size) for m in pools], rts, views,
+                     scene.camera_pos, ready=ready)
+    sp = ScenePrep(0)
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(len(pools))
+    for k, m in enumerate(pools):
+        sp.set_mesh_pool(k, rts[k], m, m.dtype.itemsize, m.size, m.size, True, ready[k])
+    sp.set_views(views, scene.camera_pos)
+    sp.run()
+    compare_gpu_to_oracle(sp, orun, rts, views, "freed")
+    sp.close()
+
+
+def test_dirty_range_updates_and_view_changes(oracle_built, sceneprep_lib):
+    """C3's animated 10% (gsp_update_transforms on dirty ranges) over several frames, the camera moving each frame."""
+    from garden_b200.binding import ScenePrep
+    scene = scenes.config_scene("C3", n=50_000)
+    t, pools = aos_inputs(scene, strides=[48, 64])
+    rts = [p.render_type for p in scene.pools]
+    sp = ScenePrep(0)
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(len(pools))
+    for k, m in enumerate(pools):
+        sp.set_mesh_pool(k, rts[k], m, m.dtype.itemsize, m.size)
+    for frame in range(3):
+        sel, p, r, s = scenes.animate_trs(scene, frame, 99)
+        t["position"][sel] = p; t["rotation"][sel] = r; t["scale"][sel] = s
+        # the caller knows its dirty set; here: one range per run of 4096 slots that contains an animated slot
+        for first in range(0, t.size, 4096):
+            sp.update_transforms(t, t.dtype.itemsize, first, min(4096, t.size - first))
+        cam = np.array([1.0 + frame, 0.5, -2.0 * frame], np.float32)
+        views, _ = V.perspective_views([(0.2 + 0.4 * frame, 0.0)], 1.3, 16 / 9, 0.01)
+        sp.set_views(views, cam)
+        sp.run()
+        orun = OracleRun((t, t.dtype.itemsize, t.size), [(m, m.dtype.itemsize, m.size) for m in pools], rts, views, cam)
+        compare_gpu_to_oracle(sp, orun, rts, views, f"frame {frame}")
+    sp.close()
+
+
+def test_world_matrices_within_2ulp(oracle_built, sceneprep_lib):
+    """north_star: world matrices within 2 ulp of the reference's calcModel — they are in fact bit-identical."""
+    import reflib
+    from garden_b200.binding import ScenePrep
+    scene = scenes.config_scene("C4", n=30_000)
+    scene.camera_pos = np.array([12.5, 3.0, -7.25], np.float32)
+    views, _ = V.perspective_views([(0.0, 0.0), (3.14, 0.0), (1.57, 0.0), (-1.57, 0.0)], 1.6, 1.0, 0.01)
+    t, pools = aos_inputs(scene)
+    sp = ScenePrep(0)
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(1)
+    sp.set_mesh_pool(0, RT_OPAQUE, pools[0], 48, pools[0].size)
+    sp.set_views(views, scene.camera_pos)
+    sp.run()
+    models = sp.download_models(0, pools[0].size)
+    vis = np.zeros(pools[0].size, bool)
+    for v in range(views.size):
+        rec, _, _ = sp.get_unsorted(v, 0)
+        vis[(rec["componentOffset"] // 48).astype(np.int64)] = True
+    assert vis.sum() > 5000
+    o = reflib.Oracle()
+    o.set_transforms(t, t.dtype.itemsize, t.size)
+    worst = 0
+    for slot in np.nonzero(vis)[0][::7]:
+        want = o.calc_model(int(slot), scene.camera_pos).reshape(4, 4)[:, :3].reshape(12)
+        a, b = models[slot].view(np.int32).astype(np.int64), want.view(np.int32).astype(np.int64)
+        worst = max(worst, int(np.abs(a - b).max()))
+    assert worst <= 2, f"world matrices differ by {worst} ulp"
+    assert worst == 0
+    sp.close()
+
+
+# ---- error behaviour of the boundary (the reference throws EcsmError / GardenError; here: status codes) -------------------
+def test_errors_are_status_codes(sceneprep_lib):
+    from garden_b200.binding import GSP_ERR_HIERARCHY, GSP_ERR_INVALID, GSP_ERR_STATE, ScenePrep, ScenePrepError
+    scene = scenes.config_scene("C2", n=1000)
+    t, pools = aos_inputs(scene)
+    sp = ScenePrep(0)
+    with pytest.raises(ScenePrepError) as e:
+        sp.run()  # no views yet
+    assert e.value.code == GSP_ERR_STATE
+    with pytest.raises(ScenePrepError) as e:
+        sp.set_transforms(t, 72, t.size)  # stride smaller than sizeof(TransformComponent)
+    assert e.value.code == GSP_ERR_INVALID
+    bad = t.copy()
+    bad["parent"][10] = 5_000_000  # parent entity without a TransformComponent: Manager::get throws (ecsm.hpp:863-873)
+    with pytest.raises(ScenePrepError) as e:
+        sp.set_transforms(bad, bad.dtype.itemsize, bad.size)
+    assert e.value.code == GSP_ERR_HIERARCHY
+    cyc = t.copy()
+    cyc["parent"][0] = cyc["entity"][4]  # 0 -> 4 -> 3 -> 2 -> 1 -> 0
+    sp.set_transforms(cyc, cyc.dtype.itemsize, cyc.size)
+    sp.set_pool_count(1)
+    sp.set_mesh_pool(0, RT_OPAQUE, pools[0], 48, pools[0].size)
+    views, _ = V.perspective_views([(0.0, 0.0)], 1.2, 1.0, 0.01)
+    sp.set_views(views, np.zeros(3, np.float32))
+    with pytest.raises(ScenePrepError) as e:
+        sp.run()
+    assert e.value.code == GSP_ERR_HIERARCHY
+    with pytest.raises(ScenePrepError):
+        sp.get_unsorted(0, 0)  # no completed frame
+    sp.close()
+
+
+def test_empty_inputs(sceneprep_lib):
+    from garden_b200.binding import ScenePrep
+    sp = ScenePrep(0)
+    t = np.zeros(0, dtype=np.dtype([("x", "u1", 80)]))
+    sp.set_transforms(None, 80, 0)
+    sp.set_pool_count(2)
+    sp.set_mesh_pool(0, RT_OPAQUE, None, 48, 0)
+    sp.set_mesh_pool(1, RT_TRANSLUCENT, None, 48, 0)
+    views, _ = V.perspective_views([(0.0, 0.0)], 1.2, 1.0, 0.01)
+    sp.set_views(views, np.zeros(3, np.float32))
+    sp.run()
+    assert sp.unsorted_buffer_count(0) == 1 and sp.sorted_buffer_count(0) == 1
+    rec, draw, inst = sp.get_unsorted(0, 0)
+    assert (rec.size, draw, inst) == (0, 0, 0)
+    assert sp.get_sorted(0, 0)[1] == 0 and sp.last_visible_total() == 0
+    sp.close()
+
+
+# ---- full BASELINE sizes: size-independent properties -----------------------------------------------------------------
+@pytest.mark.parametrize("workload,n", [("C2", 1_000_000), ("C3", 4_000_000), ("C4", 16_000_000)])
+def test_full_size_properties(sceneprep_lib, workload, n):
+    """At BASELINE.json's sizes the oracle would take minutes, so check what must hold for ANY correct result:
+    every list sorted by key with ties in ascending (pool, slot); a slot appears at most once per list; the main view's
+    list is exactly the set of slots with isVisible; cascades + camera lists are consistent with a second run (idempotence);
+    a 1/64 sample of the records is recomputed by the oracle (world matrix bits, key bits)."""
+    import bench
+    import reflib
+    from garden_b200.binding import ScenePrep
+    scene = scenes.config_scene(workload, n=n)
+    scene.camera_pos = bench.camera_pos()
+    views = bench.frame_views(workload)
+    t, pools = scenes.build_aos(scene)
+    rts = [p.render_type for p in scene.pools]
+    sp = ScenePrep(0)
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(len(pools))
+    for k, m in enumerate(pools):
+        sp.set_mesh_pool(k, rts[k], m, m.dtype.itemsize, m.size)
+    sp.set_views(views, scene.camera_pos)
+    sp.run()
+    o = reflib.Oracle()
+    o.set_transforms(t, t.dtype.itemsize, t.size)
+    first = {}
+    total = 0
+    for v in range(views.size):
+        lists = [(sp.get_unsorted(v, b)[0], False, b) for b in range(sp.unsorted_buffer_count(v))]
+        lists.append((sp.get_sorted(v, 0)[0], True, -1))
+        for rec, desc, b in lists:
+            total += rec.size
+            key = rec["distanceSq"].astype(np.float64) * (-1.0 if desc else 1.0)
+            assert np.all(np.diff(key) >= 0), f"view {v}: list not sorted"
+            ties = np.nonzero(np.diff(key) == 0)[0]
+            assert np.all(rec["componentOffset"][ties] < rec["componentOffset"][ties + 1]), f"view {v}: tie order"
+            assert np.unique(rec["componentOffset"]).size == rec.size
+            first[(v, b)] = (rec["componentOffset"].copy(), rec["distanceSq"].view(np.uint32).copy())
+            # sampled recomputation by the oracle: world matrix and key of every 64th record (unsorted buffers: pool b)
+            if b >= 0 and rec.size:
+                pool_index = [k for k, rt in enumerate(rts) if rt != RT_TRANSLUCENT][b]
+                stride = pools[pool_index].dtype.itemsize
+                off = views[v]["cameraOffset"]
+                for r in rec[:: max(64, rec.size // 300)]:
+                    slot = int(r["componentOffset"]) // stride
+                    ent = int(pools[pool_index]["entity"][slot])
+                    m = o.calc_model(ent - 1, scene.camera_pos).reshape(4, 4)  # transform slot == entity index here
+                    assert np.array_equal(m[:, :3].reshape(12).view(np.uint32), r["bakedModel"].view(np.uint32))
+                    u = (m[3, :3] + off[:3]).astype(np.float32)
+                    k32 = np.float32(np.float32(u[0] * u[0]) + np.float32(u[1] * u[1])) + np.float32(np.float32(u[2] * u[2]) + np.float32(0))
+                    assert np.float32(k32).view(np.uint32) == r["distanceSq"].view(np.uint32)
+    assert total == sp.last_visible_total() and total > n // 50
+    # main view (last): list == isVisible set
+    main = views.size - 1
+    for b, k in enumerate([k for k, rt in enumerate(rts) if rt != RT_TRANSLUCENT]):
+        m = pools[k]
+        sp.writeback_visible(k, m, m.dtype.itemsize)
+        vis_slots = np.nonzero(m["isVisible"])[0]
+        assert np.array_equal(np.sort(first[(main, b)][0] // m.dtype.itemsize), vis_slots)
+    # idempotence: a second frame over the same state gives identical lists
+    sp.run()
+    for v in range(views.size):
+        for b in range(sp.unsorted_buffer_count(v)):
+            rec = sp.get_unsorted(v, b)[0]
+            assert np.array_equal(rec["componentOffset"], first[(v, b)][0])
+            assert np.array_equal(rec["distanceSq"].view(np.uint32), first[(v, b)][1])
+    sp.close()

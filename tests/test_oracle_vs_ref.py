@@ -1,0 +1,134 @@
+"""Pins the oracle: oracle/sceneprep_oracle.c (plain-C restatement) against the reference's OWN translation units
+(oracle/_ref/libgarden_ref_parity.so = mesh.cpp + transform.cpp + thread-pool.cpp + ecsm + math, built by oracle/Makefile with
+-ffp-contract=off) — bit for bit, through the reference's real ECS memory.
+
+Needs /root/reference at build time (this container); skipped where oracle/_ref is absent. The committed golden vectors in
+tests/golden/ (generated from the same reference build by tests/golden/make_golden.py) cover the boxes without it.
+"""
+import numpy as np
+import pytest
+
+import reflib
+from garden_b200 import scenes, views as V
+from garden_b200.layout import RT_TRANSLUCENT, RT_UI
+
+from common import OracleRun, assert_frames_equal, ref_frame
+from edge_scenes import few_planes_views, mixed_scene, mixed_views
+
+pytestmark = pytest.mark.skipif(not reflib.ref_available("parity"), reason="oracle/_ref not built (no /root/reference)")
+
+
+def _oracle_on_ref_memory(ref, scene, views):
+    taddr, tstride, tocc = ref.transform_pool()
+    pools = [ref.mesh_pool(k) for k in range(len(scene.pools))]
+    rts = [p.render_type for p in scene.pools]
+    ready = [ref.pool_ready_counts(k) for k in range(len(scene.pools))]
+    draw_ready = [p.draw_ready for p in scene.pools]
+    return OracleRun((taddr, tstride, tocc), [(a, s, o) for a, s, o, c in pools], rts, views, scene.camera_pos,
+                     ready=ready, draw_ready=draw_ready, counts=[c for a, s, o, c in pools])
+
+
+def _check(scene, views, threads=-1, mutate=None):
+    rts = [p.render_type for p in scene.pools]
+    with reflib.RefEngine("parity", threads=threads) as ref:
+        ref.load_scene(scene)
+        if mutate is not None:
+            mutate(ref)
+        got = ref_frame(ref, views)
+        want = _oracle_on_ref_memory(ref, scene, views)
+        assert_frames_equal(got, want.views, rts, scene.name)
+    return got
+
+
+def test_primitives_match_reference(oracle_built):
+    """calcModel chains (transform.hpp:197-214) and Frustum(viewProj) (frustum.hpp:51-61), value by value."""
+    scene = mixed_scene(seed=3, n=1500, max_depth=20, with_ui=False, with_ready=False)
+    o = reflib.Oracle()
+    with reflib.RefEngine("parity", threads=0) as ref:
+        ref.load_scene(scene)
+        taddr, tstride, tocc = ref.transform_pool()
+        o.set_transforms(taddr, tstride, tocc)
+        tbytes = ref.transform_bytes().reshape(tocc, tstride)
+        ents = tbytes[:, 0:4].copy().view(np.uint32).reshape(-1)
+        cam = np.array([0.25, -3.0, 8.5], np.float32)
+        checked = 0
+        for slot in range(tocc):
+            if ents[slot] == 0:
+                continue
+            a = ref.calc_model(int(ents[slot]) - 1, cam)
+            b = o.calc_model(slot, cam)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"calcModel bits differ at slot {slot}"
+            checked += 1
+        assert checked > 1000
+        rng = np.random.default_rng(5)
+        for _ in range(50):
+            vp = rng.standard_normal((4, 4)).astype(np.float32)
+            assert np.array_equal(ref.frustum_planes(vp).view(np.uint32), o.frustum_planes(vp).view(np.uint32))
+
+
+def test_c1_flat(oracle_built):
+    scene = scenes.config_scene("C1")
+    views, _ = V.perspective_views([(0.4, -0.05)], 1.2, 16 / 9, 0.01)
+    got = _check(scene, views)
+    assert got[0]["unsorted"][0][1] > 500
+
+
+def test_c2_depth4_five_views(oracle_built):
+    scene = scenes.config_scene("C2", n=40_000)
+    scene.camera_pos = np.array([5.0, 2.0, -3.0], np.float32)
+    views, _ = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    _check(scene, views)
+
+
+def test_c3_depth8_opaque_translucent(oracle_built):
+    scene = scenes.config_scene("C3", n=30_000)
+    for k, p in enumerate(scene.pools):
+        p.stride = 48 + 16 * (k % 3)
+    views, _ = V.perspective_views([(1.1, 0.05)], 1.3, 16 / 9, 0.01)
+    _check(scene, views)
+
+
+@pytest.mark.parametrize("threads", [-1, 0])
+def test_mixed_scene_all_branches(oracle_built, threads):
+    scene = mixed_scene(seed=7, single_translucent=threads == 0)
+    got = _check(scene, mixed_views(), threads=threads)
+    main = got[-1]
+    assert main["ui"][1] > 0 and main["trans"][1] > 0 and all(u[1] > 0 for u in main["unsorted"])
+
+
+def test_freed_slots_and_few_planes(oracle_built):
+    """destroy() leaves free slots (entity == 0) inside the pools (linear-pool.hpp); frusta with 1 and 4 planes."""
+    scene = mixed_scene(seed=11, n=2500, with_ui=False)
+    leaves = np.ones(scene.entity_count, bool)
+    leaves[scene.parent[scene.parent >= 0]] = False
+    victims = np.nonzero(leaves)[0][::7].astype(np.uint32)
+
+    def mutate(ref):
+        ref.destroy_entities(victims)
+    _check(scene, few_planes_views(), mutate=mutate)
+
+
+def test_draw_ready_false_and_empty_pool(oracle_built):
+    scene = mixed_scene(seed=13, n=1200, with_ui=False, with_ready=False)
+    scene.pools[0].draw_ready = False
+    empty = scene.pools[2]
+    scene.pools[2] = scenes.PoolDesc(empty.render_type, empty.entity_index[:0], empty.aabb[:0], empty.enabled[:0], None,
+                                     empty.stride)
+    _check(scene, mixed_views(with_ui=False))
+
+
+def test_animated_update(oracle_built):
+    """C3's per-frame TRS rewrite (plain stores, transform.hpp:74-104) followed by another frame."""
+    scene = scenes.config_scene("C3", n=10_000)
+    for k, p in enumerate(scene.pools):
+        p.stride = 48 + 16 * (k % 3)
+    views, _ = V.perspective_views([(0.2, 0.0)], 1.3, 16 / 9, 0.01)
+    rts = [p.render_type for p in scene.pools]
+    with reflib.RefEngine("parity") as ref:
+        ref.load_scene(scene)
+        for frame in range(3):
+            sel, p, r, s = scenes.animate_trs(scene, frame, 99)
+            ref.update_trs(sel, p, r, s)
+            got = ref_frame(ref, views)
+            want = _oracle_on_ref_memory(ref, scene, views)
+            assert_frames_equal(got, want.views, rts, f"frame {frame}")
