@@ -11,6 +11,8 @@
 #include "sceneprep_internal.h"
 #include "sceneprep_math.cuh"
 #include <math.h>
+#include <algorithm>
+#include <cmath>
 #include <string.h>
 
 namespace gsp
@@ -60,21 +62,27 @@ __device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v)
 // ---- shared-memory cache of local matrices ----------------------------------------------------------------------------------
 // Leaf-first association (transform.hpp:204-210) forces every entity to multiply its own chain, but the chain's factors —
 // the ancestors' LOCAL matrices — are shared. Each tile computes the local matrix of every transform it touches once
-// (bit-identical to recomputing it) and parks it in a direct-mapped cache keyed by transform slot;
-// ancestors outside the tile (or evicted by a conflicting slot) are recomputed from the SoA streams.
+// (bit-identical to recomputing it) and parks it in a direct-mapped cache keyed by transform slot. After
+// the fill, every entry resolves its parent link to a CACHE INDEX once (kLinkEnd = root, kLinkMiss = parent not cached),
+// so a chain step in the hot loop is: one 16-bit link load, three 128-bit matrix loads, 48 multiply-adds.
+// Ancestors outside the tile (or evicted by a conflicting slot) are recomputed from the SoA streams by the slow path.
 constexpr uint32_t kCacheSize = 320, kHalo = 16; // >= tile + halo distinct slots; index = slot % kCacheSize
 constexpr uint32_t kDepthBins = 32;
+constexpr uint32_t kLinkEnd = 0xFFFFu, kLinkMiss = 0xFFFEu;
+constexpr uint32_t kDepthUnknown = 31; // chain-length hint saturates here: such chains always take the guarded slow path
 
 struct CullShared
 {
 	float4 L[kCacheSize][3];    // float4x3 per entry, 48-byte stride: 128-bit shared loads/stores are conflict-free
 	uint32_t tag[kCacheSize];   // transform slot held by the entry (kNone = empty)
 	uint32_t par[kCacheSize];   // its parent slot
-	float aabb[6][kCullTile];   // per owner slot: min xyz, max xyz
+	float4 aabbA[kCullTile];    // per owner slot: min xyz, max x
+	float2 aabbB[kCullTile];    //                 max y, z
 	uint32_t ownTs[kCullTile];  // per owner slot: transform slot (kNone = not a candidate)
+	uint16_t lnk[kCacheSize];   // cache index of the parent's entry, kLinkEnd or kLinkMiss
 	uint16_t perm[kCullTile];   // work item -> owner slot, grouped by chain depth so a warp walks chains of equal length
 	uint16_t maskOf[kCullTile]; // per owner slot: visibility bit per view
-	uint8_t ownWalk[kCullTile]; // per owner slot: walks its parent chain (candidate && modelWithAncestors)
+	uint8_t ownSteps[kCullTile]; // per owner slot: ancestors to multiply in (0 when modelWithAncestors == false)
 	uint32_t hist[kDepthBins];
 	uint32_t binStart[kDepthBins];
 	uint32_t total[kMaxViews];
@@ -102,6 +110,16 @@ __device__ __forceinline__ void cacheInsert(CullShared& sh, uint32_t t, uint32_t
 	sh.par[e] = parent;
 }
 
+__device__ __forceinline__ Mat43 cachedLocal(const CullShared& sh, uint32_t e)
+{
+	const float4 a0 = sh.L[e][0], a1 = sh.L[e][1], a2 = sh.L[e][2];
+	Mat43 L;
+	L.c[0][0] = a0.x; L.c[0][1] = a0.y; L.c[0][2] = a0.z; L.c[1][0] = a0.w;
+	L.c[1][1] = a1.x; L.c[1][2] = a1.y; L.c[2][0] = a1.z; L.c[2][1] = a1.w;
+	L.c[2][2] = a2.x; L.c[3][0] = a2.y; L.c[3][1] = a2.z; L.c[3][2] = a2.w;
+	return L;
+}
+
 // Local matrix + parent link of transform slot t: from the cache when it holds t, else recomputed from the SoA streams.
 __device__ __forceinline__ Mat43 fetchLocal(const CullShared& sh, const CullArgs& a, uint32_t t, uint32_t& parent)
 {
@@ -109,10 +127,7 @@ __device__ __forceinline__ Mat43 fetchLocal(const CullShared& sh, const CullArgs
 	Mat43 L;
 	if (sh.tag[e] == t)
 	{
-		const float4 a0 = sh.L[e][0], a1 = sh.L[e][1], a2 = sh.L[e][2];
-		L.c[0][0] = a0.x; L.c[0][1] = a0.y; L.c[0][2] = a0.z; L.c[1][0] = a0.w;
-		L.c[1][1] = a1.x; L.c[1][2] = a1.y; L.c[2][0] = a1.z; L.c[2][1] = a1.w;
-		L.c[2][2] = a2.x; L.c[3][0] = a2.y; L.c[3][1] = a2.z; L.c[3][2] = a2.w;
+		L = cachedLocal(sh, e);
 		parent = sh.par[e];
 	}
 	else
@@ -123,11 +138,43 @@ __device__ __forceinline__ Mat43 fetchLocal(const CullShared& sh, const CullArgs
 	return L;
 }
 
-// Conservative half-width of the band around a plane inside which the exact 8-corner test decides:
-// computed plane distances differ from real arithmetic by a few ulp of the magnitudes involved (|n|_1 * A + |d|, A bounding
-// every |corner lane| and every intermediate of the corner transform); 2 * 2^-16 of that leaves a factor > 30 of head room.
-// With |n|_1 <= sqrt(3) |n|_2 the band folds into the sphere radius: reach = |n|_2 * (radius + kBandR * A) + kBandD * |d|.
+// Guarded generic chain walk (cold): continues M = L(p) * M from transform slot p to the root.
+static __device__ __forceinline__ void walkChainSlow(const CullShared& sh, const CullArgs& a, uint32_t p, Mat43& M)
+{
+	uint32_t depth = 0;
+	while (p != kNone)
+	{
+		if (++depth > kMaxChainDepth)
+		{
+			atomicExch(&a.counters[kCtrError], (uint32_t)GSP_ERR_HIERARCHY);
+			break;
+		}
+		uint32_t next;
+		const Mat43 L = fetchLocal(sh, a, p, next);
+		M = matMul43(L, M);
+		p = next;
+	}
+}
+
+// ---- conservative classification -------------------------------------------------------------------------------------------
+// The reference culls an entity for a view iff some plane has all eight transformed corners at d < 0 (aabb.hpp:452-462).
+// All corners lie in a sphere (centre cw, radius r) around the transformed box centre, so with unit-normal planes
+//   min_i (n_i . cw + d_i) < -(r + band)   =>  some plane has every corner certainly behind: culled;
+//   min_i (n_i . cw + d_i) >  (r + band)   =>  every plane has every corner certainly in front: visible;
+// anything else (the box straddles a plane, or NaN/Inf anywhere) runs the reference's exact 8-corner arithmetic, so the
+// boolean is identical by construction. `band` absorbs every rounding difference between this real-arithmetic argument
+// and the floats on either side: computed plane distances differ from real arithmetic by a few ulp of
+// |n|_1 * A + |d| (A bounds every |corner lane| and every partial sum of the corner transform); kBandR * A + kBandD * |d|
+// = 2^-15 * (sqrt(3) A + |d|) leaves a factor > 30 of head room over the ~2^-21 worst case.
+// Cost per plane: 3 FMA + 1 MIN (the view loop is unrolled, every plane constant is a constant-bank operand).
 constexpr float kBandR = 1.7321f / 32768.0f, kBandD = 1.0f / 32768.0f;
+
+__device__ __forceinline__ float sqrtApprox(float x)
+{
+	float r;
+	asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 
 // Threads per block and slots per thread: a tile of kCullTile slots is handled by kCullThreads threads, kCullItems each.
 // Work items are sorted by chain length into groups of 32 (deepest first); warp w takes groups w and (last - w), so every
@@ -177,10 +224,8 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		}
 		if (inRange)
 		{
-			const float4 ba = A.aabbA[slot];
-			const float2 bb = A.aabbB[slot];
-			sh.aabb[0][own] = ba.x; sh.aabb[1][own] = ba.y; sh.aabb[2][own] = ba.z;
-			sh.aabb[3][own] = ba.w; sh.aabb[4][own] = bb.x; sh.aabb[5][own] = bb.y;
+			sh.aabbA[own] = A.aabbA[slot];
+			sh.aabbB[own] = A.aabbB[slot];
 		}
 		const bool liveTransform = (tf & kTfLive) != 0;
 		cand = cand && liveTransform && (tf & kTfActive);
@@ -194,7 +239,7 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		const bool walk = cand && (tf & kTfAncestors);
 		depthKey[r] = walk ? (uint32_t)(tf >> kTfDepthShift) : 0u;
 		sh.ownTs[own] = cand ? ts : kNone;
-		sh.ownWalk[own] = walk ? 1 : 0;
+		sh.ownSteps[own] = (uint8_t)depthKey[r];
 		rankInBin[r] = atomicAdd(&sh.hist[depthKey[r]], 1u);
 	}
 	__syncthreads();
@@ -228,6 +273,21 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 	#pragma unroll
 	for (uint32_t r = 0; r < kCullItems; r++)
 		sh.perm[sh.binStart[depthKey[r]] + rankInBin[r]] = (uint16_t)(threadIdx.x + r * kCullThreads);
+	// parent links as cache indices (once per entry instead of once per chain step)
+	for (uint32_t e = threadIdx.x; e < kCacheSize; e += kCullThreads)
+	{
+		uint32_t link = kLinkEnd;
+		if (sh.tag[e] != kNone)
+		{
+			const uint32_t p = sh.par[e];
+			if (p != kNone)
+			{
+				const uint32_t pe = p % kCacheSize;
+				link = sh.tag[pe] == p ? pe : kLinkMiss;
+			}
+		}
+		sh.lnk[e] = (uint16_t)link;
+	}
 	__syncthreads();
 
 	// ---- phases 2 + 3 run per WORK ITEM ----
@@ -249,23 +309,34 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 				M.c[i][l] = (i == l) ? 1.0f : 0.0f;
 		if (work)
 		{
-			uint32_t p;
-			M = fetchLocal(sh, A, wts, p);
-			if (!sh.ownWalk[owner])
-				p = kNone;
-			uint32_t depth = 0;
-			while (p != kNone)
+			const uint32_t steps = sh.ownSteps[owner];
+			uint32_t e = wts % kCacheSize;
+			uint32_t slowFrom = kNone; // transform slot the slow path continues from
+			bool slow = false;
+			if (sh.tag[e] == wts && steps != kDepthUnknown)
 			{
-				if (++depth > kMaxChainDepth)
+				M = cachedLocal(sh, e);
+				uint32_t link = sh.lnk[e];
+				for (uint32_t s = 0; s < steps && link < kLinkMiss; s++)
 				{
-					atomicExch(&A.counters[kCtrError], (uint32_t)GSP_ERR_HIERARCHY);
-					break;
+					e = link;
+					M = matMul43(cachedLocal(sh, e), M);
+					link = sh.lnk[e];
 				}
-				uint32_t next;
-				const Mat43 L = fetchLocal(sh, A, p, next);
-				M = matMul43(L, M);
-				p = next;
+				// the hint and the links agree unless the parent is not cached (or the hint is stale): finish generically
+				if (link != kLinkEnd && steps != 0)
+				{
+					slow = true; slowFrom = sh.par[e];
+				}
 			}
+			else
+			{
+				uint32_t p;
+				M = fetchLocal(sh, A, wts, p);
+				slow = steps != 0; slowFrom = p;
+			}
+			if (slow)
+				walkChainSlow(sh, A, slowFrom, M);
 		}
 		// translate(-cameraPosition, model): c3.xyz += -cam, w kept (matrix/transform.hpp:71-74)
 		M.c[3][0] = __fadd_rn(M.c[3][0], -P.cam[0]);
@@ -273,45 +344,46 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		M.c[3][2] = __fadd_rn(M.c[3][2], -P.cam[2]);
 
 		float mn[3], mx[3];
-		#pragma unroll
-		for (int k = 0; k < 3; k++)
 		{
-			mn[k] = sh.aabb[k][owner];
-			mx[k] = sh.aabb[3 + k][owner];
+			const float4 ba = sh.aabbA[owner];
+			const float2 bb = sh.aabbB[owner];
+			mn[0] = ba.x; mn[1] = ba.y; mn[2] = ba.z; mx[0] = ba.w; mx[1] = bb.x; mx[2] = bb.y;
 		}
 
-		// ---- phase 3a: conservative bounds of the transformed box (any rounding is fine here, the band absorbs it) ----
-		float ctr[3], ext[3], amax[3];
-		#pragma unroll
-		for (int k = 0; k < 3; k++)
-		{
-			ctr[k] = 0.5f * (mn[k] + mx[k]);
-			ext[k] = 0.5f * fabsf(mx[k] - mn[k]);
-			amax[k] = fmaxf(fabsf(mn[k]), fabsf(mx[k]));
-		}
+		// ---- phase 3a: bounding sphere of the transformed box + error band (any rounding is fine here, the band absorbs it) ----
 		float cw[3]; // world-space centre
-		float magnitude = 0.0f; // A: bounds |lane| of every corner and of every partial sum of the corner transform
-		#pragma unroll
-		for (int l = 0; l < 3; l++)
+		float reach; // sphere radius + band
+		bool finite;
 		{
-			cw[l] = fmaf(M.c[0][l], ctr[0], fmaf(M.c[1][l], ctr[1], fmaf(M.c[2][l], ctr[2], M.c[3][l])));
-			float a = fmaf(fabsf(M.c[0][l]), amax[0], fmaf(fabsf(M.c[1][l]), amax[1], fmaf(fabsf(M.c[2][l]), amax[2], fabsf(M.c[3][l]))));
-			magnitude = fmaxf(magnitude, a);
+			float ctr[3], ext[3], amax[3];
+			#pragma unroll
+			for (int k = 0; k < 3; k++)
+			{
+				ctr[k] = 0.5f * (mn[k] + mx[k]);
+				ext[k] = 0.5f * fabsf(mx[k] - mn[k]);
+				amax[k] = fmaxf(fabsf(mn[k]), fabsf(mx[k]));
+			}
+			#pragma unroll
+			for (int l = 0; l < 3; l++)
+				cw[l] = fmaf(M.c[0][l], ctr[0], fmaf(M.c[1][l], ctr[1], fmaf(M.c[2][l], ctr[2], M.c[3][l])));
+			// sum_i |c_i| * e_i <= sqrt(3 * sum_i |c_i|^2 e_i^2): with e = ext it bounds the corner distance from the centre,
+			// with e = amax (plus |c3|) it bounds every |corner lane| and every partial sum of the corner transform
+			float rr = 0.0f, ra = 0.0f;
+			#pragma unroll
+			for (int i = 0; i < 3; i++)
+			{
+				const float len2 = fmaf(M.c[i][0], M.c[i][0], fmaf(M.c[i][1], M.c[i][1], M.c[i][2] * M.c[i][2]));
+				rr = fmaf(len2, ext[i] * ext[i], rr);
+				ra = fmaf(len2, amax[i] * amax[i], ra);
+			}
+			const float c3max = fmaxf(fmaxf(fabsf(M.c[3][0]), fabsf(M.c[3][1])), fabsf(M.c[3][2]));
+			const float magnitude = fmaf(sqrtApprox(3.0f * ra), 1.0001f, c3max);
+			reach = fmaf(magnitude, kBandR, sqrtApprox(3.0f * rr) * 1.0001f);
+			// NaN / Inf anywhere in the matrix poisons this sum: such entities always take the exact test
+			finite = fabsf(((cw[0] + cw[1]) + (cw[2] + rr)) + ra) < __int_as_float(0x7f800000);
 		}
-		// radius of a sphere around the centre containing all corners: sum_i |c_i| * ext_i <= sqrt(3 * sum_i |c_i|^2 ext_i^2)
-		float rr = 0.0f;
-		#pragma unroll
-		for (int i = 0; i < 3; i++)
-		{
-			float len2 = fmaf(M.c[i][0], M.c[i][0], fmaf(M.c[i][1], M.c[i][1], M.c[i][2] * M.c[i][2]));
-			rr = fmaf(len2, ext[i] * ext[i], rr);
-		}
-		const float reachR = fmaf(magnitude, kBandR, sqrtf(3.0f * rr) * 1.0001f);
 
-		// ---- phase 3b: plane tests per view (aabb.hpp:452-462): culled if some plane has all 8 corners at d < 0 ----
-		// Branch-free classification of all six planes against the bounding sphere; only straddling planes (or NaNs) fall
-		// through to the reference's exact 8-corner arithmetic, so the boolean result is identical by construction.
-		// The view loop is fully unrolled so that every plane constant is a direct constant-bank operand.
+		// ---- phase 3b: per view, the smallest unit-plane distance of the centre decides (see above) ----
 		uint32_t exactViews = 0; // views that need the exact test
 		#pragma unroll
 		for (uint32_t v = 0; v < kViews; v++)
@@ -319,21 +391,17 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 			if (v < P.viewCount) // warp-uniform
 			{
 				const ViewConst& V = P.views[v];
-				bool behindAny = false, uncertainAny = false;
+				float dmin = fmaf(V.unit[0][0], cw[0], fmaf(V.unit[0][1], cw[1], fmaf(V.unit[0][2], cw[2], V.unit[0][3])));
 				#pragma unroll
-				for (int i = 0; i < 6; i++) // planes past planeCount are neutral (always "in front")
+				for (int i = 1; i < 6; i++) // slots past planeCount are neutral (+inf)
+					dmin = fminf(dmin, fmaf(V.unit[i][0], cw[0], fmaf(V.unit[i][1], cw[1], fmaf(V.unit[i][2], cw[2], V.unit[i][3]))));
+				const float t = reach + V.slack;
+				const bool front = dmin > t, behind = dmin < -t;
+				if (V.enabled)
 				{
-					const float dc = fmaf(V.planes[i][0], cw[0], fmaf(V.planes[i][1], cw[1], fmaf(V.planes[i][2], cw[2], V.planes[i][3])));
-					const float reach = fmaf(V.planeL2[i], reachR, V.planeAbsD[i]);
-					const bool certain = fabsf(dc) > reach;   // all eight corners certainly on one side (NaN: not certain)
-					behindAny = behindAny || (certain && dc < 0.0f); // certainly all at d < 0: the plane culls
-					uncertainAny = uncertainAny || !certain;
-				}
-				if (!behindAny && V.enabled)
-				{
-					if (!uncertainAny)
+					if (front && finite)
 						mask |= 1u << v;
-					else
+					else if (!(behind && finite))
 						exactViews |= 1u << v;
 				}
 			}
@@ -357,10 +425,6 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 				for (uint32_t i = 0; i < V.planeCount && !culled; i++)
 				{
 					const float nx = V.planes[i][0], ny = V.planes[i][1], nz = V.planes[i][2], nd = V.planes[i][3];
-					// planes the sphere test already proved "in front" cannot cull; no plane of this view is "certainly behind"
-					const float dc = fmaf(nx, cw[0], fmaf(ny, cw[1], fmaf(nz, cw[2], nd)));
-					if (dc > fmaf(V.planeL2[i], reachR, V.planeAbsD[i]))
-						continue;
 					bool allBehind = true;
 					#pragma unroll
 					for (int k = 0; k < 8; k++)
@@ -406,7 +470,8 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		if (A.visibleView != kNone && slot < P.occupancy)
 			A.visible[slot] = (uint8_t)((mask >> A.visibleView) & 1u);
 		uint32_t mine = 0; // lane v keeps the ballot word of view v
-		for (uint32_t v = 0; v < P.viewCount; v++)
+		#pragma unroll
+		for (uint32_t v = 0; v < kViews; v++)
 		{
 			const uint32_t b = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
 			if (lane == v) mine = b;
@@ -537,6 +602,46 @@ __global__ void __launch_bounds__(kChunkWords) kScatter(const __grid_constant__ 
 	}
 }
 
+// Unit-normal copies of a view's planes for the conservative classifier (see kCull). Scaling a plane by a positive
+// factor does not change which side a point is on; the factor is computed in double and its rounding is far inside the
+// band. A plane with a zero normal has the same distance d for every finite point: it either never culls (d >= 0 or NaN,
+// neutral) or culls every finite entity (d < 0). Anything that cannot be normalised safely forces the exact test.
+static void prepareClassifier(ViewConst& V)
+{
+	const float inf = INFINITY;
+	float maxAbsD = 0.0f;
+	bool forceExact = false;
+	for (uint32_t i = 0; i < 6; i++)
+	{
+		float* u = V.unit[i];
+		u[0] = u[1] = u[2] = 0.0f; u[3] = inf; // neutral
+		if (i >= V.planeCount)
+			continue;
+		const float* pl = V.planes[i];
+		const double nx = pl[0], ny = pl[1], nz = pl[2], d = pl[3];
+		if (!std::isfinite(nx) || !std::isfinite(ny) || !std::isfinite(nz) || !std::isfinite(d))
+		{
+			forceExact = true;
+			continue;
+		}
+		const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+		if (len == 0.0)
+		{
+			if (d < 0.0) u[3] = -inf;
+			continue;
+		}
+		const double ux = nx / len, uy = ny / len, uz = nz / len, ud = d / len;
+		if (len < 1e-30 || !std::isfinite(ud) || std::fabs(ud) > 1e30)
+		{
+			forceExact = true;
+			continue;
+		}
+		u[0] = (float)ux; u[1] = (float)uy; u[2] = (float)uz; u[3] = (float)ud;
+		maxAbsD = std::max(maxAbsD, std::fabs(u[3]));
+	}
+	V.slack = forceExact ? inf : maxAbsD * kBandD * 1.0001f;
+}
+
 uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter)
 {
 	auto& p = c.pools[pool];
@@ -561,19 +666,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 		any = true;
 		memcpy(V.planes, isUI ? gv.uiPlanes : gv.planes, sizeof(V.planes));
 		V.planeCount = isUI ? gv.uiPlaneCount : gv.planeCount;
-		for (uint32_t i = 0; i < 6; i++)
-		{
-			float* pl = V.planes[i];
-			if (i >= V.planeCount) // neutral plane: always classified "in front", never examined by the exact test
-			{
-				pl[0] = pl[1] = pl[2] = 0.0f; pl[3] = 1.0f;
-				V.planeL2[i] = 0.0f; V.planeAbsD[i] = 0.0f;
-				continue;
-			}
-			// rounded up a little: these only widen the band in which the exact test is used
-			V.planeL2[i] = sqrtf(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2]) * 1.0001f;
-			V.planeAbsD[i] = fabsf(pl[3]) * kBandD * 1.0001f;
-		}
+		prepareClassifier(V);
 		memcpy(V.cameraOffset, gv.cameraOffset, sizeof(V.cameraOffset));
 		A.segOffset[v] = c.segments[seg].offset;
 		int prev = c.prevPool[v][pool];

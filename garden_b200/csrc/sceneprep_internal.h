@@ -64,9 +64,11 @@ struct PoolDev
 // Per-view constants handed to the cull kernel by value (__grid_constant__).
 struct ViewConst
 {
-	float planes[6][4];
-	float planeL2[6];    // |n|_2, rounded up
-	float planeAbsD[6];  // |d| * band scale
+	float planes[6][4];  // the caller's planes, verbatim: only the exact 8-corner test reads them
+	// Conservative classifier: the same planes scaled to unit normals (host, double precision); slots past planeCount
+	// and planes that can never cull hold (0, 0, 0, +inf), planes that cull everything hold (0, 0, 0, -inf).
+	float unit[6][4];
+	float slack;         // max_i |unit d_i| * kBandD (rounded up); +inf forces the exact test for the whole view
 	float cameraOffset[4];
 	uint32_t planeCount;
 	uint32_t enabled;   // pool participates in this view

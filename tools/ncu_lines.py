@@ -6,8 +6,11 @@ import sys
 
 rep = sys.argv[1]
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
-                     capture_output=True, text=True).stdout
+kernel = sys.argv[3] if len(sys.argv) > 3 else None  # optional kernel-name regex
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+if kernel:
+    cmd += ["--kernel-name", f"regex:{kernel}"]
+txt = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hdr = None
 agg = {}
