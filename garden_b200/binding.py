@@ -53,6 +53,7 @@ SYMBOLS = {
     "gsp_get_phase_times": (_i32, [_vp, _vp]),
     "gsp_last_launch_count": (_u32, [_vp]),
     "gsp_last_visible_total": (_u64, [_vp]),
+    "gsp_selftest_math": (_i32, [_i32, _u32, _u32, _u64, _vp]),
 }
 
 

@@ -195,7 +195,7 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 		GSP_CUDA(cudaMalloc((void**)&t.parent, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.entity, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.parentEntity, (size_t)cap * sizeof(uint32_t)));
-		GSP_CUDA(cudaMalloc((void**)&t.flags, (size_t)cap));
+		GSP_CUDA(cudaMalloc((void**)&t.flags, (size_t)cap * sizeof(uint16_t)));
 		t.capacity = cap;
 	}
 	t.occupancy = occupancy;
@@ -464,12 +464,13 @@ static int rebuildLayout(Context& c)
 		GSP_CUDA(cudaMalloc((void**)&c.records, cap * sizeof(gsp_record)));
 		c.arenaCap = (uint32_t)cap;
 	}
-	const size_t statusNeed = (size_t)tiles * 4 * 256;
+	const size_t statusNeed = (size_t)tiles * 256;
 	if (statusNeed > c.sortStatusCap || !c.sortStatus)
 	{
 		cudaFree(c.sortStatus); c.sortStatus = nullptr;
 		size_t cap = std::max<size_t>(statusNeed, 1024);
-		GSP_CUDA(cudaMalloc((void**)&c.sortStatus, cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&c.sortStatus, cap * sizeof(unsigned long long)));
+		GSP_CUDA(cudaMemset(c.sortStatus, 0, cap * sizeof(unsigned long long))); // epoch 0 = never published
 		c.sortStatusCap = cap;
 	}
 	c.segDownloaded.assign(nseg, 0);
@@ -509,6 +510,11 @@ int gsp_run_async(gsp_context* ctx)
 	}
 	if (prof) cudaEventRecord(c.phaseEvents[1], c.stream);
 	GSP_CUDA(cudaMemsetAsync(c.dCounters, 0, kCtrCount * sizeof(uint32_t), c.stream));
+	if (!c.segments.empty())
+	{
+		GSP_CUDA(cudaMemsetAsync(c.sortHist, 0, c.segments.size() * 4 * 256 * sizeof(uint32_t), c.stream));
+		GSP_CUDA(cudaMemsetAsync(c.sortTickets, 0, c.segments.size() * 4 * sizeof(uint32_t), c.stream));
+	}
 	for (uint32_t p = 0; p < c.poolCount; p++)
 		launches += launchCull(c, p, prof ? c.poolEvents[p][0] : nullptr, prof ? c.poolEvents[p][1] : nullptr);
 	launches += launchSort(c, prof ? c.phaseEvents[2] : nullptr);

@@ -24,7 +24,7 @@ struct CullArgs
 	const float4* __restrict__ tPosSx;
 	const float2* __restrict__ tSYZ;
 	const uint32_t* __restrict__ tParent;
-	const uint8_t* __restrict__ tFlags;
+	const uint16_t* __restrict__ tFlags;
 	const float4* __restrict__ aabbA;
 	const float2* __restrict__ aabbB;
 	const uint32_t* __restrict__ tslot;
@@ -37,6 +37,8 @@ struct CullArgs
 	uint32_t* __restrict__ counters;
 	uint32_t* __restrict__ keys;
 	uint32_t* __restrict__ payloads;
+	uint32_t* __restrict__ sortHist; // [segment][4][256] digit histograms of the sort, accumulated by kScatter
+	uint32_t histOffset[kMaxViews];  // element offset of the list's histograms in sortHist (kNone = list is not sorted)
 	uint32_t segOffset[kMaxViews];   // arena offset of this pool's list in view v
 	uint32_t baseCounter[kMaxViews]; // counter index holding the list length before this pool (kNone = 0)
 	uint32_t visibleView;            // view whose result is stored to isVisible (kNone = none)
@@ -44,8 +46,8 @@ struct CullArgs
 	uint32_t chunks;
 };
 
-constexpr uint32_t kChunkTiles = 32;                               // tiles per compaction chunk
-constexpr uint32_t kChunkWords = kChunkTiles * (kCullTile / 32);   // ballot words per chunk = threads of kScatter
+constexpr uint32_t kChunkTiles = 8;                                // tiles per compaction chunk
+constexpr uint32_t kChunkWords = kChunkTiles * (kCullTile / 32);   // ballot words per chunk (one warp of kScatter per chunk)
 constexpr uint32_t kFlagAggregate = 1u << 30, kFlagInclusive = 2u << 30, kValueMask = (1u << 30) - 1;
 
 __device__ __forceinline__ uint32_t ldVolatile(const uint32_t* p)
@@ -69,11 +71,11 @@ __device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v)
 constexpr uint32_t kCacheSize = 320, kHalo = 16; // >= tile + halo distinct slots; index = slot % kCacheSize
 constexpr uint32_t kDepthBins = 32;
 constexpr uint32_t kLinkEnd = 0xFFFFu, kLinkMiss = 0xFFFEu;
-constexpr uint32_t kDepthUnknown = 31; // chain-length hint saturates here: such chains always take the guarded slow path
+constexpr uint32_t kDepthUnknown = kTfDepthMax; // chain-length hint saturates here: such chains take the guarded slow path
 
 struct CullShared
 {
-	float4 L[kCacheSize][3];    // float4x3 per entry, 48-byte stride: 128-bit shared loads/stores are conflict-free
+	float4 L[kCacheSize][3];    // per entry: row l = (c0[l], c1[l], c2[l], c3[l]); 48-byte stride: 128-bit accesses conflict-free
 	uint32_t tag[kCacheSize];   // transform slot held by the entry (kNone = empty)
 	uint32_t par[kCacheSize];   // its parent slot
 	float4 aabbA[kCullTile];    // per owner slot: min xyz, max x
@@ -95,7 +97,7 @@ __device__ __forceinline__ Mat43 loadLocal43(const CullArgs& a, uint32_t t)
 	float4 q = a.tRot[t];
 	float4 p = a.tPosSx[t];
 	float2 s = a.tSYZ[t];
-	return localModel43(p.x, p.y, p.z, q.x, q.y, q.z, q.w, p.w, s.x, s.y);
+	return localModel43(p.x, p.y, p.z, q.x, q.y, q.z, q.w, p.w, s.x, s.y, (a.tFlags[t] & kTfExactLocal) != 0);
 }
 
 __device__ __forceinline__ void cacheInsert(CullShared& sh, uint32_t t, uint32_t parent, const Mat43& L)
@@ -104,19 +106,21 @@ __device__ __forceinline__ void cacheInsert(CullShared& sh, uint32_t t, uint32_t
 	// claim the entry first: two slots of one tile may collide, and only the winner may write the payload
 	if (atomicCAS(&sh.tag[e], kNone, t) != kNone)
 		return;
-	sh.L[e][0] = make_float4(L.c[0][0], L.c[0][1], L.c[0][2], L.c[1][0]);
-	sh.L[e][1] = make_float4(L.c[1][1], L.c[1][2], L.c[2][0], L.c[2][1]);
-	sh.L[e][2] = make_float4(L.c[2][2], L.c[3][0], L.c[3][1], L.c[3][2]);
+	#pragma unroll
+	for (int l = 0; l < 3; l++)
+		sh.L[e][l] = make_float4(L.c[0][l], L.c[1][l], L.c[2][l], L.c[3][l]);
 	sh.par[e] = parent;
 }
 
 __device__ __forceinline__ Mat43 cachedLocal(const CullShared& sh, uint32_t e)
 {
-	const float4 a0 = sh.L[e][0], a1 = sh.L[e][1], a2 = sh.L[e][2];
 	Mat43 L;
-	L.c[0][0] = a0.x; L.c[0][1] = a0.y; L.c[0][2] = a0.z; L.c[1][0] = a0.w;
-	L.c[1][1] = a1.x; L.c[1][2] = a1.y; L.c[2][0] = a1.z; L.c[2][1] = a1.w;
-	L.c[2][2] = a2.x; L.c[3][0] = a2.y; L.c[3][1] = a2.z; L.c[3][2] = a2.w;
+	#pragma unroll
+	for (int l = 0; l < 3; l++)
+	{
+		const float4 a = sh.L[e][l];
+		L.c[0][l] = a.x; L.c[1][l] = a.y; L.c[2][l] = a.z; L.c[3][l] = a.w;
+	}
 	return L;
 }
 
@@ -204,43 +208,67 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 	const uint32_t tile = blockIdx.x;
 
 	// ---- filter (mesh.cpp:140-155) + phase 1: local matrix of the own transform into the cache ----
+	// Both slots of the thread move through the two dependent load levels together (two round trips to memory, not four),
+	// and their local matrices are computed by straight-line code so the two dependency chains interleave.
 	uint32_t depthKey[kCullItems], rankInBin[kCullItems];
-	#pragma unroll
-	for (uint32_t r = 0; r < kCullItems; r++)
 	{
-		const uint32_t own = threadIdx.x + r * kCullThreads;
-		const uint32_t slot = tile * kCullTile + own;
-		const bool inRange = slot < P.occupancy;
-		bool cand = inRange && (A.mflags[slot] & kMfCandidate);
-		const uint32_t ts = inRange ? A.tslot[slot] : kNone;
-		// flags, TRS and parent link depend only on `ts`: issue all the loads together (one latency, not four)
-		uint8_t tf = 0;
-		float4 tq = make_float4(0.f, 0.f, 0.f, 1.f), tp = make_float4(0.f, 0.f, 0.f, 1.f);
-		float2 tsyz = make_float2(1.f, 1.f);
-		uint32_t parentLink = kNone;
-		if (ts != kNone)
+		uint32_t ts[kCullItems];
+		bool cand[kCullItems];
+		#pragma unroll
+		for (uint32_t r = 0; r < kCullItems; r++)
 		{
-			tf = A.tFlags[ts]; tq = A.tRot[ts]; tp = A.tPosSx[ts]; tsyz = A.tSYZ[ts]; parentLink = A.tParent[ts];
+			const uint32_t own = threadIdx.x + r * kCullThreads;
+			const uint32_t slot = tile * kCullTile + own;
+			const bool inRange = slot < P.occupancy;
+			cand[r] = inRange && (A.mflags[slot] & kMfCandidate);
+			ts[r] = inRange ? A.tslot[slot] : kNone;
+			if (inRange)
+			{
+				sh.aabbA[own] = A.aabbA[slot];
+				sh.aabbB[own] = A.aabbB[slot];
+			}
 		}
-		if (inRange)
+		uint16_t tf[kCullItems];
+		float4 tq[kCullItems], tp[kCullItems];
+		float2 tsyz[kCullItems];
+		uint32_t parentLink[kCullItems];
+		#pragma unroll
+		for (uint32_t r = 0; r < kCullItems; r++)
 		{
-			sh.aabbA[own] = A.aabbA[slot];
-			sh.aabbB[own] = A.aabbB[slot];
+			// flags, TRS and parent link depend only on `ts`: all loads of both slots are issued together
+			tf[r] = 0; tq[r] = make_float4(0.f, 0.f, 0.f, 1.f); tp[r] = make_float4(0.f, 0.f, 0.f, 1.f);
+			tsyz[r] = make_float2(1.f, 1.f); parentLink[r] = kNone;
+			if (ts[r] != kNone)
+			{
+				tf[r] = A.tFlags[ts[r]]; tq[r] = A.tRot[ts[r]]; tp[r] = A.tPosSx[ts[r]]; tsyz[r] = A.tSYZ[ts[r]];
+				parentLink[r] = A.tParent[ts[r]];
+			}
 		}
-		const bool liveTransform = (tf & kTfLive) != 0;
-		cand = cand && liveTransform && (tf & kTfActive);
-		if (liveTransform)
+		Mat43 L[kCullItems];
+		#pragma unroll
+		for (uint32_t r = 0; r < kCullItems; r++)
+			localModel43Fast<false>(tp[r].x, tp[r].y, tp[r].z, tq[r].x, tq[r].y, tq[r].z, tq[r].w, tp[r].w, tsyz[r].x, tsyz[r].y, L[r]);
+		#pragma unroll
+		for (uint32_t r = 0; r < kCullItems; r++)
 		{
-			Mat43 L = localModel43(tp.x, tp.y, tp.z, tq.x, tq.y, tq.z, tq.w, tp.w, tsyz.x, tsyz.y);
-			cacheInsert(sh, ts, parentLink, L);
-			atomicMin(&sh.minSlot, ts);
+			const uint32_t own = threadIdx.x + r * kCullThreads;
+			const bool liveTransform = (tf[r] & kTfLive) != 0;
+			const bool c = cand[r] && liveTransform && (tf[r] & kTfActive);
+			if (liveTransform)
+			{
+				if (tf[r] & kTfExactLocal) // zero / subnormal entries, out-of-range inputs: the exact 4-lane code (rare)
+					L[r] = localModel43Slow(tp[r].x, tp[r].y, tp[r].z, tq[r].x, tq[r].y, tq[r].z, tq[r].w, tp[r].w, tsyz[r].x, tsyz[r].y);
+				cacheInsert(sh, ts[r], parentLink[r], L[r]);
+				atomicMin(&sh.minSlot, ts[r]);
+			}
+			// chain length (capped) sorts the tile's work; modelWithAncestors == false means no walk at all (transform.hpp:200)
+			const bool walk = c && (tf[r] & kTfAncestors);
+			const uint32_t steps = walk ? (uint32_t)(tf[r] >> kTfDepthShift) : 0u;
+			depthKey[r] = min(steps, kDepthBins - 1);
+			sh.ownTs[own] = c ? ts[r] : kNone;
+			sh.ownSteps[own] = (uint8_t)steps;
+			rankInBin[r] = atomicAdd(&sh.hist[depthKey[r]], 1u);
 		}
-		// chain length (capped) sorts the tile's work; modelWithAncestors == false means no walk at all (transform.hpp:200)
-		const bool walk = cand && (tf & kTfAncestors);
-		depthKey[r] = walk ? (uint32_t)(tf >> kTfDepthShift) : 0u;
-		sh.ownTs[own] = cand ? ts : kNone;
-		sh.ownSteps[own] = (uint8_t)depthKey[r];
-		rankInBin[r] = atomicAdd(&sh.hist[depthKey[r]], 1u);
 	}
 	__syncthreads();
 	if (warp == 0 && lane < kHalo)
@@ -315,14 +343,23 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 			bool slow = false;
 			if (sh.tag[e] == wts && steps != kDepthUnknown)
 			{
-				M = cachedLocal(sh, e);
+				Mat43P Mp; // column pairs straight out of the row-major cache entry
+				#pragma unroll
+				for (int l = 0; l < 3; l++)
+				{
+					const float4 a = sh.L[e][l];
+					Mp.p[l][0] = pack2(a.x, a.y); Mp.p[l][1] = pack2(a.z, a.w);
+				}
 				uint32_t link = sh.lnk[e];
+				#pragma unroll 2
 				for (uint32_t s = 0; s < steps && link < kLinkMiss; s++)
 				{
 					e = link;
-					M = matMul43(cachedLocal(sh, e), M);
+					const float4 a[3] = { sh.L[e][0], sh.L[e][1], sh.L[e][2] };
+					Mp = matMul43P(a, Mp);
 					link = sh.lnk[e];
 				}
+				M = unpairMat(Mp);
 				// the hint and the links agree unless the parent is not cached (or the hint is stale): finish generically
 				if (link != kLinkEnd && steps != 0)
 				{
@@ -391,10 +428,13 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 			if (v < P.viewCount) // warp-uniform
 			{
 				const ViewConst& V = P.views[v];
-				float dmin = fmaf(V.unit[0][0], cw[0], fmaf(V.unit[0][1], cw[1], fmaf(V.unit[0][2], cw[2], V.unit[0][3])));
+				// planes (2j, 2j+1) share one packed FMA chain; slots past planeCount are neutral (+inf)
+				f32x2 d[3];
 				#pragma unroll
-				for (int i = 1; i < 6; i++) // slots past planeCount are neutral (+inf)
-					dmin = fminf(dmin, fmaf(V.unit[i][0], cw[0], fmaf(V.unit[i][1], cw[1], fmaf(V.unit[i][2], cw[2], V.unit[i][3]))));
+				for (int j = 0; j < 3; j++)
+					d[j] = fma2(pack2(V.ux[j].x, V.ux[j].y), pack2(cw[0], cw[0]), fma2(pack2(V.uy[j].x, V.uy[j].y), pack2(cw[1], cw[1]),
+						fma2(pack2(V.uz[j].x, V.uz[j].y), pack2(cw[2], cw[2]), pack2(V.ud[j].x, V.ud[j].y))));
+				const float dmin = fminf(fminf(fminf(lo2(d[0]), hi2(d[0])), fminf(lo2(d[1]), hi2(d[1]))), fminf(lo2(d[2]), hi2(d[2])));
 				const float t = reach + V.slack;
 				const bool front = dmin > t, behind = dmin < -t;
 				if (V.enabled)
@@ -548,57 +588,116 @@ __global__ void __launch_bounds__(kScanThreads) kScanChunks(const __grid_constan
 		A.counters[ctrPoolEnd(P.poolIndex, v)] = sCarry;
 }
 
-// Compaction + key. One block per (chunk, view): thread i owns ballot word i of the chunk (32 slots); a block scan of
-// the popcounts gives each word its list offset, then every set bit becomes one (key, payload) entry. Lists come out in
-// slot order, so the stable radix sort breaks ties by slot.
-__global__ void __launch_bounds__(kChunkWords) kScatter(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+// Compaction + key + sort histograms. Work unit = one chunk (kChunkWords ballot words = 2048 slots) of one view, handled by
+// ONE WARP with no block-level synchronisation: each lane owns 2 consecutive words (one 64-bit load), a warp scan of the
+// popcounts gives every lane its offset inside the chunk, each lane expands its set bits into a shared-memory list of
+// slot offsets, and then the OUTPUT positions are dealt round-robin to the lanes, so every lane gathers and stores on
+// every iteration no matter how the visible slots cluster. Units are dealt to the warps of a persistent grid view-fastest,
+// so the views' gathers of one region of world matrices run together (L2 reuse). Lists come out in slot order, so the
+// stable radix sort breaks ties by slot. The four 8-bit digit histograms of the keys are accumulated in shared memory on
+// the way and added to the list's global histograms once per block (this replaces a separate histogram pass over the keys).
+constexpr uint32_t kScatterWarps = 8, kScatterThreads = kScatterWarps * 32, kWordsPerLane = kChunkWords / 32;
+static_assert(kWordsPerLane == 2, "one 64-bit load per lane");
+__global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
 {
-	const uint32_t v = blockIdx.y;
-	const ViewConst& V = P.views[v];
-	if (!V.enabled)
-		return;
-	__shared__ uint32_t sWarp[kChunkWords / 32];
+	__shared__ uint16_t sList[kScatterWarps][kChunkWords * 32]; // slot offsets inside the chunk, in list order
+	extern __shared__ uint32_t sHistDyn[]; // [viewCount][4][256]
+	uint32_t (*sHist)[4][256] = reinterpret_cast<uint32_t (*)[4][256]>(sHistDyn);
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t chunk = blockIdx.x;
-	const uint32_t wordIndex = chunk * kChunkWords + threadIdx.x;
-	const uint32_t words = A.tiles * (kCullTile / 32);
-	uint32_t word = wordIndex < words ? A.visBits[(size_t)v * words + wordIndex] : 0;
-	const uint32_t cnt = __popc(word);
-	uint32_t inc = cnt;
-	#pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-		if (lane >= (uint32_t)o) inc += t;
-	}
-	if (lane == 31)
-		sWarp[warp] = inc;
+	for (uint32_t i = threadIdx.x; i < P.viewCount * 4 * 256; i += kScatterThreads)
+		sHistDyn[i] = 0;
 	__syncthreads();
-	uint32_t before = 0;
-	#pragma unroll
-	for (uint32_t w = 0; w < kChunkWords / 32; w++)
-		if (w < warp) before += sWarp[w];
-	uint32_t pos = A.chunkCount[(size_t)v * A.chunks + chunk] + before + inc - cnt;
-	uint32_t* keys = A.keys + A.segOffset[v];
-	uint32_t* pays = A.payloads + A.segOffset[v];
-	const float ox = V.cameraOffset[0], oy = V.cameraOffset[1], oz = V.cameraOffset[2];
-	while (word)
+	const uint32_t words = A.tiles * (kCullTile / 32);
+	const uint32_t units = A.chunks * P.viewCount;
+	for (uint32_t u = blockIdx.x * kScatterWarps + warp; u < units; u += gridDim.x * kScatterWarps)
 	{
-		const uint32_t bit = __ffs(word) - 1;
-		word &= word - 1;
-		const uint32_t slot = wordIndex * 32 + bit;
-		const float4 w2 = A.world[(size_t)slot * 3 + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
-		float key;
-		if (P.key2D)
-			key = __fadd_rn(w2.w, 1.0f); // mesh.cpp:250
-		else
-			key = lengthSq3(__fadd_rn(w2.y, ox), __fadd_rn(w2.z, oy), __fadd_rn(w2.w, oz)); // mesh.cpp:172,251
-		uint32_t k = floatToOrdered(key);
-		if (P.descending)
-			k = ~k;
-		keys[pos] = k;
-		pays[pos] = (P.poolIndex << 28) | slot;
-		pos++;
+		const uint32_t v = u % P.viewCount, chunk = u / P.viewCount;
+		const ViewConst& V = P.views[v];
+		if (!V.enabled) // warp-uniform
+			continue;
+		const uint32_t firstWord = chunk * kChunkWords + lane * kWordsPerLane;
+		uint2 w = make_uint2(0u, 0u);
+		if (firstWord + kWordsPerLane <= words) // (words is a multiple of 8: kCullTile / 32 words per tile)
+			w = *reinterpret_cast<const uint2*>(A.visBits + (size_t)v * words + firstWord);
+		const uint32_t sum = __popc(w.x) + __popc(w.y);
+		uint32_t inc = sum;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= (uint32_t)o) inc += t;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+		if (total == 0)
+			continue;
+		__syncwarp(); // the previous unit's readers are done with this warp's list
+		{
+			uint32_t pos = inc - sum;
+			uint32_t bits = w.x, offset = lane * 64;
+			while (bits)
+			{
+				sList[warp][pos++] = (uint16_t)(offset + __ffs(bits) - 1);
+				bits &= bits - 1;
+			}
+			bits = w.y; offset += 32;
+			while (bits)
+			{
+				sList[warp][pos++] = (uint16_t)(offset + __ffs(bits) - 1);
+				bits &= bits - 1;
+			}
+		}
+		__syncwarp();
+		const uint32_t base = A.chunkCount[(size_t)v * A.chunks + chunk];
+		uint32_t* keys = A.keys + A.segOffset[v];
+		uint32_t* pays = A.payloads + A.segOffset[v];
+		const float ox = V.cameraOffset[0], oy = V.cameraOffset[1], oz = V.cameraOffset[2];
+		const bool sorted = A.histOffset[v] != kNone; // OIT buffers are never sorted (mesh.cpp:273-277): no histogram
+		// kGatherBatch independent gathers in flight per lane (the loop is bound by their latency, not by bandwidth)
+		constexpr uint32_t kGatherBatch = 4;
+		for (uint32_t j0 = lane; j0 < total; j0 += 32 * kGatherBatch)
+		{
+			uint32_t slot[kGatherBatch];
+			float4 w2[kGatherBatch];
+			#pragma unroll
+			for (uint32_t b = 0; b < kGatherBatch; b++)
+			{
+				const uint32_t j = j0 + 32 * b;
+				slot[b] = chunk * (kChunkWords * 32) + (j < total ? sList[warp][j] : sList[warp][j0]);
+				w2[b] = A.world[(size_t)slot[b] * 3 + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
+			}
+			#pragma unroll
+			for (uint32_t b = 0; b < kGatherBatch; b++)
+			{
+				const uint32_t j = j0 + 32 * b;
+				if (j >= total)
+					break;
+				float key;
+				if (P.key2D)
+					key = __fadd_rn(w2[b].w, 1.0f); // mesh.cpp:250
+				else
+					key = lengthSq3(__fadd_rn(w2[b].y, ox), __fadd_rn(w2[b].z, oy), __fadd_rn(w2[b].w, oz)); // mesh.cpp:172,251
+				uint32_t k = floatToOrdered(key);
+				if (P.descending)
+					k = ~k;
+				keys[base + j] = k;
+				pays[base + j] = (P.poolIndex << 28) | slot[b];
+				if (sorted)
+				{
+					atomicAdd(&sHist[v][0][k & 255u], 1u);
+					atomicAdd(&sHist[v][1][(k >> 8) & 255u], 1u);
+					atomicAdd(&sHist[v][2][(k >> 16) & 255u], 1u);
+					atomicAdd(&sHist[v][3][k >> 24], 1u);
+				}
+			}
+		}
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < P.viewCount * 4 * 256; i += kScatterThreads)
+	{
+		const uint32_t v = i >> 10;
+		const uint32_t c = sHistDyn[i];
+		if (c && A.histOffset[v] != kNone)
+			atomicAdd(&A.sortHist[A.histOffset[v] + (i & 1023u)], c);
 	}
 }
 
@@ -613,8 +712,11 @@ static void prepareClassifier(ViewConst& V)
 	bool forceExact = false;
 	for (uint32_t i = 0; i < 6; i++)
 	{
-		float* u = V.unit[i];
-		u[0] = u[1] = u[2] = 0.0f; u[3] = inf; // neutral
+		float* ux = i & 1 ? &V.ux[i >> 1].y : &V.ux[i >> 1].x;
+		float* uy = i & 1 ? &V.uy[i >> 1].y : &V.uy[i >> 1].x;
+		float* uz = i & 1 ? &V.uz[i >> 1].y : &V.uz[i >> 1].x;
+		float* ud = i & 1 ? &V.ud[i >> 1].y : &V.ud[i >> 1].x;
+		*ux = *uy = *uz = 0.0f; *ud = inf;
 		if (i >= V.planeCount)
 			continue;
 		const float* pl = V.planes[i];
@@ -627,17 +729,17 @@ static void prepareClassifier(ViewConst& V)
 		const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
 		if (len == 0.0)
 		{
-			if (d < 0.0) u[3] = -inf;
+			if (d < 0.0) *ud = -inf;
 			continue;
 		}
-		const double ux = nx / len, uy = ny / len, uz = nz / len, ud = d / len;
-		if (len < 1e-30 || !std::isfinite(ud) || std::fabs(ud) > 1e30)
+		const double nux = nx / len, nuy = ny / len, nuz = nz / len, nud = d / len;
+		if (len < 1e-30 || !std::isfinite(nud) || std::fabs(nud) > 1e30)
 		{
 			forceExact = true;
 			continue;
 		}
-		u[0] = (float)ux; u[1] = (float)uy; u[2] = (float)uz; u[3] = (float)ud;
-		maxAbsD = std::max(maxAbsD, std::fabs(u[3]));
+		*ux = (float)nux; *uy = (float)nuy; *uz = (float)nuz; *ud = (float)nud;
+		maxAbsD = std::max(maxAbsD, std::fabs(*ud));
 	}
 	V.slack = forceExact ? inf : maxAbsD * kBandD * 1.0001f;
 }
@@ -660,7 +762,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 		ViewConst& V = P.views[v];
 		int seg = c.segOf[v][pool];
 		V.enabled = seg >= 0 && c.participates[v][pool];
-		A.segOffset[v] = 0; A.baseCounter[v] = kNone;
+		A.segOffset[v] = 0; A.baseCounter[v] = kNone; A.histOffset[v] = kNone;
 		if (!V.enabled)
 			continue;
 		any = true;
@@ -669,6 +771,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 		prepareClassifier(V);
 		memcpy(V.cameraOffset, gv.cameraOffset, sizeof(V.cameraOffset));
 		A.segOffset[v] = c.segments[seg].offset;
+		A.histOffset[v] = c.segments[seg].sorted ? (uint32_t)seg * 4u * 256u : kNone;
 		int prev = c.prevPool[v][pool];
 		A.baseCounter[v] = prev >= 0 ? ctrPoolEnd((uint32_t)prev, v) : kNone;
 		if (gv.shadowPass < 0)
@@ -689,7 +792,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	A.aabbA = p.aabbA; A.aabbB = p.aabbB; A.tslot = p.tslot; A.mflags = p.flags; A.ready = p.ready;
 	A.world = p.world; A.visible = p.visible;
 	A.visBits = p.visBits; A.chunkCount = p.cullStatus; A.counters = c.dCounters;
-	A.keys = c.keys[0]; A.payloads = c.payloads[0];
+	A.keys = c.keys[0]; A.payloads = c.payloads[0]; A.sortHist = c.sortHist;
 	A.tiles = (p.occupancy + kCullTile - 1) / kCullTile;
 	A.chunks = (A.tiles + kChunkTiles - 1) / kChunkTiles;
 	p.visibleValid = A.visibleView != kNone;
@@ -715,7 +818,19 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	else kCull<16><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
 	if (afterCull) cudaEventRecord(afterCull, c.stream);
 	kScanChunks<<<P.viewCount, kScanThreads, 0, c.stream>>>(P, A);
-	kScatter<<<dim3(A.chunks, P.viewCount), kChunkWords, 0, c.stream>>>(P, A);
+	{
+		// persistent grid: one wave of blocks, every warp strides over (chunk, view) units
+		const uint32_t units = A.chunks * P.viewCount;
+		const uint32_t blocks = std::max(1u, std::min((units + kScatterWarps - 1) / kScatterWarps, 148u * 4u));
+		const size_t histBytes = (size_t)P.viewCount * 4 * 256 * sizeof(uint32_t);
+		static bool attrSet = false;
+		if (!attrSet)
+		{
+			cudaFuncSetAttribute(kScatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxViews * 4 * 256 * sizeof(uint32_t));
+			attrSet = true;
+		}
+		kScatter<<<blocks, kScatterThreads, histBytes, c.stream>>>(P, A);
+	}
 	if (afterScatter) cudaEventRecord(afterScatter, c.stream);
 	c.poolLaunched[pool] = true;
 	return 3;

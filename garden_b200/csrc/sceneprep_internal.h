@@ -22,9 +22,13 @@ constexpr uint32_t kTfEntity = 0, kTfParent = 4, kTfPos = 16, kTfScale = 32, kTf
 // MeshRenderComponent, include/garden/system/render/mesh.hpp:45-55
 constexpr uint32_t kMcEntity = 0, kMcEnabled = 14, kMcVisible = 15, kMcAabbMin = 16, kMcAabbMax = 32, kMcMinStride = 48;
 
-// transform flags (SoA)
-constexpr uint8_t kTfLive = 1, kTfActive = 2, kTfAncestors = 4;
-constexpr uint32_t kTfDepthShift = 3; // bits 3..7: chain length capped at 31 (work-balancing hint only)
+// transform flags (SoA, 16 bits)
+constexpr uint16_t kTfLive = 1, kTfActive = 2, kTfAncestors = 4;
+// the local matrix of this transform needs the guarded 4-lane code (zero / subnormal entries, out-of-range or non-finite
+// TRS): decided once at staging time by localModel43Fast<true>, so the per-frame kernel carries no guards
+constexpr uint16_t kTfExactLocal = 8;
+constexpr uint32_t kTfDepthShift = 8; // bits 8..15: chain length, saturating at 255 (= unknown: guarded generic walk)
+constexpr uint32_t kTfDepthMax = 255;
 // mesh flags (SoA): static filter of mesh.cpp:140-147 (entity != 0 && isEnabled && !degenerate AABB)
 constexpr uint8_t kMfCandidate = 1;
 
@@ -38,7 +42,7 @@ struct TransformsDev
 	uint32_t* parent = nullptr; // parent transform slot or kNone
 	uint32_t* entity = nullptr; // owner entity id (0 = free slot)
 	uint32_t* parentEntity = nullptr;
-	uint8_t* flags = nullptr;
+	uint16_t* flags = nullptr;
 	uint32_t* entityToSlot = nullptr; // entity id -> slot + 1
 	uint32_t entityCap = 0;
 };
@@ -67,7 +71,8 @@ struct ViewConst
 	float planes[6][4];  // the caller's planes, verbatim: only the exact 8-corner test reads them
 	// Conservative classifier: the same planes scaled to unit normals (host, double precision); slots past planeCount
 	// and planes that can never cull hold (0, 0, 0, +inf), planes that cull everything hold (0, 0, 0, -inf).
-	float unit[6][4];
+	// Stored as pairs of planes (2j, 2j+1) per coefficient so that one packed FMA serves two planes.
+	float2 ux[3], uy[3], uz[3], ud[3];
 	float slack;         // max_i |unit d_i| * kBandD (rounded up); +inf forces the exact test for the whole view
 	float cameraOffset[4];
 	uint32_t planeCount;
@@ -139,7 +144,8 @@ struct Context
 	uint32_t* hCounters = nullptr; // pinned
 	// sort scratch
 	uint32_t* sortHist = nullptr;   // [segments][4][256]
-	uint32_t* sortStatus = nullptr; // [segments][tiles][256] per pass (re-zeroed by the prepare kernel)
+	unsigned long long* sortStatus = nullptr; // [tiles][256] look-back words tagged with the launch epoch (never cleared)
+	uint32_t sortEpoch = 0;
 	uint32_t* sortTickets = nullptr; // [segments][4]
 	uint32_t* segTileOffset = nullptr; // device: prefix of tiles per segment (capacity based)
 	uint32_t sortTilesTotal = 0, sortScratchSegs = 0;

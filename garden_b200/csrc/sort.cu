@@ -6,9 +6,11 @@
 // mesh.hpp:204), payload = pool << 28 | slot. The compaction emits each list in (pool, slot) order and the sort is stable,
 // so equal keys keep ascending (pool, slot) order — the canonical tie-break (the reference's order on ties is unspecified).
 //
-// Algorithm (Adinets & Merrill, "Onesweep"): one up-front pass builds the 4 digit histograms of every segment; each pass
-// then reads a tile once, ranks it in shared memory, resolves the tile's global digit offsets with a decoupled look-back
-// over the preceding tiles and scatters. Per element traffic: 4 B (histogram) + 4 x (8 B read + 8 B write).
+// Algorithm (Adinets & Merrill, "Onesweep"): the 4 digit histograms of every segment are built up front (by kScatter, while
+// it writes the keys); each pass then reads a tile once, ranks it in shared memory, resolves the tile's global digit offsets
+// with a decoupled look-back over the preceding tiles and scatters. Per element traffic: 4 x (8 B read + 8 B write).
+// Look-back status words carry the launch's epoch in their upper half, so they never need clearing: a word written by an
+// earlier pass or frame simply reads as "not published yet".
 #include "sceneprep_internal.h"
 #include <algorithm>
 
@@ -24,10 +26,10 @@ struct SortArgs
 	const SegmentDev* __restrict__ segments;
 	const uint32_t* __restrict__ counters; // segment length = counters[countIndex] (kNone -> 0)
 	uint32_t* __restrict__ hist;           // [segment][pass][256]
-	uint32_t* __restrict__ status;         // [pass][tileBase(segment) + tile][256]
+	unsigned long long* __restrict__ status; // [tileBase(segment) + tile][256]: epoch << 32 | flag << 30 | value
 	uint32_t* __restrict__ tickets;        // [segment][pass]
 	const uint32_t* __restrict__ segTileOffset; // first status tile of each segment
-	uint32_t tilesTotal;                   // status tiles per pass
+	uint32_t epoch;                        // unique per (frame, pass) launch
 	uint32_t segmentCountTotal;            // number of segments
 };
 
@@ -35,55 +37,17 @@ __device__ __forceinline__ uint32_t segmentCount(const SortArgs& a, const Segmen
 {
 	return s.countIndex == kNone ? 0u : a.counters[s.countIndex];
 }
-__device__ __forceinline__ uint32_t ldRelaxed(const uint32_t* p)
+__device__ __forceinline__ unsigned long long ldRelaxed(const unsigned long long* p)
 {
-	uint32_t v;
-	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
 // The status word is the only thing a successor tile reads from this tile, so a relaxed store is enough. (A release
 // store would first drain this thread's scattered output stores of the previous tile and delay the publication.)
-__device__ __forceinline__ void stRelaxed(uint32_t* p, uint32_t v)
+__device__ __forceinline__ void stRelaxed(unsigned long long* p, unsigned long long v)
 {
-	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-
-// Up-front histogram of all 4 digits; also clears the look-back status words of the tile for all 4 passes.
-__global__ void __launch_bounds__(kSortThreads) kSortHistogram(const __grid_constant__ SortArgs A,
-	const uint32_t* __restrict__ keys)
-{
-	const SegmentDev seg = A.segments[blockIdx.y];
-	const uint32_t count = segmentCount(A, seg);
-	const uint32_t base = blockIdx.x * kSortTile;
-	if (!seg.sorted || base >= count)
-		return;
-	__shared__ uint32_t sHist[kPasses][kRadix];
-	for (uint32_t i = threadIdx.x; i < kPasses * kRadix; i += kSortThreads)
-		(&sHist[0][0])[i] = 0;
-	const uint32_t statusTile = A.segTileOffset[blockIdx.y] + blockIdx.x;
-	#pragma unroll
-	for (uint32_t p = 0; p < kPasses; p++)
-		A.status[((size_t)p * A.tilesTotal + statusTile) * kRadix + threadIdx.x] = 0;
-	__syncthreads();
-	const uint32_t* k = keys + seg.offset + base;
-	const uint32_t n = min(kSortTile, count - base);
-	#pragma unroll 4
-	for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
-	{
-		uint32_t key = k[i];
-		atomicAdd(&sHist[0][key & 255u], 1u);
-		atomicAdd(&sHist[1][(key >> 8) & 255u], 1u);
-		atomicAdd(&sHist[2][(key >> 16) & 255u], 1u);
-		atomicAdd(&sHist[3][key >> 24], 1u);
-	}
-	__syncthreads();
-	uint32_t* h = A.hist + (size_t)blockIdx.y * kPasses * kRadix;
-	for (uint32_t i = threadIdx.x; i < kPasses * kRadix; i += kSortThreads)
-	{
-		uint32_t c = (&sHist[0][0])[i];
-		if (c)
-			atomicAdd(&h[i], c);
-	}
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
 // Block-wide exclusive scan of one value per thread (kSortThreads == kRadix values).
@@ -110,7 +74,7 @@ __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* sWa
 
 constexpr uint32_t kLookbackBatch = 8; // predecessor tiles inspected per step (independent loads in flight)
 
-__global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_constant__ SortArgs A, uint32_t pass,
+__global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_constant__ SortArgs A, uint32_t pass, uint32_t epoch,
 	const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ payIn,
 	uint32_t* __restrict__ keysOut, uint32_t* __restrict__ payOut)
 {
@@ -165,7 +129,8 @@ __global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_consta
 		const uint32_t tile = sWork[1];
 		const SegmentDev seg = A.segments[segIndex];
 		const uint32_t count = segmentCount(A, seg);
-		uint32_t* statusBase = A.status + ((size_t)pass * A.tilesTotal + A.segTileOffset[segIndex]) * kRadix + d;
+		unsigned long long* statusBase = A.status + (size_t)A.segTileOffset[segIndex] * kRadix + d;
+		const unsigned long long tag = (unsigned long long)epoch << 32;
 		// global exclusive start of digit d in this pass = exclusive scan of the segment histogram
 		const uint32_t histD = A.hist[((size_t)segIndex * kPasses + pass) * kRadix + d];
 		const uint32_t base = tile * kSortTile;
@@ -229,8 +194,8 @@ __global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_consta
 		uint32_t realCount = tileCount;
 		if (d == kRadix - 1)
 			realCount -= kSortTile - n;
-		uint32_t* st = statusBase + (size_t)tile * kRadix;
-		stRelaxed(st, (tile == 0 ? kFlagInclusive : kFlagAggregate) | realCount);
+		unsigned long long* st = statusBase + (size_t)tile * kRadix;
+		stRelaxed(st, tag | (tile == 0 ? kFlagInclusive : kFlagAggregate) | realCount);
 		const uint32_t binStart = blockExclusiveScan(tileCount, sWarpTotals);
 		const uint32_t digitBase = blockExclusiveScan(histD, sWarpTotals);
 
@@ -241,27 +206,29 @@ __global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_consta
 			bool done = false;
 			while (!done)
 			{
-				uint32_t sv[kLookbackBatch];
+				unsigned long long sv[kLookbackBatch];
 				#pragma unroll
 				for (uint32_t j = 0; j < kLookbackBatch; j++)
 				{
 					const int32_t idx = t - (int32_t)j;
-					sv[j] = idx >= 0 ? ldRelaxed(statusBase + (size_t)idx * kRadix) : kFlagInclusive;
+					sv[j] = idx >= 0 ? ldRelaxed(statusBase + (size_t)idx * kRadix) : (tag | kFlagInclusive);
 				}
 				#pragma unroll
 				for (uint32_t j = 0; j < kLookbackBatch; j++)
 				{
 					if (!done)
 					{
-						while ((sv[j] & ~kValueMask) == 0)
+						// published by this launch? (any other epoch is a stale word of an earlier pass or frame)
+						while ((sv[j] >> 32) != epoch)
 							sv[j] = ldRelaxed(statusBase + (size_t)(t - (int32_t)j) * kRadix);
-						exclusive += sv[j] & kValueMask;
-						done = (sv[j] & kFlagInclusive) != 0;
+						const uint32_t word = (uint32_t)sv[j];
+						exclusive += word & kValueMask;
+						done = (word & kFlagInclusive) != 0;
 					}
 				}
 				t -= (int32_t)kLookbackBatch;
 			}
-			stRelaxed(st, kFlagInclusive | (exclusive + realCount));
+			stRelaxed(st, tag | kFlagInclusive | (exclusive + realCount));
 		}
 		sBinStart[d] = binStart;
 		sGlobal[d] = (int32_t)(digitBase + exclusive) - (int32_t)binStart;
@@ -293,44 +260,25 @@ __global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_consta
 
 uint32_t launchSort(Context& c, cudaEvent_t afterHistogram)
 {
+	if (afterHistogram) cudaEventRecord(afterHistogram, c.stream); // (the histograms are built by kScatter)
 	const uint32_t nseg = (uint32_t)c.segments.size();
-	if (nseg == 0)
-	{
-		if (afterHistogram) cudaEventRecord(afterHistogram, c.stream);
-		return 0;
-	}
-	uint32_t maxTiles = 0;
-	bool anySorted = false;
-	for (auto& s : c.segments)
-	{
-		if (!s.sorted) continue;
-		anySorted = true;
-		maxTiles = max(maxTiles, (s.capacity + kSortTile - 1) / kSortTile);
-	}
-	if (!anySorted || maxTiles == 0)
-	{
-		if (afterHistogram) cudaEventRecord(afterHistogram, c.stream);
-		return 0;
-	}
-	SortArgs A;
-	A.segments = c.dSegments; A.counters = c.dCounters; A.hist = c.sortHist; A.status = c.sortStatus;
-	A.tickets = c.sortTickets; A.segTileOffset = c.segTileOffset; A.tilesTotal = c.sortTilesTotal;
-	A.segmentCountTotal = nseg;
-	cudaMemsetAsync(c.sortHist, 0, (size_t)nseg * kPasses * kRadix * sizeof(uint32_t), c.stream);
-	cudaMemsetAsync(c.sortTickets, 0, (size_t)nseg * kPasses * sizeof(uint32_t), c.stream);
-	dim3 grid(maxTiles, nseg);
-	// sort passes are persistent (tiles claimed by ticket): 3 resident blocks per SM, split over the segments
 	uint32_t totalCapTiles = 0;
 	for (auto& sgm : c.segments)
 		if (sgm.sorted) totalCapTiles += (sgm.capacity + kSortTile - 1) / kSortTile;
+	if (nseg == 0 || totalCapTiles == 0)
+		return 0;
+	SortArgs A;
+	A.segments = c.dSegments; A.counters = c.dCounters; A.hist = c.sortHist; A.status = c.sortStatus;
+	A.tickets = c.sortTickets; A.segTileOffset = c.segTileOffset; A.epoch = 0;
+	A.segmentCountTotal = nseg;
+	// sort passes are persistent (tiles claimed by ticket): 3 resident blocks per SM, split over the segments
 	dim3 passGrid(std::min<uint32_t>(totalCapTiles, 148u * 3u));
-	kSortHistogram<<<grid, kSortThreads, 0, c.stream>>>(A, c.keys[0]);
-	if (afterHistogram) cudaEventRecord(afterHistogram, c.stream);
-	uint32_t launches = 1;
+	uint32_t launches = 0;
 	for (uint32_t pass = 0; pass < kPasses; pass++)
 	{
 		const uint32_t in = pass & 1, out = in ^ 1;
-		kSortPass<<<passGrid, kSortThreads, 0, c.stream>>>(A, pass, c.keys[in], c.payloads[in], c.keys[out], c.payloads[out]);
+		if (++c.sortEpoch == 0) ++c.sortEpoch; // 0 is what freshly allocated (zeroed) status memory holds
+		kSortPass<<<passGrid, kSortThreads, 0, c.stream>>>(A, pass, c.sortEpoch, c.keys[in], c.payloads[in], c.keys[out], c.payloads[out]);
 		launches++;
 	}
 	return launches; // 4 passes: sorted data ends in buffer 0

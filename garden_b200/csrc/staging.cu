@@ -6,6 +6,7 @@
 //   TransformComponent  (include/garden/system/transform.hpp:31-60)   and
 //   MeshRenderComponent (include/garden/system/render/mesh.hpp:45-55).
 #include "sceneprep_internal.h"
+#include "sceneprep_math.cuh"
 
 namespace gsp
 {
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(256) kMaxEntity(const uint8_t* __restrict__ ao
 // One thread per transform slot. `full` also (re)builds the hierarchy inputs and the entity map.
 __global__ void __launch_bounds__(256) kStageTransforms(const uint8_t* __restrict__ aos, uint32_t stride,
 	uint32_t first, uint32_t count, int full, float4* __restrict__ rot, float4* __restrict__ posSx,
-	float2* __restrict__ sYZ, uint8_t* __restrict__ flags, uint32_t* __restrict__ entity,
+	float2* __restrict__ sYZ, uint16_t* __restrict__ flags, uint32_t* __restrict__ entity,
 	uint32_t* __restrict__ parentEntity, uint32_t* __restrict__ entityToSlot)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,16 +38,20 @@ __global__ void __launch_bounds__(256) kStageTransforms(const uint8_t* __restric
 	uint32_t slot = first + i;
 	const uint8_t* t = aos + (size_t)i * stride;
 	uint32_t e = ldU32(t + kTfEntity);
-	rot[slot] = make_float4(ldF32(t + kTfRot), ldF32(t + kTfRot + 4), ldF32(t + kTfRot + 8), ldF32(t + kTfRot + 12));
-	posSx[slot] = make_float4(ldF32(t + kTfPos), ldF32(t + kTfPos + 4), ldF32(t + kTfPos + 8), ldF32(t + kTfScale));
-	sYZ[slot] = make_float2(ldF32(t + kTfScale + 4), ldF32(t + kTfScale + 8));
+	const float4 q = make_float4(ldF32(t + kTfRot), ldF32(t + kTfRot + 4), ldF32(t + kTfRot + 8), ldF32(t + kTfRot + 12));
+	const float4 ps = make_float4(ldF32(t + kTfPos), ldF32(t + kTfPos + 4), ldF32(t + kTfPos + 8), ldF32(t + kTfScale));
+	const float2 syz = make_float2(ldF32(t + kTfScale + 4), ldF32(t + kTfScale + 8));
+	rot[slot] = q; posSx[slot] = ps; sYZ[slot] = syz;
 	uint32_t w = ldU32(t + kTfSelfActive); // bytes 72..75: selfActive, ancestorsActive, modelWithAncestors, pad
-	uint8_t f = 0;
+	uint16_t f = 0;
+	Mat43 unused;
+	if (!localModel43Fast<true>(ps.x, ps.y, ps.z, q.x, q.y, q.z, q.w, ps.w, syz.x, syz.y, unused))
+		f |= kTfExactLocal; // the per-frame kernel must use the guarded 4-lane code for this transform
 	if (e) f |= kTfLive;
 	if ((w & 0xffu) && (w & 0xff00u)) f |= kTfActive;   // isActive(), transform.hpp:110
 	if (w & 0xff0000u) f |= kTfAncestors;                // modelWithAncestors, transform.hpp:60,200
-	// bits 3..7 hold the chain length (kComputeDepth); a TRS-only update keeps them
-	flags[slot] = full ? f : (uint8_t)(f | (flags[slot] & ~((1u << kTfDepthShift) - 1u)));
+	// the upper byte holds the chain length (kComputeDepth); a TRS-only update keeps it
+	flags[slot] = full ? f : (uint16_t)(f | (flags[slot] & ~((1u << kTfDepthShift) - 1u)));
 	if (full)
 	{
 		entity[slot] = e;
@@ -75,21 +80,22 @@ __global__ void __launch_bounds__(256) kResolveParents(uint32_t count, const uin
 	parent[i] = p;
 }
 
-// Chain length of every transform (number of ancestors, capped at 31) into flag bits 3..7. The cull kernel only uses it
-// to group work of equal chain length into the same warp; correctness never depends on it.
-__global__ void __launch_bounds__(256) kComputeDepth(uint32_t count, const uint32_t* __restrict__ parent, uint8_t* __restrict__ flags)
+// Chain length of every transform (number of ancestors, saturating at 255) into the upper flag byte. The cull kernel uses
+// it as the trip count of its chain loop and to group work of equal chain length into the same warp; a wrong value only
+// costs time (the links decide), never correctness.
+__global__ void __launch_bounds__(256) kComputeDepth(uint32_t count, const uint32_t* __restrict__ parent, uint16_t* __restrict__ flags)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
 		return;
 	uint32_t depth = 0;
 	uint32_t p = parent[i];
-	while (p != kNone && depth < 31)
+	while (p != kNone && depth < kTfDepthMax)
 	{
 		depth++;
 		p = parent[p];
 	}
-	flags[i] = (uint8_t)((flags[i] & ((1u << kTfDepthShift) - 1u)) | (depth << kTfDepthShift));
+	flags[i] = (uint16_t)((flags[i] & ((1u << kTfDepthShift) - 1u)) | (depth << kTfDepthShift));
 }
 
 // One thread per mesh-component slot: AABB, owner entity and the static part of the filter at mesh.cpp:140-147.

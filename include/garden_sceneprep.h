@@ -154,7 +154,7 @@ int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out);
 /* ---- introspection for benchmarks --------------------------------------------------------------------------------- */
 /* Per-phase device timing with CUDA events recorded on the context's stream around each kernel group of gsp_run.
  * Phases: 0 link (entity -> transform slot, only after structural changes), 1 world matrices + culling (kCull, all pools),
- * 2 compaction + keys (kScanChunks + kScatter), 3 sort histogram, 4 sort passes, 5 record emission. */
+ * 2 compaction + keys + sort histograms (kScanChunks + kScatter), 3 unused (always 0), 4 sort passes, 5 record emission. */
 #define GSP_PHASE_COUNT 6
 int gsp_set_profiling(gsp_context* ctx, int enabled);
 /* Milliseconds of each phase of the last completed gsp_run (zeros when profiling is off). `ms` = GSP_PHASE_COUNT floats. */
@@ -163,6 +163,11 @@ int gsp_get_phase_times(gsp_context* ctx, float* ms);
 uint32_t gsp_last_launch_count(const gsp_context* ctx);
 /* Sum over views and lists of drawCount for the last frame (needs results to be complete). */
 uint64_t gsp_last_visible_total(gsp_context* ctx);
+/* Device self-test of the exact-arithmetic shortcuts of the hot kernel (shared-reciprocal division, sqrt fast path, packed
+ * 4x3 products): `blocks` x 256 threads x `iterations` random / adversarial TRS inputs run through the shortcut and through
+ * the reference's 4-lane IEEE operation order, compared bit for bit on the device.
+ * results = { inputs tested, inputs that took the shortcut, shortcut mismatches, matrix products tested, product mismatches }. */
+int gsp_selftest_math(int device, uint32_t blocks, uint32_t iterations, uint64_t seed, uint64_t results[5]);
 /* Library version string, e.g. "garden_sceneprep 0.1 sm_100a". */
 const char* gsp_version(void);
 

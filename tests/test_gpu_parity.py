@@ -270,3 +270,20 @@ def test_full_size_properties(sceneprep_lib, workload, n):
             assert np.array_equal(rec["componentOffset"], first[(v, b)][0])
             assert np.array_equal(rec["distanceSq"].view(np.uint32), first[(v, b)][1])
     sp.close()
+
+
+def test_exact_arithmetic_shortcuts_on_device(sceneprep_lib):
+    """The hot kernel's cheaper instruction sequences (shared-reciprocal division, sqrt fast path, folded products, packed
+    FP32 pairs) against the reference's 4-lane IEEE operation order, bit for bit, over ~1.2e9 random / adversarial inputs."""
+    from garden_b200.binding import load_library
+    lib = load_library()
+    res = np.zeros(5, dtype=np.uint64)
+    for seed in (1, 2):
+        rc = lib.gsp_selftest_math(0, 148 * 8, 2048, seed, res.ctypes.data)
+        assert rc == 0
+        tested, fast, bad, mm_tested, mm_bad = (int(x) for x in res)
+        assert tested == 148 * 8 * 256 * 2048
+        assert fast > tested * 0.6 and mm_tested > tested * 0.4, (tested, fast, mm_tested)
+        print(f"selftest seed {seed}: tested {tested}, shortcut taken {fast}, mismatches {bad}; products {mm_tested}, mismatches {mm_bad}")
+        assert bad == 0, f"{bad} of {fast} shortcut results differ from the exact code"
+        assert mm_bad == 0, f"{mm_bad} of {mm_tested} packed products differ"

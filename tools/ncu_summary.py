@@ -37,7 +37,7 @@ rows = list(csv.reader(src.splitlines()))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[start]
 idx = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[start + 1:] if len(r) == len(hdr)]
+data = [r for r in rows[start + 1:] if len(r) == len(hdr) and r[idx["# Samples"]].isdigit()]
 tot = sum(int(r[idx["# Samples"]] or 0) for r in data)
 print(f"-- source: {len(data)} SASS instructions, {tot} samples; top {top_n}:")
 keys = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_branch_resolving", "stall_math", "stall_lg", "stall_mio", "stall_not_selected"]
