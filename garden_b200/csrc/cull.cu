@@ -63,33 +63,35 @@ __device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v)
 
 // ---- shared-memory cache of local matrices ----------------------------------------------------------------------------------
 // Leaf-first association (transform.hpp:204-210) forces every entity to multiply its own chain, but the chain's factors —
-// the ancestors' LOCAL matrices — are shared. Each tile computes the local matrix of every transform it touches once
-// (bit-identical to recomputing it) and parks it in a direct-mapped cache keyed by transform slot. After
-// the fill, every entry resolves its parent link to a CACHE INDEX once (kLinkEnd = root, kLinkMiss = parent not cached),
-// so a chain step in the hot loop is: one 16-bit link load, three 128-bit matrix loads, 48 multiply-adds.
-// Ancestors outside the tile (or evicted by a conflicting slot) are recomputed from the SoA streams by the slow path.
-constexpr uint32_t kCacheSize = 320, kHalo = 16; // >= tile + halo distinct slots; index = slot % kCacheSize
+// the ancestors' LOCAL matrices — are shared. Each WARP owns a tile of kWarpTile consecutive mesh slots and a private slice
+// of shared memory; it computes the local matrix of every transform its tile touches once (bit-identical to recomputing
+// it) and parks it in a direct-mapped cache keyed by transform slot. After the fill, every entry resolves
+// its parent link to a CACHE INDEX once (kLinkEnd = root, kLinkMiss = parent not cached), so a chain step in the hot loop
+// is: one 16-bit link load, three 128-bit matrix loads, 24 packed multiply-adds. Ancestors outside the tile (or evicted
+// by a conflicting slot) are recomputed from the SoA streams by the slow path.
+// Warps never synchronise with each other (only __syncwarp): while one warp waits for its loads, the others compute.
+constexpr uint32_t kWarpTile = 64, kWarpItems = kWarpTile / 32;       // slots per warp tile, slots per lane
+constexpr uint32_t kCacheSize = 80, kHalo = 16; // >= tile + halo distinct slots; index = slot % kCacheSize
 constexpr uint32_t kDepthBins = 32;
 constexpr uint32_t kLinkEnd = 0xFFFFu, kLinkMiss = 0xFFFEu;
 constexpr uint32_t kDepthUnknown = kTfDepthMax; // chain-length hint saturates here: such chains take the guarded slow path
+static_assert(kWarpItems == 2, "work items are dealt as a deep half and a shallow half");
+static_assert(kCacheSize <= 96, "three cache entries per lane at most");
 
-struct CullShared
+struct CullShared // one per warp
 {
 	float4 L[kCacheSize][3];    // per entry: row l = (c0[l], c1[l], c2[l], c3[l]); 48-byte stride: 128-bit accesses conflict-free
 	uint32_t tag[kCacheSize];   // transform slot held by the entry (kNone = empty)
 	uint32_t par[kCacheSize];   // its parent slot
-	float4 aabbA[kCullTile];    // per owner slot: min xyz, max x
-	float2 aabbB[kCullTile];    //                 max y, z
-	uint32_t ownTs[kCullTile];  // per owner slot: transform slot (kNone = not a candidate)
-	uint16_t lnk[kCacheSize];   // cache index of the parent's entry, kLinkEnd or kLinkMiss
-	uint16_t perm[kCullTile];   // work item -> owner slot, grouped by chain depth so a warp walks chains of equal length
-	uint16_t maskOf[kCullTile]; // per owner slot: visibility bit per view
-	uint8_t ownSteps[kCullTile]; // per owner slot: ancestors to multiply in (0 when modelWithAncestors == false)
+	float4 aabbA[kWarpTile];    // per owner slot: min xyz, max x
+	float2 aabbB[kWarpTile];    //                 max y, z
+	uint32_t ownTs[kWarpTile];  // per owner slot: transform slot (kNone = not a candidate)
 	uint32_t hist[kDepthBins];
-	uint32_t binStart[kDepthBins];
-	uint32_t total[kMaxViews];
 	uint32_t inst[kMaxViews];
-	uint32_t minSlot;
+	uint16_t lnk[kCacheSize];   // cache index of the parent's entry, kLinkEnd or kLinkMiss
+	uint16_t maskOf[kWarpTile]; // per owner slot: visibility bit per view
+	uint8_t perm[kWarpTile];    // work item -> owner slot, ordered by chain length (deepest first)
+	uint8_t ownSteps[kWarpTile]; // per owner slot: ancestors to multiply in (0 when modelWithAncestors == false)
 };
 
 __device__ __forceinline__ Mat43 loadLocal43(const CullArgs& a, uint32_t t)
@@ -180,45 +182,50 @@ __device__ __forceinline__ float sqrtApprox(float x)
 	return r;
 }
 
-// Threads per block and slots per thread: a tile of kCullTile slots is handled by kCullThreads threads, kCullItems each.
-// Work items are sorted by chain length into groups of 32 (deepest first); warp w takes groups w and (last - w), so every
-// warp walks chains of uniform length AND all warps of the block carry the same total work.
-constexpr uint32_t kCullThreads = 128, kCullItems = kCullTile / kCullThreads, kCullWarps = kCullThreads / 32;
-constexpr uint32_t kCullGroups = kCullTile / 32;
-static_assert(kCullItems == 2, "the snake assignment below pairs group g with group (last - g)");
+// One block = kCullWarps independent warps = kCullTile consecutive slots. Inside a warp tile the work items are ordered by
+// chain length (deepest first); lane i takes item i of the deep half and item i of the shallow half, so the warp walks
+// chains of similar length together and every lane carries about the same total.
+constexpr uint32_t kCullThreads = 128, kCullWarps = kCullThreads / 32;
+static_assert(kCullWarps * kWarpTile == kCullTile, "a block covers one kCullTile");
 
 template<uint32_t kViews>
 __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
 {
-	__shared__ CullShared sh;
-
+	__shared__ CullShared shAll[kCullWarps];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x == 0)
-		sh.minSlot = kNone;
-	if (threadIdx.x < kMaxViews)
+	const uint32_t tile = blockIdx.x * kCullWarps + warp; // warp tile
+	const uint32_t tileBase = tile * kWarpTile;
+	if (tileBase >= P.occupancy)
 	{
-		sh.inst[threadIdx.x] = 0;
-		sh.total[threadIdx.x] = 0;
+		// past the end of the pool (the block's last warps): kScatter still reads this tile's ballot words
+		if (lane < P.viewCount)
+			for (uint32_t r = 0; r < kWarpItems; r++)
+				A.visBits[(size_t)lane * (A.tiles * (kCullTile / 32)) + tile * kWarpItems + r] = 0;
+		return; // (whole warp; nothing below synchronises across warps)
 	}
-	if (threadIdx.x < kDepthBins)
-		sh.hist[threadIdx.x] = 0;
-	for (uint32_t i = threadIdx.x; i < kCacheSize; i += kCullThreads)
+	CullShared& sh = shAll[warp];
+	constexpr uint32_t kFull = 0xffffffffu;
+
+	for (uint32_t i = lane; i < kCacheSize; i += 32)
 		sh.tag[i] = kNone;
-	__syncthreads();
-	const uint32_t tile = blockIdx.x;
+	sh.hist[lane] = 0;
+	if (lane < kMaxViews)
+		sh.inst[lane] = 0;
+	__syncwarp();
 
 	// ---- filter (mesh.cpp:140-155) + phase 1: local matrix of the own transform into the cache ----
-	// Both slots of the thread move through the two dependent load levels together (two round trips to memory, not four),
+	// Both slots of the lane move through the two dependent load levels together (two round trips to memory, not four),
 	// and their local matrices are computed by straight-line code so the two dependency chains interleave.
-	uint32_t depthKey[kCullItems], rankInBin[kCullItems];
+	uint32_t depthKey[kWarpItems], rankInBin[kWarpItems];
+	uint32_t firstTs = kNone, haloNeed = 0;
 	{
-		uint32_t ts[kCullItems];
-		bool cand[kCullItems];
+		uint32_t ts[kWarpItems];
+		bool cand[kWarpItems];
 		#pragma unroll
-		for (uint32_t r = 0; r < kCullItems; r++)
+		for (uint32_t r = 0; r < kWarpItems; r++)
 		{
-			const uint32_t own = threadIdx.x + r * kCullThreads;
-			const uint32_t slot = tile * kCullTile + own;
+			const uint32_t own = lane + r * 32;
+			const uint32_t slot = tileBase + own;
 			const bool inRange = slot < P.occupancy;
 			cand[r] = inRange && (A.mflags[slot] & kMfCandidate);
 			ts[r] = inRange ? A.tslot[slot] : kNone;
@@ -228,12 +235,12 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 				sh.aabbB[own] = A.aabbB[slot];
 			}
 		}
-		uint16_t tf[kCullItems];
-		float4 tq[kCullItems], tp[kCullItems];
-		float2 tsyz[kCullItems];
-		uint32_t parentLink[kCullItems];
+		uint16_t tf[kWarpItems];
+		float4 tq[kWarpItems], tp[kWarpItems];
+		float2 tsyz[kWarpItems];
+		uint32_t parentLink[kWarpItems];
 		#pragma unroll
-		for (uint32_t r = 0; r < kCullItems; r++)
+		for (uint32_t r = 0; r < kWarpItems; r++)
 		{
 			// flags, TRS and parent link depend only on `ts`: all loads of both slots are issued together
 			tf[r] = 0; tq[r] = make_float4(0.f, 0.f, 0.f, 1.f); tp[r] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -244,14 +251,16 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 				parentLink[r] = A.tParent[ts[r]];
 			}
 		}
-		Mat43 L[kCullItems];
+		Mat43 L[kWarpItems];
 		#pragma unroll
-		for (uint32_t r = 0; r < kCullItems; r++)
+		for (uint32_t r = 0; r < kWarpItems; r++)
 			localModel43Fast<false>(tp[r].x, tp[r].y, tp[r].z, tq[r].x, tq[r].y, tq[r].z, tq[r].w, tp[r].w, tsyz[r].x, tsyz[r].y, L[r]);
+		uint32_t steps[kWarpItems];
+		uint32_t myFirst = kNone;
 		#pragma unroll
-		for (uint32_t r = 0; r < kCullItems; r++)
+		for (uint32_t r = 0; r < kWarpItems; r++)
 		{
-			const uint32_t own = threadIdx.x + r * kCullThreads;
+			const uint32_t own = lane + r * 32;
 			const bool liveTransform = (tf[r] & kTfLive) != 0;
 			const bool c = cand[r] && liveTransform && (tf[r] & kTfActive);
 			if (liveTransform)
@@ -259,50 +268,57 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 				if (tf[r] & kTfExactLocal) // zero / subnormal entries, out-of-range inputs: the exact 4-lane code (rare)
 					L[r] = localModel43Slow(tp[r].x, tp[r].y, tp[r].z, tq[r].x, tq[r].y, tq[r].z, tq[r].w, tp[r].w, tsyz[r].x, tsyz[r].y);
 				cacheInsert(sh, ts[r], parentLink[r], L[r]);
-				atomicMin(&sh.minSlot, ts[r]);
+				myFirst = min(myFirst, ts[r]);
 			}
-			// chain length (capped) sorts the tile's work; modelWithAncestors == false means no walk at all (transform.hpp:200)
+			// chain length (capped) orders the tile's work; modelWithAncestors == false means no walk at all (transform.hpp:200)
 			const bool walk = c && (tf[r] & kTfAncestors);
-			const uint32_t steps = walk ? (uint32_t)(tf[r] >> kTfDepthShift) : 0u;
-			depthKey[r] = min(steps, kDepthBins - 1);
+			steps[r] = walk ? (uint32_t)(tf[r] >> kTfDepthShift) : 0u;
+			depthKey[r] = min(steps[r], kDepthBins - 1);
 			sh.ownTs[own] = c ? ts[r] : kNone;
-			sh.ownSteps[own] = (uint8_t)steps;
+			sh.ownSteps[own] = (uint8_t)steps[r];
 			rankInBin[r] = atomicAdd(&sh.hist[depthKey[r]], 1u);
 		}
+		// chains that start before the tile: when transforms are laid out in hierarchy order their ancestors sit right before
+		// the tile's lowest transform slot; `haloNeed` of them are worth caching (anything else takes the slow path)
+		firstTs = __reduce_min_sync(kFull, myFirst);
+		uint32_t need = 0;
+		#pragma unroll
+		for (uint32_t r = 0; r < kWarpItems; r++)
+			if (steps[r] && ts[r] != kNone)
+				need = max(need, steps[r] > ts[r] - firstTs ? steps[r] - (ts[r] - firstTs) : 0u);
+		haloNeed = min(__reduce_max_sync(kFull, need), kHalo);
 	}
-	__syncthreads();
-	if (warp == 0 && lane < kHalo)
+	__syncwarp();
+	if (lane < haloNeed && firstTs != kNone && firstTs >= lane + 1)
 	{
-		// chains that start in the previous tile: their ancestors sit right before the tile's lowest transform slot
-		const uint32_t first = sh.minSlot;
-		if (first != kNone && first >= lane + 1)
+		const uint32_t h = firstTs - 1 - lane;
+		if (sh.tag[h % kCacheSize] == kNone && (A.tFlags[h] & kTfLive)) // (racing claims are settled by the CAS)
 		{
-			const uint32_t h = first - 1 - lane;
-			if (sh.tag[h % kCacheSize] == kNone && (A.tFlags[h] & kTfLive)) // (racing claims are settled by the CAS)
-			{
-				Mat43 H = loadLocal43(A, h);
-				cacheInsert(sh, h, A.tParent[h], H);
-			}
+			Mat43 H = loadLocal43(A, h);
+			cacheInsert(sh, h, A.tParent[h], H);
 		}
 	}
-	if (warp == 1) // exclusive scan of the depth histogram, deepest chains first
 	{
+		// exclusive scan of the depth histogram, deepest chains first: lane i owns bin (kDepthBins - 1 - i)
 		const uint32_t c = sh.hist[kDepthBins - 1 - lane];
 		uint32_t inc = c;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
 		{
-			uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			uint32_t t = __shfl_up_sync(kFull, inc, o);
 			if (lane >= (uint32_t)o) inc += t;
 		}
-		sh.binStart[kDepthBins - 1 - lane] = inc - c;
+		const uint32_t exclusive = inc - c;
+		#pragma unroll
+		for (uint32_t r = 0; r < kWarpItems; r++)
+		{
+			const uint32_t start = __shfl_sync(kFull, exclusive, kDepthBins - 1 - depthKey[r]);
+			sh.perm[start + rankInBin[r]] = (uint8_t)(lane + r * 32);
+		}
 	}
-	__syncthreads();
-	#pragma unroll
-	for (uint32_t r = 0; r < kCullItems; r++)
-		sh.perm[sh.binStart[depthKey[r]] + rankInBin[r]] = (uint16_t)(threadIdx.x + r * kCullThreads);
+	__syncwarp();
 	// parent links as cache indices (once per entry instead of once per chain step)
-	for (uint32_t e = threadIdx.x; e < kCacheSize; e += kCullThreads)
+	for (uint32_t e = lane; e < kCacheSize; e += 32)
 	{
 		uint32_t link = kLinkEnd;
 		if (sh.tag[e] != kNone)
@@ -316,15 +332,14 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		}
 		sh.lnk[e] = (uint16_t)link;
 	}
-	__syncthreads();
+	__syncwarp();
 
-	// ---- phases 2 + 3 run per WORK ITEM ----
+	// ---- phases 2 + 3 run per WORK ITEM: r = 0 the deep half, r = 1 the shallow half ----
 	#pragma unroll 1
-	for (uint32_t r = 0; r < kCullItems; r++)
+	for (uint32_t r = 0; r < kWarpItems; r++)
 	{
-		const uint32_t group = r == 0 ? warp : kCullGroups - 1 - warp;
-		const uint32_t owner = sh.perm[group * 32 + lane];
-		const uint32_t wslot = tile * kCullTile + owner;
+		const uint32_t owner = sh.perm[r * 32 + lane];
+		const uint32_t wslot = tileBase + owner;
 		const uint32_t wts = sh.ownTs[owner];
 		const bool work = wts != kNone;
 		uint32_t mask = 0;
@@ -496,15 +511,17 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		}
 		sh.maskOf[owner] = (uint16_t)mask;
 	}
-	__syncthreads();
+	__syncwarp();
 
 	// ---- back to slot order: isVisible, one ballot word per 32 slots and view, the tile's visible count per view ----
 	// (no inter-tile dependency in this kernel: list positions are assigned by kScanChunks + kScatter below)
+	const uint32_t words = A.tiles * (kCullTile / 32);
+	uint32_t visibleCount = 0; // lane v: visible slots of the tile in view v
 	#pragma unroll
-	for (uint32_t r = 0; r < kCullItems; r++)
+	for (uint32_t r = 0; r < kWarpItems; r++)
 	{
-		const uint32_t own = threadIdx.x + r * kCullThreads;
-		const uint32_t slot = tile * kCullTile + own;
+		const uint32_t own = lane + r * 32;
+		const uint32_t slot = tileBase + own;
 		const uint32_t mask = sh.maskOf[own];
 		// isVisible of the (last) main view, written for every slot like mesh.cpp:144-146,152-153,161-167
 		if (A.visibleView != kNone && slot < P.occupancy)
@@ -513,24 +530,22 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		#pragma unroll
 		for (uint32_t v = 0; v < kViews; v++)
 		{
-			const uint32_t b = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
+			const uint32_t b = __ballot_sync(kFull, (mask >> v) & 1u);
 			if (lane == v) mine = b;
 		}
 		if (lane < P.viewCount)
 		{
-			A.visBits[((size_t)lane * A.tiles + tile) * (kCullTile / 32) + (own >> 5)] = mine;
-			if (mine)
-				atomicAdd(&sh.total[lane], (uint32_t)__popc(mine));
+			A.visBits[(size_t)lane * words + tile * kWarpItems + r] = mine;
+			visibleCount += __popc(mine);
 		}
 	}
-	__syncthreads();
-	if (threadIdx.x < P.viewCount)
+	if (lane < P.viewCount)
 	{
-		const uint32_t v = threadIdx.x;
-		if (sh.total[v]) // visible slots per chunk of kChunkTiles tiles: the only cross-tile quantity the compaction needs
-			atomicAdd(&A.chunkCount[(size_t)v * A.chunks + tile / kChunkTiles], sh.total[v]);
-		if (P.hasReady && sh.inst[v])
-			atomicAdd(&A.counters[ctrPoolInst(P.poolIndex, v)], sh.inst[v]);
+		// visible slots per chunk of kChunkTiles tiles: the only cross-tile quantity the compaction needs
+		if (visibleCount)
+			atomicAdd(&A.chunkCount[(size_t)lane * A.chunks + tileBase / (kChunkTiles * kCullTile)], visibleCount);
+		if (P.hasReady && sh.inst[lane])
+			atomicAdd(&A.counters[ctrPoolInst(P.poolIndex, lane)], sh.inst[lane]);
 	}
 }
 
