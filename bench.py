@@ -273,41 +273,65 @@ def run_b200_arm(args):
     sp.set_profiling(False)
 
     # ---- end to end through the C ABI with host buffers ----
+    # every step: the whole AoS pools + views go host -> device (the ECS has no dirty tracking; pinned memory is read in
+    # place by the staging kernels), the frame runs, every draw list comes back, isVisible is stored into the host pool
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     records_bytes = 0
+    parts = np.zeros(4)
 
-    def e2e_frame():
+    def e2e_frame(delta: bool = False):
         nonlocal records_bytes
+        t0 = time.perf_counter()
         stage()
+        t1 = time.perf_counter()
         sp.run()
+        t2 = time.perf_counter()
+        sp.fetch_all_async()  # the lists travel on the copy stream while isVisible is stored into the host pool
+        changed = 0
+        for k, (m, _) in enumerate(pool_pins):
+            if delta:
+                changed += sp.writeback_visible_delta(k, m, m.dtype.itemsize)
+            else:
+                sp.writeback_visible(k, m, m.dtype.itemsize)
+        t3 = time.perf_counter()
         total = 0
         for v in range(views.size):
             for b in range(sp.unsorted_buffer_count(v)):
-                rec, draw, _ = sp.get_unsorted(v, b, copy=False)
+                rec, draw, _ = sp.get_unsorted(v, b, copy=False)  # (the first getter waits for the transfer)
                 total += draw
             rec, draw = sp.get_sorted(v, 0, copy=False)
             total += draw
-        for k, (m, _) in enumerate(pool_pins):
-            sp.writeback_visible(k, m, m.dtype.itemsize)
+        t4 = time.perf_counter()
+        parts[:] += (t1 - t0, t2 - t1, t3 - t2, t4 - t3)
         records_bytes = total * 64
-        return total
+        return total, changed
 
     e2e_frame()
     barrier()
+    parts[:] = 0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_frame()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_parts = (parts / e2e_steps * 1e3).round(3).tolist()
     h2d = t_pin.nbytes + sum(m.nbytes for m, _ in pool_pins) + views.nbytes
-    d2h = records_bytes + sum(m.size for m, _ in pool_pins)
+    d2h = records_bytes + sum((m.size + 7) // 8 for m, _ in pool_pins)
+    # variant: isVisible travels as the list of slots that changed since the bytes the host uploaded
+    e2e_frame(delta=True)  # (allocates the changed-slot list once)
+    t0 = time.perf_counter()
+    changed_total = 0
+    for _ in range(e2e_steps):
+        changed_total += e2e_frame(delta=True)[1]
+    torch.cuda.synchronize()
+    e2e_delta_s = (time.perf_counter() - t0) / e2e_steps
 
     # ---- reduce over ranks: max time, summed work ----
-    stats = torch.tensor([elapsed_ms, e2e_s, float(visible_total)], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([elapsed_ms, e2e_s, float(visible_total), e2e_delta_s], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed_ms, e2e_s, visible_sum = float(mx[0]), float(mx[1]), float(sm[2])
+        elapsed_ms, e2e_s, visible_sum, e2e_delta_s = float(mx[0]), float(mx[1]), float(sm[2]), float(mx[3])
     else:
         visible_sum = float(visible_total)
     ms_per_step = elapsed_ms / args.steps
@@ -350,7 +374,13 @@ def run_b200_arm(args):
             "roofline": roofline,
             "e2e": {"value": total_entities / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "full AoS pool upload (ECS has no dirty tracking) + run + all draw lists to host + isVisible write-back"},
+                    "what": "full AoS pool upload from pinned host memory (ECS has no dirty tracking; read in place by the "
+                            "staging kernels) + run + all draw lists to host + isVisible stored into the host pool",
+                    "parts_ms": {"upload+stage": e2e_parts[0], "run": e2e_parts[1],
+                                 "isVisible_writeback (lists travelling meanwhile)": e2e_parts[2],
+                                 "wait_for_lists": e2e_parts[3]},
+                    "delta_writeback": {"value": total_entities / e2e_delta_s, "ms_per_step": e2e_delta_s * 1e3,
+                                        "changed_slots_per_step": changed_total / e2e_steps}},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }

@@ -48,6 +48,11 @@ SYMBOLS = {
     "gsp_export_runs": (_i32, [_vp, _vp, _vp, _u32]),
     "gsp_merge_gathered": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),
+    "gsp_writeback_visible_delta": (_i32, [_vp, _u32, _vp, _u32, _pu32]),
+    "gsp_fetch_all": (_i32, [_vp]),
+    "gsp_fetch_all_async": (_i32, [_vp]),
+    "gsp_pin_host": (_i32, [_vp, C.c_size_t]),
+    "gsp_unpin_host": (_i32, [_vp]),
     "gsp_download_models": (_i32, [_vp, _u32, _vp]),
     "gsp_set_profiling": (_i32, [_vp, _i32]),
     "gsp_get_phase_times": (_i32, [_vp, _vp]),
@@ -90,6 +95,17 @@ def _ptr(a) -> int:
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return int(a)
+
+
+def pin_host(arr: np.ndarray):
+    """cudaHostRegister of a numpy buffer: the staging kernels then read it in place over PCIe."""
+    rc = load_library().gsp_pin_host(arr.ctypes.data, arr.nbytes)
+    if rc != GSP_OK:
+        raise ScenePrepError(rc, "gsp_pin_host failed")
+
+
+def unpin_host(arr: np.ndarray):
+    load_library().gsp_unpin_host(arr.ctypes.data)
 
 
 class ScenePrep:
@@ -212,6 +228,17 @@ class ScenePrep:
 
     def writeback_visible(self, pool: int, aos, stride: int):
         self._check(self.lib.gsp_writeback_visible(self.h, pool, _ptr(aos), stride))
+
+    def writeback_visible_delta(self, pool: int, aos, stride: int) -> int:
+        changed = C.c_uint32()
+        self._check(self.lib.gsp_writeback_visible_delta(self.h, pool, _ptr(aos), stride, C.byref(changed)))
+        return changed.value
+
+    def fetch_all(self):
+        self._check(self.lib.gsp_fetch_all(self.h))
+
+    def fetch_all_async(self):
+        self._check(self.lib.gsp_fetch_all_async(self.h))
 
     def download_models(self, pool: int, occupancy: int) -> np.ndarray:
         out = np.zeros((occupancy, 12), dtype=np.float32)

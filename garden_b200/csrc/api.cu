@@ -4,7 +4,9 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <new>
 
 using namespace gsp;
@@ -24,6 +26,8 @@ static std::string gCreateError;
 			return GSP_ERR_CUDA;                                                                   \
 		}                                                                                          \
 	} while (0)
+
+extern "C" { static int fetchWait(Context& c); }
 
 static int fail(Context& c, int code, const char* message)
 {
@@ -98,8 +102,10 @@ int gsp_create(int device, gsp_context** out)
 	c.device = device;
 	memset(c.segOf, -1, sizeof(c.segOf));
 	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking) != cudaSuccess ||
+		cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking) != cudaSuccess ||
+		cudaEventCreateWithFlags(&c.copyEvent, cudaEventDisableTiming) != cudaSuccess ||
 		cudaMalloc((void**)&c.dCounters, kCtrCount * sizeof(uint32_t)) != cudaSuccess ||
-		cudaMallocHost((void**)&c.hCounters, kCtrCount * sizeof(uint32_t)) != cudaSuccess)
+		cudaMallocHost((void**)&c.hCounters, (kCtrCount + 8) * sizeof(uint32_t)) != cudaSuccess)
 	{
 		gCreateError = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
 		delete ctx;
@@ -120,6 +126,7 @@ void gsp_destroy(gsp_context* ctx)
 	Context& c = ctx->c;
 	cudaSetDevice(c.device);
 	cudaStreamSynchronize(c.stream);
+	if (c.copyStream) cudaStreamSynchronize(c.copyStream);
 	auto& t = c.tf;
 	cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);
 	cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.entityToSlot);
@@ -131,7 +138,7 @@ void gsp_destroy(gsp_context* ctx)
 	cudaFree(c.dSegments); cudaFree(c.keys[0]); cudaFree(c.keys[1]); cudaFree(c.payloads[0]); cudaFree(c.payloads[1]);
 	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortHist); cudaFree(c.sortStatus); cudaFree(c.sortTickets);
 	cudaFree(c.segTileOffset); cudaFree(c.dAosScratch);
-	cudaFreeHost(c.hCounters); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible);
+	cudaFreeHost(c.hCounters); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible); cudaFree(c.dVisScratch);
 	if (c.phaseEventsCreated)
 	{
 		for (auto& e : c.phaseEvents)
@@ -140,6 +147,9 @@ void gsp_destroy(gsp_context* ctx)
 			for (auto& e : pe)
 				cudaEventDestroy(e);
 	}
+	cudaStreamSynchronize(c.copyStream);
+	cudaStreamDestroy(c.copyStream);
+	cudaEventDestroy(c.copyEvent);
 	cudaStreamDestroy(c.ownStream);
 	delete ctx;
 }
@@ -161,14 +171,63 @@ int gsp_set_stream(gsp_context* ctx, void* cudaStream)
 }
 
 //----------------------------------------------------------------------------------------------------------------------
-static int uploadAos(Context& c, const void* aos, size_t bytes)
+// Where the staging kernels read the caller's AoS bytes from:
+//  * pinned / registered host memory (cudaMallocHost, cudaHostRegister, gsp_pin_host): read in place over PCIe by the
+//    staging kernel ("zero copy") — no intermediate device buffer, the re-layout overlaps the transfer;
+//  * device memory: read in place;
+//  * pageable host memory: copied into a device scratch buffer first (cudaMemcpyAsync stages it through the driver).
+// GSP_UPLOAD=copy in the environment forces the scratch path for pinned memory too (A/B measurements).
+static int resolveSource(Context& c, const void* aos, size_t bytes, const void** src)
 {
+	static const bool forceCopy = []{ const char* e = getenv("GSP_UPLOAD"); return e && !strcmp(e, "copy"); }();
+	cudaPointerAttributes attr = {};
+	cudaError_t err = cudaPointerGetAttributes(&attr, aos);
+	if (err != cudaSuccess)
+	{
+		cudaGetLastError(); // (older drivers report unregistered host memory as an error)
+		attr.type = cudaMemoryTypeUnregistered;
+	}
+	if ((attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr.devicePointer)
+	{
+		*src = attr.devicePointer;
+		return GSP_OK;
+	}
+	if (attr.type == cudaMemoryTypeHost && attr.devicePointer && !forceCopy)
+	{
+		*src = attr.devicePointer;
+		c.zeroCopyBytes += bytes;
+		return GSP_OK;
+	}
 	size_t cap = c.dAosScratchCap;
 	uint8_t* ptr = (uint8_t*)c.dAosScratch;
 	GSP_CUDA(ensureDevice(ptr, cap, bytes, false, c.stream));
 	c.dAosScratch = ptr; c.dAosScratchCap = cap;
 	GSP_CUDA(cudaMemcpyAsync(c.dAosScratch, aos, bytes, cudaMemcpyHostToDevice, c.stream));
+	*src = c.dAosScratch;
 	return GSP_OK;
+}
+
+int gsp_pin_host(void* ptr, size_t bytes)
+{
+	if (!ptr || !bytes)
+		return GSP_ERR_INVALID;
+	cudaError_t err = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+	if (err == cudaErrorHostMemoryAlreadyRegistered)
+	{
+		cudaGetLastError();
+		return GSP_OK;
+	}
+	return err == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
+}
+
+int gsp_unpin_host(void* ptr)
+{
+	if (!ptr)
+		return GSP_ERR_INVALID;
+	cudaError_t err = cudaHostUnregister(ptr);
+	if (err != cudaSuccess)
+		cudaGetLastError();
+	return err == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
 }
 
 int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint32_t occupancy)
@@ -202,24 +261,26 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 	c.linkDirty = true; c.resultsValid = false;
 	if (occupancy == 0)
 		return GSP_OK;
-	int rc = uploadAos(c, aos, (size_t)stride * occupancy);
+	const void* src = nullptr;
+	int rc = resolveSource(c, aos, (size_t)stride * occupancy, &src);
 	if (rc) return rc;
-	// entity -> slot map sized by the largest live entity id
+	// one pass over the caller's bytes: SoA streams, entity / parent-entity ids, the largest live entity id
 	uint32_t* dMax = c.dCounters + kCtrError + 1;
 	GSP_CUDA(cudaMemsetAsync(dMax, 0, sizeof(uint32_t), c.stream));
-	launchMaxEntity(c, c.dAosScratch, stride, occupancy, dMax);
-	uint32_t maxEntity = 0;
-	GSP_CUDA(cudaMemcpyAsync(&maxEntity, dMax, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
-	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(cudaMemsetAsync(c.dError, 0, sizeof(uint32_t), c.stream));
+	launchStageTransforms(c, src, stride, 0, occupancy, true, dMax);
+	uint32_t* hScalars = c.hCounters + kCtrCount; // two pinned words past the frame counters
+	GSP_CUDA(cudaMemcpyAsync(&hScalars[0], dMax, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the caller's memory is free again
+	const uint32_t maxEntity = hScalars[0];
+	// entity -> slot map sized by the largest live entity id, then parent slots and chain lengths from the SoA copy
 	GSP_CUDA(ensureDevice32(t.entityToSlot, t.entityCap, (size_t)maxEntity + 1));
 	GSP_CUDA(cudaMemsetAsync(t.entityToSlot, 0, (size_t)t.entityCap * sizeof(uint32_t), c.stream));
-	GSP_CUDA(cudaMemsetAsync(c.dError, 0, sizeof(uint32_t), c.stream));
-	launchStageTransforms(c, c.dAosScratch, stride, 0, occupancy, true);
-	uint32_t error = 0;
-	GSP_CUDA(cudaMemcpyAsync(&error, c.dError, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	launchBuildHierarchy(c);
+	GSP_CUDA(cudaMemcpyAsync(&hScalars[1], c.dError, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
 	GSP_CUDA(cudaGetLastError());
-	if (error)
+	if (hScalars[1])
 		return fail(c, GSP_ERR_HIERARCHY, "gsp_set_transforms: a parent entity has no TransformComponent");
 	return GSP_OK;
 }
@@ -235,9 +296,10 @@ int gsp_update_transforms(gsp_context* ctx, const void* aos, uint32_t stride, ui
 		return GSP_OK;
 	GSP_CUDA(cudaSetDevice(c.device));
 	// `aos` is the pool base (same pointer meaning as gsp_set_transforms); only the dirty range is uploaded.
-	int rc = uploadAos(c, (const uint8_t*)aos + (size_t)first * stride, (size_t)stride * count);
+	const void* src = nullptr;
+	int rc = resolveSource(c, (const uint8_t*)aos + (size_t)first * stride, (size_t)stride * count, &src);
 	if (rc) return rc;
-	launchStageTransforms(c, c.dAosScratch, stride, first, count, false);
+	launchStageTransforms(c, src, stride, first, count, false, nullptr);
 	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the scratch buffer and the caller's memory are free again
 	GSP_CUDA(cudaGetLastError());
 	c.resultsValid = false;
@@ -301,9 +363,10 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 	c.linkDirty = true; c.resultsValid = false;
 	if (occupancy == 0)
 		return GSP_OK;
-	int rc = uploadAos(c, aos, (size_t)stride * occupancy);
+	const void* src = nullptr;
+	int rc = resolveSource(c, aos, (size_t)stride * occupancy, &src);
 	if (rc) return rc;
-	launchStagePool(c, pool, c.dAosScratch, stride, occupancy);
+	launchStagePool(c, pool, src, stride, occupancy);
 	if (readyCounts)
 		GSP_CUDA(cudaMemcpyAsync(p.ready, readyCounts, occupancy, cudaMemcpyHostToDevice, c.stream));
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
@@ -486,6 +549,11 @@ int gsp_run_async(gsp_context* ctx)
 	if (!c.viewsSet)
 		return fail(c, GSP_ERR_STATE, "gsp_run: gsp_set_views has not been called");
 	GSP_CUDA(cudaSetDevice(c.device));
+	if (c.fetchInFlight) // the previous frame's lists are still travelling out of the record arena
+	{
+		int rc = fetchWait(c);
+		if (rc) return rc;
+	}
 	if (c.layoutDirty)
 	{
 		int rc = rebuildLayout(c);
@@ -600,6 +668,11 @@ static int downloadSegment(Context& c, int seg, const gsp_record** records)
 		std::fill(c.segDownloaded.begin(), c.segDownloaded.end(), 0);
 	}
 	uint32_t count = segmentCount(c, s);
+	if (c.segDownloaded[seg] == 2)
+	{
+		int rc = fetchWait(c);
+		if (rc) return rc;
+	}
 	if (!c.segDownloaded[seg] && count)
 	{
 		GSP_CUDA(cudaMemcpyAsync(c.hRecords + s.offset, c.records + s.offset, (size_t)count * sizeof(gsp_record),
@@ -609,6 +682,67 @@ static int downloadSegment(Context& c, int seg, const gsp_record** records)
 	}
 	*records = c.hRecords + s.offset;
 	return GSP_OK;
+}
+
+// Enqueues the download of every list that has not travelled yet on the context's COPY stream (ordered after the frame by
+// an event), so the caller — and gsp_writeback_visible's host-side scatter — overlap the transfer.
+static int fetchAllAsync(Context& c)
+{
+	if (!c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	GSP_CUDA(cudaSetDevice(c.device));
+	if (c.hRecordsCap < c.arenaElems || !c.hRecords)
+	{
+		GSP_CUDA(cudaStreamSynchronize(c.copyStream));
+		cudaFreeHost(c.hRecords); c.hRecords = nullptr; c.hRecordsCap = 0;
+		GSP_CUDA(cudaMallocHost((void**)&c.hRecords, std::max<size_t>(c.arenaElems, 16) * sizeof(gsp_record)));
+		c.hRecordsCap = std::max<size_t>(c.arenaElems, 16);
+		std::fill(c.segDownloaded.begin(), c.segDownloaded.end(), 0);
+	}
+	bool any = false;
+	for (size_t seg = 0; seg < c.segments.size(); seg++)
+	{
+		const Segment& s = c.segments[seg];
+		const uint32_t count = segmentCount(c, s);
+		if (c.segDownloaded[seg] || !count)
+			continue;
+		if (!any)
+		{
+			GSP_CUDA(cudaEventRecord(c.copyEvent, c.stream));
+			GSP_CUDA(cudaStreamWaitEvent(c.copyStream, c.copyEvent, 0));
+			any = true;
+		}
+		GSP_CUDA(cudaMemcpyAsync(c.hRecords + s.offset, c.records + s.offset, (size_t)count * sizeof(gsp_record),
+			cudaMemcpyDeviceToHost, c.copyStream));
+		c.segDownloaded[seg] = 2; // in flight
+	}
+	c.fetchInFlight = c.fetchInFlight || any;
+	return GSP_OK;
+}
+
+static int fetchWait(Context& c)
+{
+	if (!c.fetchInFlight)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	GSP_CUDA(cudaStreamSynchronize(c.copyStream));
+	for (auto& d : c.segDownloaded)
+		if (d == 2) d = 1;
+	c.fetchInFlight = false;
+	return GSP_OK;
+}
+
+int gsp_fetch_all_async(gsp_context* ctx)
+{
+	return ctx ? fetchAllAsync(ctx->c) : GSP_ERR_INVALID;
+}
+
+int gsp_fetch_all(gsp_context* ctx)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	int rc = fetchAllAsync(ctx->c);
+	return rc ? rc : fetchWait(ctx->c);
 }
 
 uint32_t gsp_unsorted_buffer_count(const gsp_context* ctx, uint32_t view)
@@ -768,30 +902,126 @@ int gsp_export_runs(gsp_context* ctx, uint32_t* dKeys, uint32_t* dPayloads, uint
 	return GSP_OK;
 }
 
+} // extern "C"
+
+// Runs fn(first, last) over [0, n) on a few host threads (the write-back scatter touches every cache line of the pool).
+template<class F>
+static void parallelFor(uint32_t n, F fn)
+{
+	uint32_t threads = std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+	if (n < (1u << 18))
+		threads = 1;
+	if (threads == 1)
+	{
+		fn(0u, n);
+		return;
+	}
+	std::vector<std::thread> pool;
+	const uint32_t per = ((n + threads - 1) / threads + 31u) & ~31u;
+	for (uint32_t t = 0; t < threads; t++)
+	{
+		const uint32_t first = std::min<uint64_t>((uint64_t)t * per, n), last = std::min<uint64_t>((uint64_t)first + per, n);
+		if (first < last)
+			pool.emplace_back([=]{ fn(first, last); });
+	}
+	for (auto& th : pool)
+		th.join();
+}
+
+// Mapped pinned host words the write-back kernels store into directly (+2 trailing words: device counter mirror).
+static int ensureVisibleScratch(Context& c, size_t words)
+{
+	if (c.visScratchCap >= words && c.hVisible)
+		return GSP_OK;
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	cudaFreeHost(c.hVisible);
+	c.hVisible = nullptr; c.dVisMapped = nullptr; c.visScratchCap = 0;
+	GSP_CUDA(cudaHostAlloc((void**)&c.hVisible, (words + 2) * sizeof(uint32_t), cudaHostAllocMapped));
+	GSP_CUDA(cudaHostGetDevicePointer((void**)&c.dVisMapped, c.hVisible, 0));
+	if (!c.dVisScratch)
+		GSP_CUDA(cudaMalloc((void**)&c.dVisScratch, 2 * sizeof(uint32_t)));
+	c.visScratchCap = words;
+	return GSP_OK;
+}
+
+static int checkWriteback(Context& c, uint32_t pool, void* aos, uint32_t stride, const char* who)
+{
+	if (pool >= c.poolCount || !aos || stride < kMcMinStride)
+	{
+		c.error = std::string(who) + ": bad pool, pointer or stride";
+		return GSP_ERR_INVALID;
+	}
+	if (!c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	return GSP_OK;
+}
+
+extern "C"
+{
+
 int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride)
 {
 	if (!ctx)
 		return GSP_ERR_INVALID;
 	Context& c = ctx->c;
-	if (pool >= c.poolCount || !aos || stride < kMcMinStride)
-		return fail(c, GSP_ERR_INVALID, "gsp_writeback_visible: bad pool, pointer or stride");
-	if (!c.resultsValid)
-		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
+	int rc = checkWriteback(c, pool, aos, stride, "gsp_writeback_visible");
+	if (rc) return rc;
 	auto& p = c.pools[pool];
 	if (!p.visibleValid || p.occupancy == 0)
 		return GSP_OK; // the reference does not touch isVisible of pools the main view skipped (mesh.cpp:426,482)
 	GSP_CUDA(cudaSetDevice(c.device));
-	if (c.hVisibleCap < p.occupancy || !c.hVisible)
-	{
-		cudaFreeHost(c.hVisible); c.hVisible = nullptr; c.hVisibleCap = 0;
-		GSP_CUDA(cudaMallocHost((void**)&c.hVisible, p.occupancy));
-		c.hVisibleCap = p.occupancy;
-	}
-	GSP_CUDA(cudaMemcpyAsync(c.hVisible, p.visible, p.occupancy, cudaMemcpyDeviceToHost, c.stream));
+	const size_t words = ((size_t)p.occupancy + 31) / 32;
+	rc = ensureVisibleScratch(c, words);
+	if (rc) return rc;
+	launchPackVisible(c, pool, c.dVisMapped);
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(cudaGetLastError());
 	uint8_t* dst = (uint8_t*)aos + kMcVisible;
-	for (uint32_t i = 0; i < p.occupancy; i++)
-		dst[(size_t)i * stride] = c.hVisible[i];
+	const uint32_t* bits = c.hVisible;
+	parallelFor(p.occupancy, [=](uint32_t first, uint32_t last) {
+		for (uint32_t i = first; i < last; i++)
+		{
+			const uint8_t v = (uint8_t)((bits[i >> 5] >> (i & 31u)) & 1u);
+			uint8_t* d = dst + (size_t)i * stride;
+			if (*d != v) // (unchanged bytes are only read: no dirty cache lines to write back)
+				*d = v;
+		}
+	});
+	return GSP_OK;
+}
+
+int gsp_writeback_visible_delta(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride, uint32_t* changedOut)
+{
+	if (changedOut)
+		*changedOut = 0;
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	int rc = checkWriteback(c, pool, aos, stride, "gsp_writeback_visible_delta");
+	if (rc) return rc;
+	auto& p = c.pools[pool];
+	if (!p.visibleValid || p.occupancy == 0)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	rc = ensureVisibleScratch(c, p.occupancy); // worst case every slot changes
+	if (rc) return rc;
+	uint32_t* dCount = c.dVisScratch;
+	GSP_CUDA(cudaMemsetAsync(dCount, 0, sizeof(uint32_t), c.stream));
+	launchVisibleDelta(c, pool, c.dVisMapped, dCount, c.dVisMapped + c.visScratchCap);
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(cudaGetLastError());
+	const uint32_t changed = c.hVisible[c.visScratchCap];
+	if (changed)
+	{
+		uint8_t* dst = (uint8_t*)aos + kMcVisible;
+		const uint32_t* list = c.hVisible;
+		parallelFor(changed, [=](uint32_t first, uint32_t last) {
+			for (uint32_t k = first; k < last; k++)
+				dst[(size_t)(list[k] & 0x7fffffffu) * stride] = (uint8_t)(list[k] >> 31);
+		});
+	}
+	if (changedOut)
+		*changedOut = changed;
 	return GSP_OK;
 }
 

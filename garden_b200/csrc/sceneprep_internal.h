@@ -31,6 +31,9 @@ constexpr uint32_t kTfDepthShift = 8; // bits 8..15: chain length, saturating at
 constexpr uint32_t kTfDepthMax = 255;
 // mesh flags (SoA): static filter of mesh.cpp:140-147 (entity != 0 && isEnabled && !degenerate AABB)
 constexpr uint8_t kMfCandidate = 1;
+// the isVisible byte the HOST currently holds for this slot (as uploaded, or as last written back): bit set = 1;
+// kMfHostVisibleOdd = the host byte is neither 0 nor 1 (always rewritten by the delta write-back)
+constexpr uint8_t kMfHostVisible = 2, kMfHostVisibleOdd = 4;
 
 // ---- device SoA mirrors -------------------------------------------------------------------------------------------
 struct TransformsDev
@@ -116,6 +119,8 @@ struct Context
 {
 	int device = 0;
 	cudaStream_t ownStream = nullptr, stream = nullptr;
+	cudaStream_t copyStream = nullptr; cudaEvent_t copyEvent = nullptr; // list downloads overlap the caller / the write-back
+	bool fetchInFlight = false;
 	std::string error;
 
 	TransformsDev tf;
@@ -153,9 +158,10 @@ struct Context
 
 	// host staging
 	void* dAosScratch = nullptr; size_t dAosScratchCap = 0;
+	uint64_t zeroCopyBytes = 0; // bytes the staging kernels read straight from pinned host memory
 	gsp_record* hRecords = nullptr; size_t hRecordsCap = 0; // pinned download area (arena-shaped)
 	std::vector<uint8_t> segDownloaded;
-	uint8_t* hVisible = nullptr; size_t hVisibleCap = 0;
+	uint32_t* hVisible = nullptr; uint32_t* dVisMapped = nullptr; uint32_t* dVisScratch = nullptr; size_t visScratchCap = 0; // isVisible write-back: bit words / changed-slot list (+1 count word)
 	uint32_t launchCount = 0;
 	bool profiling = false;
 	cudaEvent_t phaseEvents[8] = {};
@@ -178,12 +184,15 @@ constexpr uint32_t kSortThreads = 256;
 constexpr uint32_t kSortTile = kSortItems * kSortThreads;
 
 // ---- kernel launchers (each returns the number of kernels it launched, or throws nothing; errors via cudaGetLastError) ----
-uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full);
-uint32_t launchMaxEntity(Context& c, const void* dAos, uint32_t stride, uint32_t count, uint32_t* dMax);
+uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full,
+	uint32_t* dMaxEntity);
+uint32_t launchBuildHierarchy(Context& c);
 uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy);
 uint32_t launchLink(Context& c);
 uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter);
 uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);
+uint32_t launchPackVisible(Context& c, uint32_t pool, uint32_t* dBits);
+uint32_t launchVisibleDelta(Context& c, uint32_t pool, uint32_t* list, uint32_t* dCount, uint32_t* hCountMapped);
 
 } // namespace gsp

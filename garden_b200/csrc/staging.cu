@@ -7,58 +7,119 @@
 //   MeshRenderComponent (include/garden/system/render/mesh.hpp:45-55).
 #include "sceneprep_internal.h"
 #include "sceneprep_math.cuh"
+#include <algorithm>
 
 namespace gsp
 {
 
+static inline uint32_t blocksFor(uint32_t n, uint32_t per) { return (n + per - 1) / per; }
+
 __device__ __forceinline__ uint32_t ldU32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ float ldF32(const uint8_t* p) { return *reinterpret_cast<const float*>(p); }
 
-__global__ void __launch_bounds__(256) kMaxEntity(const uint8_t* __restrict__ aos, uint32_t stride, uint32_t count,
-	uint32_t* __restrict__ maxOut)
+// ---- tile loader ------------------------------------------------------------------------------------------------------------
+// A block pulls `tileSlots` consecutive AoS slots (tileSlots * stride bytes, a multiple of 16) into shared memory with
+// coalesced 128-bit loads, many in flight per thread, and the fields are picked out of shared memory afterwards. The source
+// may be device memory (the upload scratch), or PINNED HOST memory read directly over PCIe ("zero copy": no intermediate
+// device buffer, the re-layout overlaps the transfer). Sources that are not 16-byte aligned use 32-bit loads.
+constexpr uint32_t kStageThreads = 256;
+
+__device__ __forceinline__ uint4 ldStream128(const uint4* p)
 {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t e = i < count ? ldU32(aos + (size_t)i * stride + kTfEntity) : 0;
-	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
-	if ((threadIdx.x & 31) == 0 && e)
-		atomicMax(maxOut, e);
+	uint4 v;
+	asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
 }
 
-// One thread per transform slot. `full` also (re)builds the hierarchy inputs and the entity map.
-__global__ void __launch_bounds__(256) kStageTransforms(const uint8_t* __restrict__ aos, uint32_t stride,
-	uint32_t first, uint32_t count, int full, float4* __restrict__ rot, float4* __restrict__ posSx,
+__device__ __forceinline__ void loadTile(uint8_t* sTile, const uint8_t* __restrict__ src, uint32_t bytes)
+{
+	if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)
+	{
+		const uint4* s4 = reinterpret_cast<const uint4*>(src);
+		uint4* d4 = reinterpret_cast<uint4*>(sTile);
+		const uint32_t n = bytes >> 4; // (bytes is a multiple of 4; the tail below handles the rest)
+		constexpr uint32_t kBatch = 5;
+		for (uint32_t i0 = threadIdx.x; i0 < n; i0 += kStageThreads * kBatch)
+		{
+			uint4 v[kBatch];
+			#pragma unroll
+			for (uint32_t b = 0; b < kBatch; b++)
+				if (i0 + b * kStageThreads < n)
+					v[b] = ldStream128(s4 + i0 + b * kStageThreads);
+			#pragma unroll
+			for (uint32_t b = 0; b < kBatch; b++)
+				if (i0 + b * kStageThreads < n)
+					d4[i0 + b * kStageThreads] = v[b];
+		}
+		for (uint32_t i = (n << 2) + threadIdx.x; i < (bytes >> 2); i += kStageThreads)
+			reinterpret_cast<uint32_t*>(sTile)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+	}
+	else
+	{
+		const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+		uint32_t* d1 = reinterpret_cast<uint32_t*>(sTile);
+		for (uint32_t i = threadIdx.x; i < (bytes >> 2); i += kStageThreads)
+			d1[i] = s1[i];
+	}
+	__syncthreads();
+}
+
+// One block per tile of transform slots. `full` also (re)builds the hierarchy inputs (entity, parent entity, the largest
+// entity id); the entity -> slot map is built from the SoA copy afterwards (kBuildEntityMap), once its size is known.
+__global__ void __launch_bounds__(kStageThreads) kStageTransforms(const uint8_t* __restrict__ aos, uint32_t stride,
+	uint32_t first, uint32_t count, int full, uint32_t tileSlots, float4* __restrict__ rot, float4* __restrict__ posSx,
 	float2* __restrict__ sYZ, uint16_t* __restrict__ flags, uint32_t* __restrict__ entity,
-	uint32_t* __restrict__ parentEntity, uint32_t* __restrict__ entityToSlot)
+	uint32_t* __restrict__ parentEntity, uint32_t* __restrict__ maxEntity)
+{
+	extern __shared__ __align__(16) uint8_t sTile[];
+	const uint32_t tileFirst = blockIdx.x * tileSlots;
+	const uint32_t n = min(tileSlots, count - tileFirst);
+	loadTile(sTile, aos + (size_t)tileFirst * stride, n * stride);
+	uint32_t emax = 0;
+	for (uint32_t j = threadIdx.x; j < n; j += kStageThreads)
+	{
+		const uint32_t slot = first + tileFirst + j;
+		const uint8_t* t = sTile + (size_t)j * stride;
+		const uint32_t e = ldU32(t + kTfEntity);
+		const float4 q = make_float4(ldF32(t + kTfRot), ldF32(t + kTfRot + 4), ldF32(t + kTfRot + 8), ldF32(t + kTfRot + 12));
+		const float4 ps = make_float4(ldF32(t + kTfPos), ldF32(t + kTfPos + 4), ldF32(t + kTfPos + 8), ldF32(t + kTfScale));
+		const float2 syz = make_float2(ldF32(t + kTfScale + 4), ldF32(t + kTfScale + 8));
+		rot[slot] = q; posSx[slot] = ps; sYZ[slot] = syz;
+		const uint32_t w = ldU32(t + kTfSelfActive); // bytes 72..75: selfActive, ancestorsActive, modelWithAncestors, pad
+		uint16_t f = 0;
+		Mat43 unused;
+		if (!localModel43Fast<true>(ps.x, ps.y, ps.z, q.x, q.y, q.z, q.w, ps.w, syz.x, syz.y, unused))
+			f |= kTfExactLocal; // the per-frame kernel must use the guarded 4-lane code for this transform
+		if (e) f |= kTfLive;
+		if ((w & 0xffu) && (w & 0xff00u)) f |= kTfActive;   // isActive(), transform.hpp:110
+		if (w & 0xff0000u) f |= kTfAncestors;                // modelWithAncestors, transform.hpp:60,200
+		// the upper byte holds the chain length (kComputeDepth); a TRS-only update keeps it
+		flags[slot] = full ? f : (uint16_t)(f | (flags[slot] & ~((1u << kTfDepthShift) - 1u)));
+		if (full)
+		{
+			entity[slot] = e;
+			parentEntity[slot] = e ? ldU32(t + kTfParent) : 0;
+			emax = max(emax, e);
+		}
+	}
+	if (full)
+	{
+		emax = __reduce_max_sync(0xffffffffu, emax);
+		if ((threadIdx.x & 31) == 0 && emax)
+			atomicMax(maxEntity, emax);
+	}
+}
+
+// entity id -> transform slot + 1 (0 = the entity has no TransformComponent)
+__global__ void __launch_bounds__(256) kBuildEntityMap(uint32_t count, const uint32_t* __restrict__ entity,
+	uint32_t* __restrict__ entityToSlot)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
 		return;
-	uint32_t slot = first + i;
-	const uint8_t* t = aos + (size_t)i * stride;
-	uint32_t e = ldU32(t + kTfEntity);
-	const float4 q = make_float4(ldF32(t + kTfRot), ldF32(t + kTfRot + 4), ldF32(t + kTfRot + 8), ldF32(t + kTfRot + 12));
-	const float4 ps = make_float4(ldF32(t + kTfPos), ldF32(t + kTfPos + 4), ldF32(t + kTfPos + 8), ldF32(t + kTfScale));
-	const float2 syz = make_float2(ldF32(t + kTfScale + 4), ldF32(t + kTfScale + 8));
-	rot[slot] = q; posSx[slot] = ps; sYZ[slot] = syz;
-	uint32_t w = ldU32(t + kTfSelfActive); // bytes 72..75: selfActive, ancestorsActive, modelWithAncestors, pad
-	uint16_t f = 0;
-	Mat43 unused;
-	if (!localModel43Fast<true>(ps.x, ps.y, ps.z, q.x, q.y, q.z, q.w, ps.w, syz.x, syz.y, unused))
-		f |= kTfExactLocal; // the per-frame kernel must use the guarded 4-lane code for this transform
-	if (e) f |= kTfLive;
-	if ((w & 0xffu) && (w & 0xff00u)) f |= kTfActive;   // isActive(), transform.hpp:110
-	if (w & 0xff0000u) f |= kTfAncestors;                // modelWithAncestors, transform.hpp:60,200
-	// the upper byte holds the chain length (kComputeDepth); a TRS-only update keeps it
-	flags[slot] = full ? f : (uint16_t)(f | (flags[slot] & ~((1u << kTfDepthShift) - 1u)));
-	if (full)
-	{
-		entity[slot] = e;
-		parentEntity[slot] = e ? ldU32(t + kTfParent) : 0;
-		if (e)
-			entityToSlot[e] = slot + 1;
-	}
+	const uint32_t e = entity[i];
+	if (e)
+		entityToSlot[e] = i + 1;
 }
 
 // parent entity id -> parent transform slot. A live parent id without a TransformComponent is an error
@@ -98,25 +159,36 @@ __global__ void __launch_bounds__(256) kComputeDepth(uint32_t count, const uint3
 	flags[i] = (uint16_t)((flags[i] & ((1u << kTfDepthShift) - 1u)) | (depth << kTfDepthShift));
 }
 
-// One thread per mesh-component slot: AABB, owner entity and the static part of the filter at mesh.cpp:140-147.
-__global__ void __launch_bounds__(256) kStagePool(const uint8_t* __restrict__ aos, uint32_t stride, uint32_t count,
-	float4* __restrict__ aabbA, float2* __restrict__ aabbB, uint32_t* __restrict__ entity, uint8_t* __restrict__ flags)
+// One block per tile of mesh-component slots: AABB, owner entity, the static part of the filter at mesh.cpp:140-147, and the
+// isVisible byte the host currently holds (for the changed-slots-only write-back).
+__global__ void __launch_bounds__(kStageThreads) kStagePool(const uint8_t* __restrict__ aos, uint32_t stride, uint32_t count,
+	uint32_t tileSlots, float4* __restrict__ aabbA, float2* __restrict__ aabbB, uint32_t* __restrict__ entity,
+	uint8_t* __restrict__ flags)
 {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count)
-		return;
-	const uint8_t* m = aos + (size_t)i * stride;
-	uint32_t e = ldU32(m + kMcEntity);
-	uint32_t w = ldU32(m + 12); // bytes 12..15: reserved2 (u16), isEnabled, isVisible
-	float mnx = ldF32(m + kMcAabbMin), mny = ldF32(m + kMcAabbMin + 4), mnz = ldF32(m + kMcAabbMin + 8);
-	float mxx = ldF32(m + kMcAabbMax), mxy = ldF32(m + kMcAabbMax + 4), mxz = ldF32(m + kMcAabbMax + 8);
-	aabbA[i] = make_float4(mnx, mny, mnz, mxx);
-	aabbB[i] = make_float2(mxy, mxz);
-	entity[i] = e;
-	// aabb.getSize() = max - min, fixW(), areAllTrue(size <= 0)  (mesh.cpp:140-142, aabb.hpp:142)
-	bool degenerate = (__fsub_rn(mxx, mnx) <= 0.0f) && (__fsub_rn(mxy, mny) <= 0.0f) && (__fsub_rn(mxz, mnz) <= 0.0f);
-	bool enabled = (w & 0xff0000u) != 0;
-	flags[i] = (e && enabled && !degenerate) ? kMfCandidate : 0;
+	extern __shared__ __align__(16) uint8_t sTile[];
+	const uint32_t tileFirst = blockIdx.x * tileSlots;
+	const uint32_t n = min(tileSlots, count - tileFirst);
+	loadTile(sTile, aos + (size_t)tileFirst * stride, n * stride);
+	for (uint32_t j = threadIdx.x; j < n; j += kStageThreads)
+	{
+		const uint32_t i = tileFirst + j;
+		const uint8_t* m = sTile + (size_t)j * stride;
+		uint32_t e = ldU32(m + kMcEntity);
+		uint32_t w = ldU32(m + 12); // bytes 12..15: reserved2 (u16), isEnabled, isVisible
+		float mnx = ldF32(m + kMcAabbMin), mny = ldF32(m + kMcAabbMin + 4), mnz = ldF32(m + kMcAabbMin + 8);
+		float mxx = ldF32(m + kMcAabbMax), mxy = ldF32(m + kMcAabbMax + 4), mxz = ldF32(m + kMcAabbMax + 8);
+		aabbA[i] = make_float4(mnx, mny, mnz, mxx);
+		aabbB[i] = make_float2(mxy, mxz);
+		entity[i] = e;
+		// aabb.getSize() = max - min, fixW(), areAllTrue(size <= 0)  (mesh.cpp:140-142, aabb.hpp:142)
+		bool degenerate = (__fsub_rn(mxx, mnx) <= 0.0f) && (__fsub_rn(mxy, mny) <= 0.0f) && (__fsub_rn(mxz, mnz) <= 0.0f);
+		bool enabled = (w & 0xff0000u) != 0;
+		uint8_t f = (e && enabled && !degenerate) ? kMfCandidate : 0;
+		const uint32_t hostVisible = w >> 24;
+		if (hostVisible == 1) f |= kMfHostVisible;          // the host byte is a clean `true`
+		else if (hostVisible != 0) f |= kMfHostVisibleOdd;  // neither 0 nor 1: always rewritten
+		flags[i] = f;
+	}
 }
 
 __global__ void __launch_bounds__(256) kLinkPool(uint32_t count, const uint32_t* __restrict__ entity,
@@ -130,32 +202,42 @@ __global__ void __launch_bounds__(256) kLinkPool(uint32_t count, const uint32_t*
 	tslot[i] = s ? s - 1 : kNone;
 }
 
-static inline uint32_t blocksFor(uint32_t n, uint32_t per) { return (n + per - 1) / per; }
+// Slots per tile: a multiple of 4 (tile bytes stay a multiple of 16) that fits the shared-memory budget.
+static uint32_t tileSlotsFor(uint32_t stride, size_t& smemBytes)
+{
+	const size_t budget = 60 * 1024;
+	uint32_t slots = (uint32_t)std::min<size_t>(kStageThreads, budget / stride) & ~3u;
+	if (slots == 0) slots = 1; // (stride > 15 KB: one slot per tile, still correct)
+	smemBytes = (size_t)slots * stride;
+	return slots;
+}
 
-uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full)
+uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full,
+	uint32_t* dMaxEntity)
 {
 	if (count == 0)
 		return 0;
 	auto& t = c.tf;
-	kStageTransforms<<<blocksFor(count, 256), 256, 0, c.stream>>>((const uint8_t*)dAos, stride, first, count, full ? 1 : 0,
-		t.rot, t.posSx, t.sYZ, t.flags, t.entity, t.parentEntity, t.entityToSlot);
-	uint32_t n = 1;
-	if (full)
-	{
-		kResolveParents<<<blocksFor(count, 256), 256, 0, c.stream>>>(count, t.parentEntity, t.entityToSlot, t.entityCap,
-			t.parent, c.dError);
-		kComputeDepth<<<blocksFor(count, 256), 256, 0, c.stream>>>(count, t.parent, t.flags);
-		n += 2;
-	}
-	return n;
+	size_t smem;
+	const uint32_t tileSlots = tileSlotsFor(stride, smem);
+	cudaFuncSetAttribute(kStageTransforms, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	kStageTransforms<<<blocksFor(count, tileSlots), kStageThreads, smem, c.stream>>>((const uint8_t*)dAos, stride, first, count,
+		full ? 1 : 0, tileSlots, t.rot, t.posSx, t.sYZ, t.flags, t.entity, t.parentEntity, dMaxEntity);
+	return 1;
 }
 
-uint32_t launchMaxEntity(Context& c, const void* dAos, uint32_t stride, uint32_t count, uint32_t* dMax)
+// After a full staging pass: entity map, parent slots, chain lengths (all from the SoA copy in HBM).
+uint32_t launchBuildHierarchy(Context& c)
 {
+	auto& t = c.tf;
+	const uint32_t count = t.occupancy;
 	if (count == 0)
 		return 0;
-	kMaxEntity<<<blocksFor(count, 256), 256, 0, c.stream>>>((const uint8_t*)dAos, stride, count, dMax);
-	return 1;
+	kBuildEntityMap<<<blocksFor(count, 256), 256, 0, c.stream>>>(count, t.entity, t.entityToSlot);
+	kResolveParents<<<blocksFor(count, 256), 256, 0, c.stream>>>(count, t.parentEntity, t.entityToSlot, t.entityCap,
+		t.parent, c.dError);
+	kComputeDepth<<<blocksFor(count, 256), 256, 0, c.stream>>>(count, t.parent, t.flags);
+	return 3;
 }
 
 uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy)
@@ -163,8 +245,11 @@ uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t s
 	if (occupancy == 0)
 		return 0;
 	auto& p = c.pools[pool];
-	kStagePool<<<blocksFor(occupancy, 256), 256, 0, c.stream>>>((const uint8_t*)dAos, stride, occupancy,
-		p.aabbA, p.aabbB, p.entity, p.flags);
+	size_t smem;
+	const uint32_t tileSlots = tileSlotsFor(stride, smem);
+	cudaFuncSetAttribute(kStagePool, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	kStagePool<<<blocksFor(occupancy, tileSlots), kStageThreads, smem, c.stream>>>((const uint8_t*)dAos, stride, occupancy,
+		tileSlots, p.aabbA, p.aabbB, p.entity, p.flags);
 	return 1;
 }
 

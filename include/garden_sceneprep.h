@@ -15,6 +15,7 @@
 #ifndef GARDEN_SCENEPREP_H
 #define GARDEN_SCENEPREP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -81,7 +82,10 @@ int gsp_set_stream(gsp_context* ctx, void* cudaStream);
 /* Replaces the per-entity Manager::tryGet<TransformComponent>() + field reads (mesh.cpp:149; ecsm.hpp:898-905).
  * `aos` = LinearPool<TransformComponent>::getData() (linear-pool.hpp:717), `stride` = sizeof(TransformComponent) = 80
  * (include/garden/system/transform.hpp:31-60), `occupancy` = getOccupancy() (linear-pool.hpp:734).
- * The memory is copied during the call (pageable or pinned host memory both work). */
+ * The memory is consumed during the call and may change afterwards. Pinned / registered host memory (cudaMallocHost,
+ * cudaHostRegister, gsp_pin_host) is read IN PLACE over PCIe by the staging kernel (no intermediate device buffer, the
+ * AoS -> SoA re-layout overlaps the transfer); device pointers are read in place; pageable memory is copied to a device
+ * scratch buffer first (slower: the driver stages it). */
 int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint32_t occupancy);
 /* Dirty range: re-stages position/rotation/scale/active flags of slots [first, first+count); `aos` is the pool base
  * (same pointer meaning as gsp_set_transforms), only the bytes of the range are read and uploaded. The hierarchy
@@ -96,6 +100,11 @@ int gsp_set_pool_count(gsp_context* ctx, uint32_t poolCount);
  * getReadyMeshesAsync override beyond the frustum test (e.g. sprite.cpp:90-97): ready instance count per slot. */
 int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint32_t drawReady, const void* aos,
 	uint32_t stride, uint32_t occupancy, uint32_t count, const uint8_t* readyCounts);
+
+/* Page-locks and maps `bytes` of caller memory (e.g. a LinearPool's storage after it (re)allocates, linear-pool.hpp:620-628)
+ * so that gsp_set_* / gsp_update_transforms read it in place. Already-registered ranges are accepted. Process-wide. */
+int gsp_pin_host(void* ptr, size_t bytes);
+int gsp_unpin_host(void* ptr);
 
 /* ---- per frame ---------------------------------------------------------------------------------------------------- */
 /* cameraPosition = CommonConstants::cameraPos (mesh.cpp:401), shared by every view of the frame. */
@@ -114,6 +123,12 @@ uint32_t gsp_sorted_buffer_count(const gsp_context* ctx, uint32_t view);
  * memory owned by the library, valid until the next gsp_run / gsp_destroy; the list is downloaded on first request. */
 int gsp_get_unsorted(gsp_context* ctx, uint32_t view, uint32_t buffer, const gsp_record** records,
 	uint32_t* drawCount, uint32_t* instanceCount);
+/* Downloads every list of the frame that has not travelled yet: all copies are enqueued back to back with ONE host
+ * synchronisation (gsp_get_unsorted / gsp_get_sorted afterwards return pointers without further copies). */
+int gsp_fetch_all(gsp_context* ctx);
+/* Same, but only enqueues the copies (on the context's copy stream, ordered after the frame): the transfer overlaps whatever
+ * the caller does next, e.g. gsp_writeback_visible. The first gsp_get_unsorted / gsp_get_sorted (or gsp_fetch_all) waits. */
+int gsp_fetch_all_async(gsp_context* ctx);
 /* sortedBuffers[buffer]->{drawCount, instanceCount} */
 int gsp_get_sorted_counts(gsp_context* ctx, uint32_t view, uint32_t buffer, uint32_t* drawCount, uint32_t* instanceCount);
 /* which = 0: transSortedMeshes / transDrawIndex, which = 1: uiSortedMeshes / uiDrawIndex */
@@ -147,6 +162,11 @@ int gsp_merge_gathered(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32
 /* Stores MeshRenderComponent::isVisible (offset 15) for every slot of `pool` exactly as the reference's main-view pass
  * does (mesh.cpp:144-146,152-153,161-167). No-op for pools the main view did not process. */
 int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride);
+/* Same result, but only the slots whose value differs from the byte the HOST holds are transferred and stored. The library
+ * knows that byte for every slot: it was uploaded with the pool by the last gsp_set_mesh_pool, or written by the previous
+ * gsp_writeback_visible[_delta]. Precondition: `aos` is that pool and nobody else changed its isVisible bytes since.
+ * `changed` (nullable) receives the number of bytes stored. */
+int gsp_writeback_visible_delta(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride, uint32_t* changed);
 /* World matrices (TransformComponent::calcModel(cameraPosition), transform.hpp:197-214) of pool slots as float4x3,
  * valid for slots that were visible in at least one view of the last frame. `out` = occupancy * 12 floats on the host. */
 int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out);

@@ -1,0 +1,145 @@
+"""Host boundary of the C ABI: where the staging kernels read the caller's AoS bytes from (pageable copy, pinned memory read
+in place over PCIe, device pointers, unaligned bases, wide derived components) and how isVisible travels back
+(full vs changed-slots-only). Every variant must give the oracle's lists bit for bit."""
+import numpy as np
+import pytest
+
+from garden_b200 import scenes, views as V
+
+from common import OracleRun, aos_inputs, compare_gpu_to_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene():
+    scene = scenes.config_scene("C3", n=70_001)
+    scene.camera_pos = np.array([2.0, 1.0, -4.0], np.float32)
+    views, _ = V.perspective_views([(0.7, -0.05)], 1.3, 16 / 9, 0.01)
+    return scene, views
+
+
+def _stage_and_run(sp, t, pools, rts, views, cam):
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(len(pools))
+    for k, m in enumerate(pools):
+        sp.set_mesh_pool(k, rts[k], m, m.dtype.itemsize, m.size)
+    sp.set_views(views, cam)
+    sp.run()
+
+
+def _oracle(t, pools, rts, views, cam):
+    return OracleRun((t, t.dtype.itemsize, t.size), [(m, m.dtype.itemsize, m.size) for m in pools], rts, views, cam)
+
+
+@pytest.mark.parametrize("source", ["pageable", "pinned", "pinned_unaligned", "device"])
+def test_upload_sources(oracle_built, sceneprep_lib, source):
+    import torch
+    from garden_b200.binding import ScenePrep, pin_host, unpin_host
+    scene, views = _scene()
+    t, pools = aos_inputs(scene, strides=[48, 112])
+    rts = [p.render_type for p in scene.pools]
+    orun = _oracle(t, pools, rts, views, scene.camera_pos)
+    keep = []
+    if source == "pinned":
+        for a in [t] + pools:
+            pin_host(a)
+        tt, pp = t, pools
+    elif source == "pinned_unaligned":
+        # a pool whose base is only 4-byte aligned (the 32-bit load path of the tile loader)
+        def shifted(a):
+            raw = torch.empty(a.nbytes + 64, dtype=torch.uint8, pin_memory=True)
+            keep.append(raw)
+            view = raw.numpy()[4:4 + a.nbytes].view(a.dtype)
+            view[...] = a
+            return view
+        tt, pp = shifted(t), [shifted(m) for m in pools]
+    elif source == "device":
+        def dev(a):
+            d = torch.from_numpy(a.view(np.uint8).copy()).cuda()
+            keep.append(d)
+            return d.data_ptr()
+        tt, pp = dev(t), [dev(m) for m in pools]
+    else:
+        tt, pp = t, pools
+    sp = ScenePrep(0)
+    sp.set_transforms(tt, t.dtype.itemsize, t.size)
+    sp.set_pool_count(len(pools))
+    for k, m in enumerate(pools):
+        sp.set_mesh_pool(k, rts[k], pp[k], m.dtype.itemsize, m.size)
+    sp.set_views(views, scene.camera_pos)
+    sp.run()
+    sp.fetch_all()
+    compare_gpu_to_oracle(sp, orun, rts, views, source)
+    sp.close()
+    if source == "pinned":
+        for a in [t] + pools:
+            unpin_host(a)
+
+
+def test_visible_writeback_full_and_delta(oracle_built, sceneprep_lib):
+    """The camera turns every frame; the pool is staged once. After each frame the host bytes must equal the oracle's
+    isVisible whether they travel as a full bit mask or as the list of changed slots."""
+    from garden_b200.binding import ScenePrep
+    scene, _ = _scene()
+    t, pools = aos_inputs(scene, strides=[48, 64])
+    rts = [p.render_type for p in scene.pools]
+    rng = np.random.default_rng(5)
+    for m in pools:  # garbage in the host bytes: 0, 1 and values that are neither
+        m["isVisible"] = rng.integers(0, 4, m.size).astype(np.uint8) * 85
+    def clone(m):  # raw byte copy (ndarray.copy() of a padded struct dtype need not preserve the padding bytes)
+        return np.frombuffer(bytearray(m.tobytes()), dtype=m.dtype)
+    full = [clone(m) for m in pools]
+    delta = [clone(m) for m in pools]
+    sp_full, sp_delta = ScenePrep(0), ScenePrep(0)
+    changed_counts = []
+    for frame in range(4):
+        views, _ = V.perspective_views([(0.7 + 0.15 * frame, -0.05)], 1.3, 16 / 9, 0.01)
+        if frame == 0:
+            _stage_and_run(sp_full, t, full, rts, views, scene.camera_pos)
+            _stage_and_run(sp_delta, t, delta, rts, views, scene.camera_pos)
+        else:
+            for sp in (sp_full, sp_delta):
+                sp.set_views(views, scene.camera_pos)
+                sp.run()
+        orun = OracleRun((t, t.dtype.itemsize, t.size), [(m, m.dtype.itemsize, m.size) for m in pools], rts, views,
+                         scene.camera_pos)
+        total_changed = 0
+        for k in range(len(pools)):
+            sp_full.writeback_visible(k, full[k], full[k].dtype.itemsize)
+            total_changed += sp_delta.writeback_visible_delta(k, delta[k], delta[k].dtype.itemsize)
+            want = orun.views[0]["visible"][k]
+            assert np.array_equal(full[k]["isVisible"], want), f"frame {frame} pool {k}: full write-back differs"
+            assert np.array_equal(delta[k]["isVisible"], want), f"frame {frame} pool {k}: delta write-back differs"
+            # nothing but the isVisible byte may change
+            for got in (full[k], delta[k]):
+                a = got.view(np.uint8).reshape(-1, got.dtype.itemsize).copy()
+                b = pools[k].view(np.uint8).reshape(-1, got.dtype.itemsize).copy()
+                a[:, 15] = 0; b[:, 15] = 0
+                assert np.array_equal(a, b)
+        changed_counts.append(total_changed)
+    # frame 0 rewrites the garbage; later frames move only what the turning camera changed
+    assert changed_counts[0] > changed_counts[1] > 0, changed_counts
+    # mixing the two: a full write-back keeps the device's picture of the host bytes in step
+    views, _ = V.perspective_views([(2.0, 0.0)], 1.3, 16 / 9, 0.01)
+    sp_delta.set_views(views, scene.camera_pos)
+    sp_delta.run()
+    for k in range(len(pools)):
+        sp_delta.writeback_visible(k, delta[k], delta[k].dtype.itemsize)
+        assert sp_delta.writeback_visible_delta(k, delta[k], delta[k].dtype.itemsize) == 0
+    sp_full.close(); sp_delta.close()
+
+
+def test_wide_component_stride(oracle_built, sceneprep_lib):
+    """Derived mesh components are larger than MeshRenderComponent (getMeshComponentSize(), mesh.hpp:60-147): strides far
+    past the tile loader's 256-slot budget."""
+    from garden_b200.binding import ScenePrep
+    scene = scenes.config_scene("C2", n=9_000)
+    scene.camera_pos = np.array([1.0, 0.5, -2.0], np.float32)
+    views, _ = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    t, pools = aos_inputs(scene, strides=[1024])
+    rts = [p.render_type for p in scene.pools]
+    orun = _oracle(t, pools, rts, views, scene.camera_pos)
+    sp = ScenePrep(0)
+    _stage_and_run(sp, t, pools, rts, views, scene.camera_pos)
+    compare_gpu_to_oracle(sp, orun, rts, views, "stride 1024")
+    sp.close()
