@@ -49,6 +49,22 @@ def camera_pos():
     return np.array([12.5, 3.0, -7.25], dtype=np.float32)
 
 
+def load_traffic(workload: str, n: int, kernel_prefix: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same workload and
+    size (profiles/*_ncu_traffic_*.json, written by tools/ncu_traffic.py); None when no capture matches."""
+    for path in sorted((ROOT / "profiles").glob("*ncu_traffic*.json"), reverse=True):
+        try:
+            doc = json.loads(path.read_text())
+        except Exception:
+            continue
+        if doc.get("workload") != workload or int(doc.get("entities", 0)) != n:
+            continue
+        for k in doc.get("kernels", []):
+            if kernel_prefix in k["kernel"]:
+                return {"bytes": int(k["traffic_bytes"]), "source": f"profiles/{path.name}"}
+    return None
+
+
 def load_peaks():
     path = ROOT / "MEASURED_PEAKS.json"
     if path.exists():
@@ -359,10 +375,16 @@ def run_b200_arm(args):
         roofline = {
             "bound": "hbm", "kernel": kernels[dom]["name"], "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
             "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes": int(kernels[dom]["bytes"]),
             "frame": {"algorithmic_bytes": int(alg_bytes), "achieved": round(frame_gbs, 1), "frac": round(frame_gbs / peak, 3),
                       "formula": "75*N + 132*SumVis (SURVEY.md 8d), per GPU, over the timed ms_per_step"},
             "kernels": kernels,
         }
+        kernel_symbol = {1: "kCull", 2: "kScatter", 4: "kSortPass", 5: "kEmit"}[(1, 2, 4, 5)[dom]]
+        traffic = load_traffic(args.workload, n, kernel_symbol)
+        if traffic:
+            roofline["traffic"] = traffic["bytes"]
+            roofline["traffic_source"] = traffic["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -405,8 +427,8 @@ def main():
     ap.add_argument("--entities", type=int, default=0, help="override N per GPU (default: the workload's N)")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-sample", type=int, default=1_000_000, help="entities in the CPU reference sample")
-    ap.add_argument("--ref-steps", type=int, default=3)
+    ap.add_argument("--ref-sample", type=int, default=2_000_000, help="entities in the CPU reference sample")
+    ap.add_argument("--ref-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
