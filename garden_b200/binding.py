@@ -47,6 +47,10 @@ SYMBOLS = {
     "gsp_get_list_counts": (_i32, [_vp, _vp, _u32]),
     "gsp_export_runs": (_i32, [_vp, _vp, _vp, _u32]),
     "gsp_merge_gathered": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsp_exchange_block_words": (_u32, [_u32]),
+    "gsp_merge_plan_words": (_u32, [_u32, _u32]),
+    "gsp_export_runs_packed": (_i32, [_vp, _vp, _u32]),
+    "gsp_merge_gathered_packed": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),
     "gsp_writeback_visible_delta": (_i32, [_vp, _u32, _vp, _u32, _pu32]),
     "gsp_fetch_all": (_i32, [_vp]),
@@ -225,6 +229,10 @@ class ScenePrep:
 
     def export_runs(self, d_keys: int, d_payloads: int, capacity: int):
         self._check(self.lib.gsp_export_runs(self.h, d_keys, d_payloads, capacity))
+
+    def export_runs_packed(self, d_block: int, capacity: int):
+        """Enqueues the packed export of the frame that has just been enqueued (no host synchronisation)."""
+        self._check(self.lib.gsp_export_runs_packed(self.h, d_block, capacity))
 
     def writeback_visible(self, pool: int, aos, stride: int):
         self._check(self.lib.gsp_writeback_visible(self.h, pool, _ptr(aos), stride))

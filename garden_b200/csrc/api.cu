@@ -258,7 +258,7 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 		t.capacity = cap;
 	}
 	t.occupancy = occupancy;
-	c.linkDirty = true; c.resultsValid = false;
+	c.linkDirty = true; c.resultsValid = false; c.frameEnqueued = false;
 	if (occupancy == 0)
 		return GSP_OK;
 	const void* src = nullptr;
@@ -302,7 +302,7 @@ int gsp_update_transforms(gsp_context* ctx, const void* aos, uint32_t stride, ui
 	launchStageTransforms(c, src, stride, first, count, false, nullptr);
 	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the scratch buffer and the caller's memory are free again
 	GSP_CUDA(cudaGetLastError());
-	c.resultsValid = false;
+	c.resultsValid = false; c.frameEnqueued = false;
 	return GSP_OK;
 }
 
@@ -316,7 +316,7 @@ int gsp_set_pool_count(gsp_context* ctx, uint32_t poolCount)
 	for (uint32_t i = poolCount; i < (uint32_t)kMaxPools; i++)
 		c.pools[i].set = false;
 	c.poolCount = poolCount;
-	c.layoutDirty = true; c.resultsValid = false;
+	c.layoutDirty = true; c.resultsValid = false; c.frameEnqueued = false;
 	return GSP_OK;
 }
 
@@ -360,7 +360,7 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 	p.occupancy = occupancy; p.count = count; p.stride = stride; p.renderType = renderType; p.drawReady = drawReady;
 	p.hasReady = readyCounts != nullptr; p.set = true; p.visibleValid = false;
 	if (pool >= c.poolCount) { c.poolCount = pool + 1; c.layoutDirty = true; }
-	c.linkDirty = true; c.resultsValid = false;
+	c.linkDirty = true; c.resultsValid = false; c.frameEnqueued = false;
 	if (occupancy == 0)
 		return GSP_OK;
 	const void* src = nullptr;
@@ -392,7 +392,7 @@ int gsp_set_views(gsp_context* ctx, uint32_t viewCount, const gsp_view* views, c
 			(c.views[v].uiPlaneCount == 0) != (views[v].uiPlaneCount == 0);
 	c.views.assign(views, views + viewCount);
 	memcpy(c.cameraPos, cameraPosition, sizeof(c.cameraPos));
-	c.viewsSet = true; c.resultsValid = false;
+	c.viewsSet = true; c.resultsValid = false; c.frameEnqueued = false;
 	if (shapeChanged)
 		c.layoutDirty = true;
 	return GSP_OK;
@@ -595,6 +595,7 @@ int gsp_run_async(gsp_context* ctx)
 	c.launchCount = launches;
 	std::fill(c.segDownloaded.begin(), c.segDownloaded.end(), 0);
 	c.resultsValid = false;
+	c.frameEnqueued = true;
 	return GSP_OK;
 }
 
@@ -899,6 +900,21 @@ int gsp_export_runs(gsp_context* ctx, uint32_t* dKeys, uint32_t* dPayloads, uint
 		}
 		offset += n;
 	}
+	return GSP_OK;
+}
+
+int gsp_export_runs_packed(gsp_context* ctx, uint32_t* dBlock, uint32_t capacityElems)
+{
+	if (!ctx || !dBlock)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (!c.frameEnqueued || c.layoutDirty)
+		return fail(c, GSP_ERR_STATE, "gsp_export_runs_packed: no frame has been enqueued (gsp_run_async) since the last change");
+	if (c.segments.empty() || c.segments.size() > kExMaxLists)
+		return fail(c, GSP_ERR_INVALID, "gsp_export_runs_packed: the frame has no lists (or more than the block header holds)");
+	GSP_CUDA(cudaSetDevice(c.device));
+	launchExportPacked(c, dBlock, capacityElems);
+	GSP_CUDA(cudaGetLastError());
 	return GSP_OK;
 }
 

@@ -90,32 +90,52 @@ __global__ void kMergeBounds(const __grid_constant__ MergeArgs A)
 	}
 }
 
-// grid (blocks, ranks, lists): each thread places elements of one run's sub-range into my slice.
+// grid (blocks, ranks, lists): a block takes chunks of kMergeChunk consecutive elements of one run's sub-range and places
+// them into my slice. Positions inside the other runs are monotone along the chunk, so the block first brackets the
+// chunk in every other run (two full binary searches per run, one thread each) and every element then searches only
+// its bracket — a window about as long as the chunk that stays in L1 — instead of the whole run.
+constexpr uint32_t kMergeChunk = 1024;
 __global__ void __launch_bounds__(256) kMergeSlice(const __grid_constant__ MergeArgs A)
 {
+	__shared__ uint32_t sLo[32], sHi[32];
 	const uint32_t list = blockIdx.z, run = blockIdx.y;
 	const uint32_t lo = A.bounds[(list * A.ranks + run) * 2 + 0], hi = A.bounds[(list * A.ranks + run) * 2 + 1];
 	const uint32_t sliceStart = A.sliceInfo[list * 2 + 0];
 	const uint32_t* myKeys = A.keys + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
 	const uint32_t* myPays = A.payloads + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
 	const uint32_t outBase = A.outOffsets[list];
-	for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x)
+	for (uint32_t i0 = lo + blockIdx.x * kMergeChunk; i0 < hi; i0 += gridDim.x * kMergeChunk)
 	{
-		const uint32_t key = myKeys[i];
-		uint32_t pos = i;
-		for (uint32_t r = 0; r < A.ranks; r++)
+		const uint32_t i1 = min(i0 + kMergeChunk, hi);
+		__syncthreads();
+		if (threadIdx.x < A.ranks && threadIdx.x != run)
 		{
-			if (r == run)
-				continue;
+			const uint32_t r = threadIdx.x;
 			const uint32_t n = A.counts[r * A.lists + list];
 			const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
+			const uint32_t firstKey = myKeys[i0], lastKey = myKeys[i1 - 1];
 			// lower ranks win ties (they hold lower global entity indices)
-			pos += r < run ? upperBound(a, n, key) : lowerBound(a, n, key);
+			sLo[r] = r < run ? upperBound(a, n, firstKey) : lowerBound(a, n, firstKey);
+			sHi[r] = r < run ? upperBound(a, n, lastKey) : lowerBound(a, n, lastKey);
 		}
-		const uint32_t o = outBase + (pos - sliceStart);
-		A.outKeys[o] = key;
-		A.outPayloads[o] = myPays[i];
-		A.outRanks[o] = (uint8_t)run;
+		__syncthreads();
+		for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+		{
+			const uint32_t key = myKeys[i];
+			uint32_t pos = i;
+			for (uint32_t r = 0; r < A.ranks; r++)
+			{
+				if (r == run)
+					continue;
+				const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list] + sLo[r];
+				const uint32_t n = sHi[r] - sLo[r];
+				pos += sLo[r] + (r < run ? upperBound(a, n, key) : lowerBound(a, n, key));
+			}
+			const uint32_t o = outBase + (pos - sliceStart);
+			A.outKeys[o] = key;
+			A.outPayloads[o] = myPays[i];
+			A.outRanks[o] = (uint8_t)run;
+		}
 	}
 }
 
@@ -124,9 +144,145 @@ uint32_t launchMerge(cudaStream_t stream, const MergeArgs& A, uint32_t maxRunLen
 	if (A.lists == 0 || A.ranks == 0)
 		return 0;
 	kMergeBounds<<<A.lists, 32, 0, stream>>>(A);
-	const uint32_t blocks = std::max(1u, std::min((maxRunLength / A.ranks + 255u) / 256u + 1u, 148u * 4u / std::max(1u, A.ranks)));
+	const uint32_t blocks = std::max(1u, std::min((maxRunLength / A.ranks + kMergeChunk - 1u) / kMergeChunk + 1u, 148u * 8u / std::max(1u, A.ranks)));
 	kMergeSlice<<<dim3(blocks, A.ranks, A.lists), 256, 0, stream>>>(A);
 	return 2;
+}
+
+
+// ---- host-synchronisation-free exchange ---------------------------------------------------------------------------------
+// The per-list lengths only exist on the device when the frame has just been enqueued, so the whole exchange is laid out
+// around a fixed-capacity BLOCK per rank that carries its own description:
+//   words [0, kExHeaderWords): header = { kExMagic, lists, total, capacity, overflow, 0, 0, 0, count[0 .. lists) }
+//   words [H, H + capacity): keys of all lists back to back;   words [H + capacity, H + 2 * capacity): payloads
+// One all-gather of equal-sized blocks moves everything; kMergePlan then derives offsets / totals from the gathered
+// headers on the device. A block whose lists do not fit its capacity is flagged (and carries no elements): the host finds
+// out from the plan flags one frame later, grows the capacity and repeats that frame.
+struct ExportArgs
+{
+	const SegmentDev* __restrict__ segments;
+	const uint32_t* __restrict__ counters;
+	const uint32_t* __restrict__ keys;
+	const uint32_t* __restrict__ payloads;
+	uint32_t* __restrict__ block;
+	uint32_t lists, capacity;
+};
+
+__global__ void __launch_bounds__(256) kExportPacked(const __grid_constant__ ExportArgs A)
+{
+	__shared__ uint32_t sCount[kExMaxLists], sStart[kExMaxLists];
+	__shared__ uint32_t sTotal;
+	if (threadIdx.x == 0)
+	{
+		uint32_t running = 0;
+		for (uint32_t l = 0; l < A.lists; l++)
+		{
+			const SegmentDev sg = A.segments[l];
+			const uint32_t c = sg.countIndex == kNone ? 0u : A.counters[sg.countIndex];
+			sCount[l] = c; sStart[l] = running;
+			running += c;
+		}
+		sTotal = running;
+	}
+	__syncthreads();
+	const bool overflow = sTotal > A.capacity;
+	if (blockIdx.x == 0)
+	{
+		for (uint32_t i = threadIdx.x; i < kExHeaderWords; i += blockDim.x)
+		{
+			uint32_t w = 0;
+			if (i == 0) w = kExMagic;
+			else if (i == 1) w = A.lists;
+			else if (i == 2) w = sTotal;
+			else if (i == 3) w = A.capacity;
+			else if (i == 4) w = overflow ? 1u : 0u;
+			else if (i >= kExHeaderFixed && i < kExHeaderFixed + A.lists) w = overflow ? 0u : sCount[i - kExHeaderFixed];
+			A.block[i] = w;
+		}
+	}
+	if (overflow)
+		return;
+	uint32_t* dk = A.block + kExHeaderWords;
+	uint32_t* dp = dk + A.capacity;
+	for (uint32_t l = 0; l < A.lists; l++)
+	{
+		const uint32_t n = sCount[l], from = A.segments[l].offset, to = sStart[l];
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		{
+			dk[to + i] = A.keys[from + i];
+			dp[to + i] = A.payloads[from + i];
+		}
+	}
+}
+
+uint32_t launchExportPacked(Context& c, uint32_t* dBlock, uint32_t capacity)
+{
+	ExportArgs A;
+	A.segments = c.dSegments; A.counters = c.dCounters; A.keys = c.keys[0]; A.payloads = c.payloads[0];
+	A.block = dBlock; A.lists = (uint32_t)c.segments.size(); A.capacity = capacity;
+	kExportPacked<<<148 * 4, 256, 0, c.stream>>>(A);
+	return 1;
+}
+
+// One block: offsets / counts / output offsets of the merge from the gathered headers; flags for the host.
+// plan layout (uint32 words): offsets[ranks*lists] | counts[ranks*lists] | outOffsets[lists] | bounds[lists*ranks*2] | flags[8]
+//   flags = { error bits (1 = a rank overflowed its block, 2 = bad header, 4 = merged lists exceed outCapacity),
+//             merged total, largest per-rank total (what the block capacity must hold), 0... }
+__global__ void kMergePlan(const uint32_t* __restrict__ gathered, uint32_t blockWords, uint32_t ranks, uint32_t lists,
+	uint32_t outCapacity, uint32_t* __restrict__ plan)
+{
+	uint32_t* offsets = plan;
+	uint32_t* counts = plan + ranks * lists;
+	uint32_t* outOffsets = counts + ranks * lists;
+	uint32_t* flags = outOffsets + lists + lists * ranks * 2;
+	__shared__ uint32_t sError, sMaxTotal;
+	if (threadIdx.x == 0) { sError = 0; sMaxTotal = 0; }
+	__syncthreads();
+	if (threadIdx.x < ranks)
+	{
+		const uint32_t* h = gathered + (size_t)threadIdx.x * blockWords;
+		uint32_t e = 0;
+		if (h[0] != kExMagic || h[1] != lists) e |= 2u;
+		if (h[4]) e |= 1u;
+		if (e) atomicOr(&sError, e);
+		atomicMax(&sMaxTotal, h[2]);
+	}
+	__syncthreads();
+	const bool bad = sError != 0;
+	if (threadIdx.x < ranks)
+	{
+		const uint32_t r = threadIdx.x;
+		const uint32_t* h = gathered + (size_t)r * blockWords + kExHeaderFixed;
+		uint32_t running = 0;
+		for (uint32_t l = 0; l < lists; l++)
+		{
+			const uint32_t c = bad ? 0u : h[l];
+			offsets[r * lists + l] = running;
+			counts[r * lists + l] = c;
+			running += c;
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint64_t running = 0;
+		for (uint32_t l = 0; l < lists; l++)
+		{
+			outOffsets[l] = (uint32_t)running;
+			for (uint32_t r = 0; r < ranks; r++)
+				running += counts[r * lists + l];
+		}
+		uint32_t e = sError;
+		if (running > outCapacity)
+		{
+			// nothing may be written: drop every run (kMergeBounds / kMergeSlice then see empty lists)
+			e |= 4u;
+			for (uint32_t i = 0; i < ranks * lists; i++)
+				counts[i] = 0;
+		}
+		flags[0] = e; flags[1] = (uint32_t)running; flags[2] = sMaxTotal;
+		flags[3] = 0; flags[4] = 0; flags[5] = 0; flags[6] = 0; flags[7] = 0;
+	}
 }
 
 } // namespace gsp
@@ -146,5 +302,35 @@ extern "C" int gsp_merge_gathered(void* cudaStream, uint32_t ranks, uint32_t myR
 	A.sliceInfo = dSliceInfo; A.outKeys = dOutKeys; A.outPayloads = dOutPayloads; A.outRanks = dOutRanks;
 	A.outOffsets = dOutOffsets; A.rankStride = rankStride; A.ranks = ranks; A.lists = lists; A.myRank = myRank;
 	launchMerge((cudaStream_t)cudaStream, A, maxRunLength);
+	return cudaGetLastError() == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
+}
+
+extern "C" uint32_t gsp_exchange_block_words(uint32_t capacityElems)
+{
+	return kExHeaderWords + 2u * capacityElems;
+}
+
+extern "C" uint32_t gsp_merge_plan_words(uint32_t ranks, uint32_t lists)
+{
+	return 2u * ranks * lists + lists + 2u * lists * ranks + 8u;
+}
+
+extern "C" int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
+	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
+	uint8_t* dOutRanks, uint32_t outCapacity)
+{
+	if (ranks == 0 || ranks > 32 || myRank >= ranks || lists == 0 || lists > kExMaxLists || !dGathered || !dPlan || !dSliceInfo ||
+		!dOutKeys || !dOutPayloads || !dOutRanks)
+		return GSP_ERR_INVALID;
+	cudaStream_t stream = (cudaStream_t)cudaStream;
+	const uint32_t blockWords = kExHeaderWords + 2u * capacityElems;
+	kMergePlan<<<1, 32, 0, stream>>>(dGathered, blockWords, ranks, lists, outCapacity, dPlan);
+	MergeArgs A;
+	A.keys = dGathered + kExHeaderWords; A.payloads = dGathered + kExHeaderWords + capacityElems;
+	A.offsets = dPlan; A.counts = dPlan + ranks * lists;
+	A.outOffsets = dPlan + 2 * ranks * lists; A.bounds = dPlan + 2 * ranks * lists + lists;
+	A.sliceInfo = dSliceInfo; A.outKeys = dOutKeys; A.outPayloads = dOutPayloads; A.outRanks = dOutRanks;
+	A.rankStride = blockWords; A.ranks = ranks; A.lists = lists; A.myRank = myRank;
+	launchMerge(stream, A, capacityElems);
 	return cudaGetLastError() == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
 }

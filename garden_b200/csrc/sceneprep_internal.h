@@ -130,6 +130,7 @@ struct Context
 	std::vector<gsp_view> views;
 	float cameraPos[3] = {0, 0, 0};
 	bool viewsSet = false, linkDirty = true, layoutDirty = true, resultsValid = false;
+	bool frameEnqueued = false; // a frame has been enqueued since the last structural change (its results may still be in flight)
 
 	// segments
 	std::vector<Segment> segments;
@@ -183,6 +184,10 @@ constexpr uint32_t kSortItems = 16;       // keys per thread in the radix sort
 constexpr uint32_t kSortThreads = 256;
 constexpr uint32_t kSortTile = kSortItems * kSortThreads;
 
+// ---- packed exchange block of the multi-GPU path (merge.cu) ----
+constexpr uint32_t kExHeaderWords = 256, kExHeaderFixed = 8, kExMaxLists = kExHeaderWords - kExHeaderFixed;
+constexpr uint32_t kExMagic = 0x47535031u; // "GSP1"
+
 // ---- kernel launchers (each returns the number of kernels it launched, or throws nothing; errors via cudaGetLastError) ----
 uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full,
 	uint32_t* dMaxEntity);
@@ -192,6 +197,7 @@ uint32_t launchLink(Context& c);
 uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter);
 uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);
+uint32_t launchExportPacked(Context& c, uint32_t* dBlock, uint32_t capacity);
 uint32_t launchPackVisible(Context& c, uint32_t pool, uint32_t* dBits);
 uint32_t launchVisibleDelta(Context& c, uint32_t pool, uint32_t* list, uint32_t* dCount, uint32_t* hCountMapped);
 

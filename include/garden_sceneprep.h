@@ -159,6 +159,21 @@ int gsp_merge_gathered(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32
 	uint32_t* dBounds, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads, uint8_t* dOutRanks,
 	const uint32_t* dOutOffsets);
 
+/* Host-synchronisation-free variant of the same exchange. A frame only has to be ENQUEUED (gsp_run_async): list lengths are
+ * read on the device. Every rank fills one fixed-capacity block
+ *   [0, 256) header { magic, lists, total, capacity, overflow, 0, 0, 0, count[lists] } | keys[capacity] | payloads[capacity]
+ * (gsp_exchange_block_words(capacity) 32-bit words), ONE all-gather of equal blocks moves everything, and the merge plans
+ * itself from the gathered headers. dPlan = gsp_merge_plan_words(ranks, lists) words of device scratch; its last 8 words
+ * are flags the caller reads back whenever convenient: { error bits (1 a block overflowed its capacity, 2 bad header,
+ * 4 merged lists exceed outCapacity), merged total, largest per-rank total, 0... }. With a non-zero error word nothing was
+ * merged: grow the capacity to hold flags[2] (or outCapacity to hold flags[1]) and repeat the frame. */
+uint32_t gsp_exchange_block_words(uint32_t capacityElems);
+uint32_t gsp_merge_plan_words(uint32_t ranks, uint32_t lists);
+int gsp_export_runs_packed(gsp_context* ctx, uint32_t* dBlock, uint32_t capacityElems);
+int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
+	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
+	uint8_t* dOutRanks, uint32_t outCapacity);
+
 /* Stores MeshRenderComponent::isVisible (offset 15) for every slot of `pool` exactly as the reference's main-view pass
  * does (mesh.cpp:144-146,152-153,161-167). No-op for pools the main view did not process. */
 int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride);

@@ -101,3 +101,112 @@ def test_emulated_ranks_merge_equals_single_sort(sceneprep_lib, ranks):
     global_p = (merged_p & 0xF0000000) | ((merged_p & 0x0FFFFFFF) + np.array(starts, np.uint32)[merged_r])
     assert np.array_equal(merged_k, full_k)
     assert np.array_equal(global_p, full_p)
+
+
+def _shards(whole, ranks, chains, depth):
+    n = whole.entity_count
+    per = (chains // ranks) * (depth + 1)
+    starts = [r * per for r in range(ranks)] + [n]
+    out = []
+    for r in range(ranks):
+        a, b = starts[r], starts[r + 1]
+        out.append(scenes.SceneDesc(whole.position[a:b], whole.rotation[a:b], whole.scale[a:b],
+                                    np.where(whole.parent[a:b] >= 0, whole.parent[a:b] - a, -1).astype(np.int32), whole.tflags[a:b],
+                                    [scenes.PoolDesc(whole.pools[0].render_type, np.arange(b - a, dtype=np.uint32), whole.pools[0].aabb[a:b])],
+                                    None, whole.camera_pos))
+    return out, starts
+
+
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks):
+    """The host-synchronisation-free exchange (gsp_export_runs_packed -> [all-gather] -> gsp_merge_gathered_packed):
+    blocks are exported right after gsp_run_async (no gsp_sync), laid out as the all-gather would, merged per rank, and
+    checked against the numpy merge and against a single sort of the whole scene. Then the overflow protocol."""
+    import torch
+    from garden_b200.binding import ScenePrep
+    chains, depth = 3000, 4
+    n = chains * (depth + 1)
+    whole = scenes.make_scene(n, depth, 11, (-150, -10, -150, 150, 10, 150))
+    whole.camera_pos = np.array([2.0, 1.0, -3.0], np.float32)
+    views, _ = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    sp = ScenePrep(0)
+    _prepare(sp, whole, views)
+    full_counts, full_k, full_p = _runs_to_host(sp, torch)
+    lists = full_counts.size
+    lib = sp.lib
+    cap = int(full_counts.sum())  # plenty for every shard
+    words = lib.gsp_exchange_block_words(cap)
+    gathered = torch.zeros(words * ranks, dtype=torch.int32, device="cuda")
+    shards, starts = _shards(whole, ranks, chains, depth)
+    shard_runs = []
+    for r, sc in enumerate(shards):
+        t, pools = scenes.build_aos(sc)
+        sp.set_transforms(t, t.dtype.itemsize, t.size)
+        sp.set_pool_count(len(pools))
+        for k, m in enumerate(pools):
+            sp.set_mesh_pool(k, sc.pools[k].render_type, m, m.dtype.itemsize, m.size)
+        sp.set_views(views, sc.camera_pos)
+        sp.run_async()  # no sync: the export reads the list lengths on the device
+        sp.export_runs_packed(gathered[r * words:].data_ptr(), cap)
+        sp.sync()
+        shard_runs.append(_runs_to_host(sp, torch))
+    torch.cuda.synchronize()
+    hdr = gathered.cpu().numpy().view(np.uint32).reshape(ranks, words)[:, :8 + lists]
+    all_counts = np.stack([c for c, _, _ in shard_runs])
+    assert np.array_equal(hdr[:, 8:8 + lists].astype(np.int64), all_counts)
+    assert np.all(hdr[:, 0] == 0x47535031) and np.all(hdr[:, 1] == lists) and np.all(hdr[:, 4] == 0)
+    offsets, _, out_offsets, totals = plan_gather(all_counts)
+    total = int(totals.sum())
+    plan = torch.zeros(lib.gsp_merge_plan_words(ranks, lists), dtype=torch.int32, device="cuda")
+    merged_k = np.zeros(total, np.uint32); merged_p = np.zeros(total, np.uint32); merged_r = np.zeros(total, np.uint8)
+    covered = np.zeros(total, bool)
+    for me in range(ranks):
+        out_k = torch.zeros(total, dtype=torch.int32, device="cuda"); out_p = torch.zeros_like(out_k)
+        out_r = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        sinfo = torch.zeros(lists * 2, dtype=torch.int32, device="cuda")
+        rc = lib.gsp_merge_gathered_packed(0, ranks, me, lists, cap, gathered.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
+                                           out_k.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total)
+        assert rc == 0
+        torch.cuda.synchronize()
+        pl = plan.cpu().numpy().view(np.uint32)
+        assert pl[-8] == 0 and pl[-7] == total and pl[-6] == all_counts.sum(axis=1).max()
+        assert np.array_equal(pl[2 * ranks * lists: 2 * ranks * lists + lists], out_offsets)
+        info = sinfo.cpu().numpy().reshape(lists, 2)
+        ok, op, orr = out_k.cpu().numpy().view(np.uint32), out_p.cpu().numpy().view(np.uint32), out_r.cpu().numpy()
+        for l in range(lists):
+            start, length = int(info[l, 0]), int(info[l, 1])
+            runs_k = [shard_runs[r][1][offsets[r, l]: offsets[r, l] + all_counts[r, l]] for r in range(ranks)]
+            runs_p = [shard_runs[r][2][offsets[r, l]: offsets[r, l] + all_counts[r, l]] for r in range(ranks)]
+            ek, ep, er, estart = merge_reference(runs_k, runs_p, my_rank=me)
+            assert (start, length) == (estart, ek.size), f"rank {me} list {l}: slice bounds"
+            o = int(out_offsets[l])
+            assert np.array_equal(ok[o:o + length], ek) and np.array_equal(op[o:o + length], ep) and np.array_equal(orr[o:o + length], er)
+            g = slice(o + start, o + start + length)
+            assert not covered[g].any()
+            covered[g] = True
+            merged_k[g], merged_p[g], merged_r[g] = ek, ep, er
+    assert covered.all()
+    global_p = (merged_p & 0xF0000000) | ((merged_p & 0x0FFFFFFF) + np.array(starts, np.uint32)[merged_r])
+    assert np.array_equal(merged_k, full_k) and np.array_equal(global_p, full_p)
+
+    # overflow protocol: a block that cannot hold the rank's lists is flagged, carries nothing, and the merge reports it
+    small = max(int(all_counts.sum(axis=1).max()) // 2, 1)
+    words_s = lib.gsp_exchange_block_words(small)
+    g2 = torch.zeros(words_s * ranks, dtype=torch.int32, device="cuda")
+    sp.run_async()
+    for r in range(ranks):
+        sp.export_runs_packed(g2[r * words_s:].data_ptr(), small)  # (the last shard, into every block)
+    sentinel = torch.full((total,), 0x5a5a5a5a, dtype=torch.int32, device="cuda")
+    out_p = sentinel.clone(); out_r = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    sinfo = torch.zeros(lists * 2, dtype=torch.int32, device="cuda")
+    rc = lib.gsp_merge_gathered_packed(0, ranks, 0, lists, small, g2.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
+                                       sentinel.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total)
+    assert rc == 0
+    sp.sync()
+    torch.cuda.synchronize()
+    pl = plan.cpu().numpy().view(np.uint32)
+    assert pl[-8] & 1, "overflow must be reported"
+    assert pl[-6] == int(shard_runs[-1][0].sum()), "the needed capacity is reported"
+    assert bool((sentinel == 0x5a5a5a5a).all()), "nothing may be merged from an overflowed exchange"
+    assert int(sinfo.cpu().numpy().reshape(lists, 2)[:, 1].sum()) == 0
+    sp.close()

@@ -87,6 +87,29 @@ def main():
         assert (start, gk.size) == (estart, ek.size), f"rank {rank} list {l}: slice bounds {start},{gk.size} vs {estart},{ek.size}"
         assert np.array_equal(gk, ek) and np.array_equal(gp, ep) and np.array_equal(gr, er), f"rank {rank} list {l}: content"
         checked += int(gk.size)
+    # ---- the pipelined, host-synchronisation-free exchange: same slices, three frames in flight, then the overflow path ----
+    from garden_b200.dist import PipelinedRunMerger
+    pm = PipelinedRunMerger(sp)
+    for _ in range(3):
+        pm.frame()
+        assert pm.poll() == []
+    pm.finish()
+    res2 = pm.last_result()
+    assert np.array_equal(res2["counts"], all_counts) and int(res2["flags"][0]) == 0
+    for l in range(lists):
+        a0, b0 = slices[l], res2["slices"][l]
+        assert a0[0] == b0[0] and np.array_equal(a0[1], b0[1]) and np.array_equal(a0[2], b0[2]) and np.array_equal(a0[3], b0[3]), \
+            f"rank {rank} list {l}: pipelined exchange differs from the synchronous one"
+    tiny = PipelinedRunMerger(sp, capacity=max(int(all_counts.sum(axis=1).max()) // 3, 1))
+    tiny.frame()
+    failed = tiny.finish(check=False)
+    assert failed and failed[0][1] & 1 and failed[0][2] == int(all_counts.sum(axis=1).max()), failed
+    tiny.grow(failed[0][2])
+    tiny.frame()
+    assert tiny.finish(check=False) == []
+    res3 = tiny.last_result()
+    for l in range(lists):
+        assert np.array_equal(slices[l][1], res3["slices"][l][1]) and np.array_equal(slices[l][2], res3["slices"][l][2])
     spans = [None] * world
     dist.all_gather_object(spans, [(s[0], int(s[1].size)) for s in slices])
     if rank == 0:
@@ -98,7 +121,8 @@ def main():
             assert pos == int(totals[l]), f"list {l}: slices cover {pos} of {int(totals[l])}"
         print(json.dumps({"dist_parity": "ok", "world": world, "entities": n, "lists": int(lists),
                           "merged_total": int(totals.sum()), "rank0_checked": checked,
-                          "bytes_gathered": res["bytes_gathered"]}), flush=True)
+                          "bytes_gathered": res["bytes_gathered"],
+                          "pipelined": "ok (3 frames in flight, overflow -> grow -> repeat)"}), flush=True)
     sp.close()
     dist.barrier()
     dist.destroy_process_group()
