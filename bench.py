@@ -23,6 +23,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+_JSON_OUT = sys.stdout
 
 from garden_b200 import scenes, views as V  # noqa: E402
 
@@ -195,7 +196,7 @@ def run_reference_arm(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -315,6 +316,48 @@ def run_b200_arm(args):
         phase += sp.phase_times()
     phase /= prof_steps
     sp.set_profiling(False)
+
+    # ---- SURVEY.md 8f rows, timed alone with CUDA events on the same stream (not part of the headline frame) ----
+    next_rows = []
+    if world == 1:
+        peak_gbs, _ = load_peaks()
+        # f1: instance data (mvp) of the main view's first buffer, straight into device memory
+        vi = int(views.size) - 1  # the main camera is the last view of the frame (cascades first)
+        _, main_draw, _ = sp.get_unsorted_device(vi, 0)
+        if main_draw:
+            inst = torch.empty(main_draw * 16, dtype=torch.float32, device="cuda")
+            vp0 = np.asarray(V.camera_and_cascades(0.6, -0.12, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))[1][vi]
+                             if args.workload != "C3" else V.perspective_views([(0.6, -0.05)], 1.2, 16 / 9, 0.01)[1][vi],
+                             dtype=np.float32).reshape(16)
+            sp.run_async()
+            for _ in range(3):
+                sp.emit_instances_device(vi, 0, 0, vp0, inst.data_ptr(), main_draw)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            a.record(stream)
+            for _ in range(reps):
+                sp.emit_instances_device(vi, 0, 0, vp0, inst.data_ptr(), main_draw)
+            b.record(stream)
+            sp.sync()
+            ms = a.elapsed_time(b) / reps
+            nbytes = main_draw * (48 + 64)  # bakedModel read + mvp write per instance
+            next_rows.append({"row": "f1 instance mvp (kInstances)", "instances": int(main_draw), "ms": round(ms, 4),
+                              "bytes": int(nbytes), "GBps": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                              "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak_gbs, 3),
+                              "note": "main-camera list; the record arena was just written, so part of the reads are L2 hits"})
+            del inst
+        # f3: setActive of 10k entities (deactivate, then reactivate: the scene is unchanged afterwards)
+        ids = np.arange(1, min(n, 10_000 * 9) + 1, 9, dtype=np.uint32)  # chain roots of the generator's depth-8 chains
+        t0 = time.perf_counter()
+        sp.set_active(ids, False)
+        t1 = time.perf_counter()
+        sp.set_active(ids, True)
+        t2 = time.perf_counter()
+        nbytes = n * (2 + 2 + 4)  # flags read + written, parent link, per transform (ancestor re-reads hit L2)
+        ms = min(t1 - t0, t2 - t1) * 1e3
+        next_rows.append({"row": "f3 setActive (kSetSelfActive + kPropagateActive), host-timed incl. id upload + sync",
+                          "entities_toggled": int(ids.size), "transforms": int(n), "ms": round(ms, 4), "bytes": int(nbytes),
+                          "GBps": round(nbytes / (ms * 1e-3) / 1e9, 1), "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak_gbs, 3)})
 
     # ---- end to end through the C ABI with host buffers ----
     # every step: the whole AoS pools + views go host -> device (the ECS has no dirty tracking; pinned memory is read in
@@ -439,6 +482,8 @@ def run_b200_arm(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }
+        if next_rows:
+            line["next_rows"] = next_rows
         if world > 1:
             line["exchange"] = {"frame_latency_ms_serialised": latency_ms, "allgather_bytes_per_rank": exchange_bytes,
                                 "collectives_per_frame": 1, "host_syncs_per_frame": 0, "parts_rank0": exchange_parts}
@@ -446,7 +491,7 @@ def run_b200_arm(args):
             res = reference_engine_run(args.workload, args.ref_sample, args.ref_steps, 1, args.seed)
             line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                                     "sample": res["sample"], "ms_per_step": res["ms_per_step"]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     sp.close()
     if world > 1:
         dist.barrier()
@@ -454,6 +499,11 @@ def run_b200_arm(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner) is sent to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -51,6 +51,10 @@ SYMBOLS = {
     "gsp_merge_plan_words": (_u32, [_u32, _u32]),
     "gsp_export_runs_packed": (_i32, [_vp, _vp, _u32]),
     "gsp_merge_gathered_packed": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "gsp_emit_instances": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _u32, _u32, _u32]),
+    "gsp_emit_instances_device": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _u32, _u32, _u32]),
+    "gsp_set_active": (_i32, [_vp, _vp, _u32, _i32]),
+    "gsp_writeback_active": (_i32, [_vp, _vp, _u32]),
     "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),
     "gsp_writeback_visible_delta": (_i32, [_vp, _u32, _vp, _u32, _pu32]),
     "gsp_fetch_all": (_i32, [_vp]),
@@ -233,6 +237,26 @@ class ScenePrep:
     def export_runs_packed(self, d_block: int, capacity: int):
         """Enqueues the packed export of the frame that has just been enqueued (no host synchronisation)."""
         self._check(self.lib.gsp_export_runs_packed(self.h, d_block, capacity))
+
+    def emit_instances(self, view: int, kind: int, buffer: int, view_proj, count: int, stride: int = 64, mvp_offset: int = 0):
+        """Host instance buffer of one draw list: returns [count, stride] bytes with mvp at mvp_offset of every instance."""
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        out = np.zeros((max(count, 1), stride), dtype=np.uint8)
+        self._check(self.lib.gsp_emit_instances(self.h, view, kind, buffer, vp.ctypes.data, out.ctypes.data, stride, mvp_offset, count))
+        return out[:count]
+
+    def emit_instances_device(self, view: int, kind: int, buffer: int, view_proj, d_instances: int, capacity: int,
+                              stride: int = 64, mvp_offset: int = 0):
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        self._check(self.lib.gsp_emit_instances_device(self.h, view, kind, buffer, vp.ctypes.data, d_instances, stride,
+                                                       mvp_offset, capacity))
+
+    def set_active(self, entity_ids, active: bool):
+        ids = np.ascontiguousarray(entity_ids, dtype=np.uint32)
+        self._check(self.lib.gsp_set_active(self.h, ids.ctypes.data, ids.size, 1 if active else 0))
+
+    def writeback_active(self, aos, stride: int):
+        self._check(self.lib.gsp_writeback_active(self.h, _ptr(aos), stride))
 
     def writeback_visible(self, pool: int, aos, stride: int):
         self._check(self.lib.gsp_writeback_visible(self.h, pool, _ptr(aos), stride))

@@ -903,6 +903,112 @@ int gsp_export_runs(gsp_context* ctx, uint32_t* dKeys, uint32_t* dPayloads, uint
 	return GSP_OK;
 }
 
+// ---- SURVEY.md §8f rows -------------------------------------------------------------------------------------------------
+static int emitInstances(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer, const float* viewProj, void* dst,
+	uint32_t stride, uint32_t mvpOffset, uint32_t capacity, bool deviceDst)
+{
+	if (!ctx || !viewProj || listKind < 0 || listKind > 2)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if ((!dst && capacity) || stride < 64 || (stride & 15) || (mvpOffset & 15) || (uint64_t)mvpOffset + 64 > stride)
+		return fail(c, GSP_ERR_INVALID, "gsp_emit_instances: need stride >= 64, stride and mvpOffset multiples of 16, mvp inside the stride");
+	if (deviceDst ? (!c.frameEnqueued || c.layoutDirty) : !c.resultsValid)
+		return fail(c, GSP_ERR_STATE, "gsp_emit_instances: no frame to read (gsp_run_async for device output, completed gsp_run for host output)");
+	if (view >= c.views.size())
+		return fail(c, GSP_ERR_INVALID, "view index out of range");
+	const int seg = findSegment(c, view, listKind, buffer);
+	if (seg < 0 || capacity == 0)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	if (deviceDst)
+	{
+		launchInstances(c, seg, viewProj, dst, stride, mvpOffset, capacity);
+		GSP_CUDA(cudaGetLastError());
+		return GSP_OK;
+	}
+	const uint32_t count = std::min(capacity, segmentCount(c, c.segments[seg]));
+	if (count == 0)
+		return GSP_OK;
+	// host destination: packed 64-byte matrices on the device, then one strided copy into the caller's instance buffer
+	size_t cap = c.dAosScratchCap;
+	uint8_t* ptr = (uint8_t*)c.dAosScratch;
+	GSP_CUDA(ensureDevice(ptr, cap, (size_t)count * 64, false, c.stream));
+	c.dAosScratch = ptr; c.dAosScratchCap = cap;
+	launchInstances(c, seg, viewProj, c.dAosScratch, 64, 0, count);
+	GSP_CUDA(cudaMemcpy2DAsync((uint8_t*)dst + mvpOffset, stride, c.dAosScratch, 64, 64, count, cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	GSP_CUDA(cudaGetLastError());
+	return GSP_OK;
+}
+int gsp_emit_instances(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer, const float* viewProj, void* instances,
+	uint32_t stride, uint32_t mvpOffset, uint32_t capacity)
+{
+	return emitInstances(ctx, view, listKind, buffer, viewProj, instances, stride, mvpOffset, capacity, false);
+}
+int gsp_emit_instances_device(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer, const float* viewProj,
+	void* dInstances, uint32_t stride, uint32_t mvpOffset, uint32_t capacity)
+{
+	return emitInstances(ctx, view, listKind, buffer, viewProj, dInstances, stride, mvpOffset, capacity, true);
+}
+
+int gsp_set_active(gsp_context* ctx, const uint32_t* entityIds, uint32_t count, int active)
+{
+	if (!ctx || (!entityIds && count))
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	auto& t = c.tf;
+	if (!t.flags || !t.entityToSlot)
+		return fail(c, GSP_ERR_STATE, "gsp_set_active: gsp_set_transforms has not been called");
+	GSP_CUDA(cudaSetDevice(c.device));
+	uint32_t* dIds = nullptr;
+	if (count)
+	{
+		size_t cap = c.dAosScratchCap;
+		uint8_t* ptr = (uint8_t*)c.dAosScratch;
+		GSP_CUDA(ensureDevice(ptr, cap, (size_t)count * sizeof(uint32_t), false, c.stream));
+		c.dAosScratch = ptr; c.dAosScratchCap = cap;
+		dIds = (uint32_t*)c.dAosScratch;
+		GSP_CUDA(cudaMemcpyAsync(dIds, entityIds, (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+	}
+	GSP_CUDA(cudaMemsetAsync(c.dError, 0, sizeof(uint32_t), c.stream));
+	launchSetActive(c, dIds, count, active);
+	uint32_t* hScalars = c.hCounters + kCtrCount;
+	GSP_CUDA(cudaMemcpyAsync(&hScalars[1], c.dError, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the caller's id array is free again
+	GSP_CUDA(cudaGetLastError());
+	c.resultsValid = false; c.frameEnqueued = false;
+	if (hScalars[1] == (uint32_t)GSP_ERR_HIERARCHY)
+		return fail(c, GSP_ERR_HIERARCHY, "gsp_set_active: transform hierarchy is cyclic or deeper than 4096");
+	if (hScalars[1])
+		return fail(c, GSP_ERR_INVALID, "gsp_set_active: an entity id has no TransformComponent (the other ids were applied)");
+	return GSP_OK;
+}
+
+int gsp_writeback_active(gsp_context* ctx, void* aos, uint32_t stride)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	auto& t = c.tf;
+	if ((!aos && t.occupancy) || stride < kTfMinStride)
+		return fail(c, GSP_ERR_INVALID, "gsp_writeback_active: bad pointer or stride");
+	if (!t.flags || t.occupancy == 0)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	std::vector<uint16_t> flags(t.occupancy);
+	GSP_CUDA(cudaMemcpyAsync(flags.data(), t.flags, (size_t)t.occupancy * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	uint8_t* base = (uint8_t*)aos;
+	for (uint32_t i = 0; i < t.occupancy; i++)
+	{
+		if (!(flags[i] & kTfLive))
+			continue; // freed slots keep their default-constructed bytes
+		base[(size_t)i * stride + kTfSelfActive] = (flags[i] & kTfSelfBit) ? 1 : 0;
+		base[(size_t)i * stride + kTfAncestorsActive] = (flags[i] & kTfAncBit) ? 1 : 0;
+	}
+	return GSP_OK;
+}
+
 int gsp_export_runs_packed(gsp_context* ctx, uint32_t* dBlock, uint32_t capacityElems)
 {
 	if (!ctx || !dBlock)

@@ -91,10 +91,116 @@ __global__ void kMergeBounds(const __grid_constant__ MergeArgs A)
 }
 
 // grid (blocks, ranks, lists): a block takes chunks of kMergeChunk consecutive elements of one run's sub-range and places
-// them into my slice. Positions inside the other runs are monotone along the chunk, so the block first brackets the
-// chunk in every other run (two full binary searches per run, one thread each) and every element then searches only
-// its bracket — a window about as long as the chunk that stays in L1 — instead of the whole run.
-constexpr uint32_t kMergeChunk = 1024;
+// them into my slice. Positions inside the other runs are monotone along the run, so
+//  * the block first brackets the chunk in every other run (two full binary searches per run, one thread each);
+//  * a thread owns kMergeItems CONSECUTIVE elements: per other run it does one binary search inside the bracket for its
+//    first element and then only advances (a few steps on average; a fresh bracketed binary search when the advance is long).
+// Cost per element: O(ranks) short advances instead of O(ranks * log(run length)) dependent loads.
+constexpr uint32_t kMergeItems = 8, kMergeThreads = 128, kMergeChunk = kMergeItems * kMergeThreads;
+template<bool kUpper> // kUpper: count elements <= key (ties go to the other run), else elements < key
+__device__ __forceinline__ uint32_t boundIn(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t key)
+{
+	while (lo < hi)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		const uint32_t v = a[mid];
+		if (kUpper ? v <= key : v < key) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+template<bool kUpper>
+__device__ __forceinline__ void rankItems(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, const uint32_t (&key)[kMergeItems],
+	uint32_t count, uint32_t (&pos)[kMergeItems])
+{
+	uint32_t p = boundIn<kUpper>(a, lo, hi, key[0]);
+	pos[0] += p;
+	#pragma unroll
+	for (uint32_t e = 1; e < kMergeItems; e++)
+	{
+		if (e < count)
+		{
+			uint32_t steps = 0;
+			while (p < hi && steps < 4)
+			{
+				const uint32_t v = a[p];
+				if (!(kUpper ? v <= key[e] : v < key[e]))
+					break;
+				p++; steps++;
+			}
+			if (steps == 4)
+				p = boundIn<kUpper>(a, p, hi, key[e]);
+			pos[e] += p;
+		}
+	}
+}
+__device__ __forceinline__ uint32_t stagedIndex(uint32_t i) { return i + (i >> 5); } // conflict-free for stride-8 readers
+__global__ void __launch_bounds__(kMergeThreads) kMergeSliceWide(const __grid_constant__ MergeArgs A)
+{
+	__shared__ uint32_t sLo[32], sHi[32];
+	__shared__ uint32_t sKey[kMergeChunk + kMergeChunk / 32], sPay[kMergeChunk + kMergeChunk / 32];
+	const uint32_t list = blockIdx.z, run = blockIdx.y;
+	const uint32_t lo = A.bounds[(list * A.ranks + run) * 2 + 0], hi = A.bounds[(list * A.ranks + run) * 2 + 1];
+	const uint32_t sliceStart = A.sliceInfo[list * 2 + 0];
+	const uint32_t* myKeys = A.keys + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
+	const uint32_t* myPays = A.payloads + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
+	const uint32_t outBase = A.outOffsets[list];
+	for (uint32_t i0 = lo + blockIdx.x * kMergeChunk; i0 < hi; i0 += gridDim.x * kMergeChunk)
+	{
+		const uint32_t i1 = min(i0 + kMergeChunk, hi);
+		__syncthreads();
+		for (uint32_t j = threadIdx.x; j < i1 - i0; j += kMergeThreads) // coalesced staging of the chunk
+		{
+			sKey[stagedIndex(j)] = myKeys[i0 + j];
+			sPay[stagedIndex(j)] = myPays[i0 + j];
+		}
+		if (threadIdx.x < A.ranks && threadIdx.x != run)
+		{
+			const uint32_t r = threadIdx.x;
+			const uint32_t n = A.counts[r * A.lists + list];
+			const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
+			const uint32_t firstKey = myKeys[i0], lastKey = myKeys[i1 - 1];
+			// lower ranks win ties (they hold lower global entity indices)
+			sLo[r] = r < run ? upperBound(a, n, firstKey) : lowerBound(a, n, firstKey);
+			sHi[r] = r < run ? upperBound(a, n, lastKey) : lowerBound(a, n, lastKey);
+		}
+		__syncthreads();
+		const uint32_t local = threadIdx.x * kMergeItems, first = i0 + local;
+		if (first >= i1)
+			continue;
+		const uint32_t count = min(kMergeItems, i1 - first);
+		uint32_t key[kMergeItems], pos[kMergeItems];
+		#pragma unroll
+		for (uint32_t e = 0; e < kMergeItems; e++)
+		{
+			key[e] = e < count ? sKey[stagedIndex(local + e)] : 0xFFFFFFFFu;
+			pos[e] = first + e;
+		}
+		for (uint32_t r = 0; r < A.ranks; r++)
+		{
+			if (r == run)
+				continue;
+			const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
+			if (r < run)
+				rankItems<true>(a, sLo[r], sHi[r], key, count, pos);
+			else
+				rankItems<false>(a, sLo[r], sHi[r], key, count, pos);
+		}
+		#pragma unroll
+		for (uint32_t e = 0; e < kMergeItems; e++)
+		{
+			if (e < count)
+			{
+				const uint32_t o = outBase + (pos[e] - sliceStart);
+				A.outKeys[o] = key[e];
+				A.outPayloads[o] = sPay[stagedIndex(local + e)];
+				A.outRanks[o] = (uint8_t)run;
+			}
+		}
+	}
+}
+
+// Few ranks (2 or 3): one element per thread, consecutive threads on consecutive elements (coalesced reads, neighbouring
+// writes); each element runs a binary search inside the chunk's bracket of every other run.
 __global__ void __launch_bounds__(256) kMergeSlice(const __grid_constant__ MergeArgs A)
 {
 	__shared__ uint32_t sLo[32], sHi[32];
@@ -114,7 +220,6 @@ __global__ void __launch_bounds__(256) kMergeSlice(const __grid_constant__ Merge
 			const uint32_t n = A.counts[r * A.lists + list];
 			const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
 			const uint32_t firstKey = myKeys[i0], lastKey = myKeys[i1 - 1];
-			// lower ranks win ties (they hold lower global entity indices)
 			sLo[r] = r < run ? upperBound(a, n, firstKey) : lowerBound(a, n, firstKey);
 			sHi[r] = r < run ? upperBound(a, n, lastKey) : lowerBound(a, n, lastKey);
 		}
@@ -127,9 +232,8 @@ __global__ void __launch_bounds__(256) kMergeSlice(const __grid_constant__ Merge
 			{
 				if (r == run)
 					continue;
-				const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list] + sLo[r];
-				const uint32_t n = sHi[r] - sLo[r];
-				pos += sLo[r] + (r < run ? upperBound(a, n, key) : lowerBound(a, n, key));
+				const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
+				pos += r < run ? boundIn<true>(a, sLo[r], sHi[r], key) : boundIn<false>(a, sLo[r], sHi[r], key);
 			}
 			const uint32_t o = outBase + (pos - sliceStart);
 			A.outKeys[o] = key;
@@ -145,7 +249,10 @@ uint32_t launchMerge(cudaStream_t stream, const MergeArgs& A, uint32_t maxRunLen
 		return 0;
 	kMergeBounds<<<A.lists, 32, 0, stream>>>(A);
 	const uint32_t blocks = std::max(1u, std::min((maxRunLength / A.ranks + kMergeChunk - 1u) / kMergeChunk + 1u, 148u * 8u / std::max(1u, A.ranks)));
-	kMergeSlice<<<dim3(blocks, A.ranks, A.lists), 256, 0, stream>>>(A);
+	if (A.ranks <= 3)
+		kMergeSlice<<<dim3(blocks, A.ranks, A.lists), 256, 0, stream>>>(A);
+	else
+		kMergeSliceWide<<<dim3(blocks, A.ranks, A.lists), kMergeThreads, 0, stream>>>(A);
 	return 2;
 }
 
@@ -170,7 +277,7 @@ struct ExportArgs
 
 __global__ void __launch_bounds__(256) kExportPacked(const __grid_constant__ ExportArgs A)
 {
-	__shared__ uint32_t sCount[kExMaxLists], sStart[kExMaxLists];
+	__shared__ uint32_t sCount[kExMaxLists], sStart[kExMaxLists], sFrom[kExMaxLists];
 	__shared__ uint32_t sTotal;
 	if (threadIdx.x == 0)
 	{
@@ -179,7 +286,7 @@ __global__ void __launch_bounds__(256) kExportPacked(const __grid_constant__ Exp
 		{
 			const SegmentDev sg = A.segments[l];
 			const uint32_t c = sg.countIndex == kNone ? 0u : A.counters[sg.countIndex];
-			sCount[l] = c; sStart[l] = running;
+			sCount[l] = c; sStart[l] = running; sFrom[l] = sg.offset;
 			running += c;
 		}
 		sTotal = running;
@@ -206,11 +313,26 @@ __global__ void __launch_bounds__(256) kExportPacked(const __grid_constant__ Exp
 	uint32_t* dp = dk + A.capacity;
 	for (uint32_t l = 0; l < A.lists; l++)
 	{
-		const uint32_t n = sCount[l], from = A.segments[l].offset, to = sStart[l];
-		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		const uint32_t n = sCount[l], from = sFrom[l], to = sStart[l];
+		// 4 independent elements in flight per thread and array
+		const uint32_t stride = gridDim.x * blockDim.x;
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride)
 		{
-			dk[to + i] = A.keys[from + i];
-			dp[to + i] = A.payloads[from + i];
+			uint32_t k[4], q[4];
+			#pragma unroll
+			for (uint32_t u = 0; u < 4; u++)
+				if (i + u * stride < n)
+				{
+					k[u] = A.keys[from + i + u * stride];
+					q[u] = A.payloads[from + i + u * stride];
+				}
+			#pragma unroll
+			for (uint32_t u = 0; u < 4; u++)
+				if (i + u * stride < n)
+				{
+					dk[to + i + u * stride] = k[u];
+					dp[to + i + u * stride] = q[u];
+				}
 		}
 	}
 }

@@ -27,6 +27,8 @@ constexpr uint16_t kTfLive = 1, kTfActive = 2, kTfAncestors = 4;
 // the local matrix of this transform needs the guarded 4-lane code (zero / subnormal entries, out-of-range or non-finite
 // TRS): decided once at staging time by localModel43Fast<true>, so the per-frame kernel carries no guards
 constexpr uint16_t kTfExactLocal = 8;
+// the component's own selfActive / ancestorsActive bytes (transform.hpp:57-58); kTfActive = both (isActive(), :110)
+constexpr uint16_t kTfSelfBit = 16, kTfAncBit = 32;
 constexpr uint32_t kTfDepthShift = 8; // bits 8..15: chain length, saturating at 255 (= unknown: guarded generic walk)
 constexpr uint32_t kTfDepthMax = 255;
 // mesh flags (SoA): static filter of mesh.cpp:140-147 (entity != 0 && isEnabled && !degenerate AABB)
@@ -197,6 +199,8 @@ uint32_t launchLink(Context& c);
 uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter);
 uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);
+uint32_t launchInstances(Context& c, int seg, const float* viewProj, void* dDst, uint32_t stride, uint32_t offset, uint32_t capacity);
+uint32_t launchSetActive(Context& c, const uint32_t* dIds, uint32_t count, int active);
 uint32_t launchExportPacked(Context& c, uint32_t* dBlock, uint32_t capacity);
 uint32_t launchPackVisible(Context& c, uint32_t pool, uint32_t* dBits);
 uint32_t launchVisibleDelta(Context& c, uint32_t pool, uint32_t* list, uint32_t* dCount, uint32_t* hCountMapped);

@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(kStageThreads) kStageTransforms(const uint8_t*
 		if (!localModel43Fast<true>(ps.x, ps.y, ps.z, q.x, q.y, q.z, q.w, ps.w, syz.x, syz.y, unused))
 			f |= kTfExactLocal; // the per-frame kernel must use the guarded 4-lane code for this transform
 		if (e) f |= kTfLive;
+		if (w & 0xffu) f |= kTfSelfBit;
+		if (w & 0xff00u) f |= kTfAncBit;
 		if ((w & 0xffu) && (w & 0xff00u)) f |= kTfActive;   // isActive(), transform.hpp:110
 		if (w & 0xff0000u) f |= kTfAncestors;                // modelWithAncestors, transform.hpp:60,200
 		// the upper byte holds the chain length (kComputeDepth); a TRS-only update keeps it

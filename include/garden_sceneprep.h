@@ -174,6 +174,27 @@ int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint32_t myRank,
 	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
 	uint8_t* dOutRanks, uint32_t outCapacity);
 
+/* ---- the callers either side of the path ----------------------------------------------------------------- */
+/* Instance data of one draw list, in draw order: for record i, mvp = (float4x4)(viewProj * f32x4x4(bakedModel, (0,0,0,1)))
+ * stored at instances + i * stride + mvpOffset (64 bytes, column-major) — what renderUnsorted / renderSorted pass to
+ * IMeshRenderSystem::drawAsync and every setInstanceData stores first (mesh.cpp:600-603,632-635, sprite.cpp:122-130;
+ * instanceIndex == drawIndex for the default getInstancesAsync() == 1). viewProj: 16 floats, column-major.
+ * listKind: 0 = unsortedBuffers[buffer], 1 = transSortedMeshes, 2 = uiSortedMeshes. stride and mvpOffset are multiples of 16.
+ * At most `capacity` instances are written. The host variant needs a completed gsp_run; the device variant only needs the
+ * frame to be enqueued (the draw count is read on the device) and leaves the result in caller-owned device memory, e.g. a
+ * Vulkan buffer imported as CUDA external memory. */
+int gsp_emit_instances(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer, const float* viewProj, void* instances,
+	uint32_t stride, uint32_t mvpOffset, uint32_t capacity);
+int gsp_emit_instances_device(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer, const float* viewProj,
+	void* dInstances, uint32_t stride, uint32_t mvpOffset, uint32_t capacity);
+/* TransformComponent::setActive(active) (source/system/transform.cpp:75-127) for `count` entities (1-based ECS ids) on the
+ * staged hierarchy: selfActive is set, ancestorsActive is re-derived for every transform (AND of its ancestors' selfActive,
+ * the invariant every setActive call maintains), and the next gsp_run filters on the new isActive() values.
+ * gsp_writeback_active stores the resulting selfActive / ancestorsActive bytes (offsets 72 / 73) into the caller's pool.
+ * A later gsp_set_transforms / gsp_update_transforms re-reads these bytes from the caller's memory. */
+int gsp_set_active(gsp_context* ctx, const uint32_t* entityIds, uint32_t count, int active);
+int gsp_writeback_active(gsp_context* ctx, void* aos, uint32_t stride);
+
 /* Stores MeshRenderComponent::isVisible (offset 15) for every slot of `pool` exactly as the reference's main-view pass
  * does (mesh.cpp:144-146,152-153,161-167). No-op for pools the main view did not process. */
 int gsp_writeback_visible(gsp_context* ctx, uint32_t pool, void* aos, uint32_t stride);

@@ -388,6 +388,21 @@ void ref_calc_model(uint32_t entityIndex, const float* cameraPos, float* out)
 	memcpy(out, &model, 64);
 }
 
+// Instance data of a draw list the way renderUnsorted / renderSorted + drawAsync produce it (mesh.cpp:600-603,
+// sprite.cpp:122-130): model = f32x4x4(bakedModel, (0,0,0,1)); mvp = (float4x4)(viewProj * model). out: count x 16 floats.
+void ref_instance_mvp(const float* viewProj, const void* records, uint32_t count, float* out)
+{
+	f32x4x4 vp;
+	memcpy(&vp, viewProj, 64);
+	auto meshes = (const MeshRenderSystem::UnsortedMesh*)records;
+	for (uint32_t i = 0; i < count; i++)
+	{
+		auto model = f32x4x4(meshes[i].bakedModel, f32x4(0.0f, 0.0f, 0.0f, 1.0f));
+		auto mvp = (float4x4)(vp * model);
+		memcpy(out + (size_t)i * 16, &mvp, 64);
+	}
+}
+
 // Times `frames` frames; one frame = viewCount serial prepareMeshes calls (mesh.cpp:795-847,893-903 order:
 // shadow passes first, main view last is the caller's choice of ordering in the arrays).
 // planes: [viewCount][6][4], cameraOffsets: [viewCount][4], shadowPasses: [viewCount]. Writes per-frame ms.

@@ -458,3 +458,124 @@ void oracle_frustum_planes(const float m[16], float planes[6][4])
 		planes[5][l] = t[3][l] - t[2][l];
 	}
 }
+
+/* ---- SURVEY.md §8f rows ----------------------------------------------------------------------------------------------- */
+
+/* f1. renderUnsorted / renderSorted rebuild the model as f32x4x4(mesh.bakedModel, f32x4(0, 0, 0, 1)) (mesh.cpp:600,632,
+ * simd/matrix/float.hpp:87-89: lanes xyz from the float4x3 columns, lane W of column i = r3[i]) and every drawAsync
+ * stores mvp = (float4x4)(viewProj * model) into the instance buffer (sprite.cpp:122-130). */
+void oracle_instance_mvp(const float viewProj[16], const OracleRecord* records, uint32_t count, float* out)
+{
+	for (uint32_t i = 0; i < count; i++)
+	{
+		float model[16];
+		for (int c = 0; c < 4; c++)
+		{
+			model[c * 4 + 0] = records[i].bakedModel[c * 3 + 0];
+			model[c * 4 + 1] = records[i].bakedModel[c * 3 + 1];
+			model[c * 4 + 2] = records[i].bakedModel[c * 3 + 2];
+			model[c * 4 + 3] = c == 3 ? 1.0f : 0.0f;
+		}
+		oracle_mat_mul(viewProj, model, out + (size_t)i * 16);
+	}
+}
+
+/* f3. TransformComponent::setActive, source/system/transform.cpp:75-127, on the AoS pool. The reference walks the
+ * `childs` arrays with an explicit stack; the arrays are not part of the pool bytes, so child lists are rebuilt here from
+ * the parent links (counting sort by parent), which visits the same set of descendants. */
+int oracle_set_active(void* transforms, uint32_t stride, uint32_t occupancy, const uint32_t* entityIds, uint32_t count,
+	int active)
+{
+	uint8_t* base = (uint8_t*)transforms;
+	if (!base || stride < 80 || (!entityIds && count))
+		return -1;
+	uint32_t maxEntity = 0;
+	for (uint32_t i = 0; i < occupancy; i++)
+	{
+		uint32_t e = ld_u32(base + (size_t)i * stride + T_ENTITY);
+		if (e > maxEntity) maxEntity = e;
+	}
+	/* entity id -> slot + 1 (Manager::get<TransformComponent>(entity)) */
+	uint32_t* slotOf = (uint32_t*)calloc((size_t)maxEntity + 1, sizeof(uint32_t));
+	uint32_t* childStart = (uint32_t*)calloc((size_t)occupancy + 2, sizeof(uint32_t));
+	uint32_t* childList = (uint32_t*)malloc(((size_t)occupancy + 1) * sizeof(uint32_t));
+	uint32_t* stack = (uint32_t*)malloc(((size_t)occupancy + 1) * sizeof(uint32_t));
+	if (!slotOf || !childStart || !childList || !stack)
+	{
+		free(slotOf); free(childStart); free(childList); free(stack);
+		return -1;
+	}
+	for (uint32_t i = 0; i < occupancy; i++)
+	{
+		uint32_t e = ld_u32(base + (size_t)i * stride + T_ENTITY);
+		if (e) slotOf[e] = i + 1;
+	}
+	for (uint32_t i = 0; i < occupancy; i++)
+	{
+		const uint8_t* t = base + (size_t)i * stride;
+		uint32_t e = ld_u32(t + T_ENTITY), p = ld_u32(t + T_PARENT);
+		if (e && p && p <= maxEntity && slotOf[p])
+			childStart[slotOf[p] - 1 + 1]++;
+	}
+	for (uint32_t i = 0; i < occupancy; i++)
+		childStart[i + 1] += childStart[i];
+	{
+		uint32_t* fill = (uint32_t*)calloc((size_t)occupancy + 1, sizeof(uint32_t));
+		if (!fill) { free(slotOf); free(childStart); free(childList); free(stack); return -1; }
+		for (uint32_t i = 0; i < occupancy; i++)
+		{
+			const uint8_t* t = base + (size_t)i * stride;
+			uint32_t e = ld_u32(t + T_ENTITY), p = ld_u32(t + T_PARENT);
+			if (e && p && p <= maxEntity && slotOf[p])
+			{
+				uint32_t ps = slotOf[p] - 1;
+				childList[childStart[ps] + fill[ps]++] = i;
+			}
+		}
+		free(fill);
+	}
+	int rc = 0;
+	for (uint32_t k = 0; k < count; k++)
+	{
+		uint32_t e = entityIds[k];
+		if (!e || e > maxEntity || !slotOf[e]) { rc = -1; continue; }
+		uint8_t* self = base + (size_t)(slotOf[e] - 1) * stride;
+		uint8_t isActive = active ? 1 : 0;
+		if ((self[T_SELF_ACTIVE] != 0) == (isActive != 0))
+			continue;                               /* :77-78 */
+		self[T_SELF_ACTIVE] = isActive;             /* :80 */
+		uint32_t top = 0;
+		stack[top++] = slotOf[e] - 1;               /* :83 */
+		if (isActive)
+		{
+			if (!self[T_ANC_ACTIVE])
+				continue;                           /* :87-88 */
+			while (top)
+			{
+				uint32_t s = stack[--top];
+				uint8_t* t = base + (size_t)s * stride;
+				if (!t[T_SELF_ACTIVE])
+					continue;                       /* :94-95 */
+				for (uint32_t c = childStart[s]; c < childStart[s + 1]; c++)
+				{
+					base[(size_t)childList[c] * stride + T_ANC_ACTIVE] = 1; /* :104 */
+					stack[top++] = childList[c];
+				}
+			}
+		}
+		else
+		{
+			while (top)
+			{
+				uint32_t s = stack[--top];
+				for (uint32_t c = childStart[s]; c < childStart[s + 1]; c++)
+				{
+					base[(size_t)childList[c] * stride + T_ANC_ACTIVE] = 0; /* :122 */
+					stack[top++] = childList[c];
+				}
+			}
+		}
+	}
+	free(slotOf); free(childStart); free(childList); free(stack);
+	return rc;
+}

@@ -77,6 +77,16 @@ void oracle_mat_mul(const float a[16], const float b[16], float out[16]);
 /* math::calcModel(position, rotation, scale) general branch (matrix/transform.hpp:251-256). */
 void oracle_local_model(const float pos[3], const float rot[4], const float scale[3], float out[16]);
 
+/* ---- SURVEY.md §8f rows ("next") ------------------------------------------------------------------------------------ */
+/* f1: per-instance mvp = (float4x4)(viewProj * f32x4x4(bakedModel, (0,0,0,1))) for every record of a draw list, in draw
+ * order (mesh.cpp:600-603 + sprite.cpp:122-130). viewProj column-major; out: count x 16 floats. */
+void oracle_instance_mvp(const float viewProj[16], const OracleRecord* records, uint32_t count, float* out);
+/* f3: TransformComponent::setActive (source/system/transform.cpp:75-127) applied to `count` entities in order, on the AoS
+ * transform pool in place (selfActive @72, ancestorsActive @73): explicit stack walk over child lists rebuilt from the
+ * parent links, exactly as the reference walks `childs`. entityIds are 1-based ECS ids. Returns 0, or -1 on bad input. */
+int oracle_set_active(void* transforms, uint32_t stride, uint32_t occupancy, const uint32_t* entityIds, uint32_t count,
+	int active);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,5 +95,50 @@ def main():
         print(f"{name}: {scene.entity_count} entities, {views.size} views, {total} records -> {path.stat().st_size / 1024:.0f} KiB")
 
 
+def f_rows():
+    """Golden vectors of the SURVEY.md 8f rows, from the reference itself -> tests/golden/frows/f_rows.npz:
+      f1  per view: viewProj, the reference's draw list (first 400 records) and (float4x4)(viewProj * model) per record;
+      f3  transform pool bytes, a sequence of TransformComponent::setActive calls, and bytes 72/73 after every call."""
+    out = {}
+    scene = scenes.config_scene("C2", n=4000)
+    scene.camera_pos = np.array([5.0, 2.0, -3.0], np.float32)
+    views, vps = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    with reflib.RefEngine("parity", threads=0) as ref:
+        ref.load_scene(scene)
+        for v in range(views.size):
+            ref.prepare(views[v])
+            rec = canonical(ref.get_unsorted(0)[0], False)[:400]
+            vp = np.asarray(vps[v], dtype=np.float32).reshape(16)
+            out[f"f1_vp{v}"] = vp
+            out[f"f1_records{v}"] = rec
+            out[f"f1_mvp{v}"] = ref.instance_mvp(vp, rec)
+    out["f1_views"] = np.array([views.size], np.uint32)
+    scene = mixed_scene(seed=5, n=1200, max_depth=12, with_ui=False, with_ready=False)
+    rng = np.random.default_rng(23)
+    with reflib.RefEngine("parity", threads=0) as ref:
+        ref.load_scene(scene)
+        _, tstride, tocc = ref.transform_pool()
+        tbytes = ref.transform_bytes().reshape(tocc, tstride).copy()
+        tbytes[:, 8:16] = 0    # uid
+        tbytes[:, 64:72] = 0   # childs
+        out["f3_transforms"] = tbytes
+        ents = tbytes[:, 0:4].copy().view(np.uint32).reshape(-1)
+        live = np.nonzero(ents)[0]
+        steps = 10
+        for step in range(steps):
+            pick = rng.choice(live, size=int(rng.integers(1, 40)), replace=True)
+            active = bool(step % 3 == 2) if step < 6 else bool(rng.integers(0, 2))
+            ref.set_active(ents[pick] - 1, active)
+            out[f"f3_ids{step}"] = ents[pick].astype(np.uint32)
+            out[f"f3_active{step}"] = np.array([1 if active else 0], np.uint8)
+            out[f"f3_after{step}"] = ref.transform_bytes().reshape(tocc, tstride)[:, 72:74].copy()
+        out["f3_steps"] = np.array([steps], np.uint32)
+    (HERE / "frows").mkdir(exist_ok=True)
+    path = HERE / "frows" / "f_rows.npz"
+    np.savez_compressed(path, **out)
+    print(f"f_rows -> {path.stat().st_size / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     main()
+    f_rows()

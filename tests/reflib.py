@@ -79,6 +79,7 @@ class RefEngine:
         L.ref_get_sorted.argtypes = [_i32, _pp, _pu32]
         L.ref_calc_model.argtypes = [_u32, _vp, _vp]
         L.ref_time_frames.argtypes = [_u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp]
+        L.ref_instance_mvp.argtypes = [_vp, _vp, _u32, _vp]
         if L.ref_init(threads, 1 if use_oit else 0) != 0:
             raise RuntimeError("reference engine is already initialised in this process")
         self.pool_strides = []
@@ -124,6 +125,20 @@ class RefEngine:
             self.lib.ref_set_active(idx.size, idx.ctypes.data, 0)
         cam = f32(scene.camera_pos)
         self.lib.ref_set_camera(cam.ctypes.data)
+
+    def set_active(self, indices, active: bool):
+        """TransformComponent::setActive for the given entity INDICES (0-based creation order), in order."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        self.lib.ref_set_active(idx.size, idx.ctypes.data, 1 if active else 0)
+
+    def instance_mvp(self, view_proj, records: np.ndarray) -> np.ndarray:
+        """(float4x4)(viewProj * f32x4x4(bakedModel, (0,0,0,1))) per record, by the reference's own math library."""
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        rec = np.ascontiguousarray(records)
+        out = np.zeros((rec.size, 16), dtype=np.float32)
+        if rec.size:
+            self.lib.ref_instance_mvp(vp.ctypes.data, rec.ctypes.data, rec.size, out.ctypes.data)
+        return out
 
     def destroy_entities(self, indices):
         idx = np.ascontiguousarray(indices, dtype=np.uint32)
@@ -254,6 +269,9 @@ class Oracle:
         L.oracle_frustum_planes.argtypes = [_vp, _vp]
         L.oracle_mat_mul.argtypes = [_vp, _vp, _vp]
         L.oracle_local_model.argtypes = [_vp, _vp, _vp, _vp]
+        L.oracle_instance_mvp.argtypes = [_vp, _vp, _u32, _vp]
+        L.oracle_set_active.argtypes = [_vp, _u32, _u32, _vp, _u32, _i32]
+        L.oracle_set_active.restype = _i32
         self.h = L.oracle_create()
         self._keep = []
         self.occupancy = {}
@@ -338,3 +356,16 @@ class Oracle:
         out = np.zeros((6, 4), dtype=np.float32)
         self.lib.oracle_frustum_planes(m.ctypes.data, out.ctypes.data)
         return out
+
+    def instance_mvp(self, view_proj, records: np.ndarray) -> np.ndarray:
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        rec = np.ascontiguousarray(records)
+        out = np.zeros((rec.size, 16), dtype=np.float32)
+        if rec.size:
+            self.lib.oracle_instance_mvp(vp.ctypes.data, rec.ctypes.data, rec.size, out.ctypes.data)
+        return out
+
+    def set_active(self, transforms: np.ndarray, stride: int, occupancy: int, entity_ids, active: bool) -> int:
+        """TransformComponent::setActive on AoS transform bytes IN PLACE (entity ids are 1-based)."""
+        ids = np.ascontiguousarray(entity_ids, dtype=np.uint32)
+        return self.lib.oracle_set_active(transforms.ctypes.data, stride, occupancy, ids.ctypes.data, ids.size, 1 if active else 0)

@@ -132,3 +132,46 @@ def test_animated_update(oracle_built):
             got = ref_frame(ref, views)
             want = _oracle_on_ref_memory(ref, scene, views)
             assert_frames_equal(got, want.views, rts, f"frame {frame}")
+
+
+# ---- SURVEY.md §8f rows -------------------------------------------------------------------------------------------------
+def test_instance_mvp_matches_reference(oracle_built):
+    """f1: (float4x4)(viewProj * f32x4x4(bakedModel, (0,0,0,1))) by the reference's math library vs the restatement, bit for
+    bit, on the draw lists of every view of a C2-shaped scene (perspective and orthographic viewProj)."""
+    scene = scenes.config_scene("C2", n=4000)
+    scene.camera_pos = np.array([5.0, 2.0, -3.0], np.float32)
+    views, vps = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    o = reflib.Oracle()
+    total = 0
+    with reflib.RefEngine("parity", threads=0) as ref:
+        ref.load_scene(scene)
+        for v in range(views.size):
+            ref.prepare(views[v])
+            rec = ref.get_unsorted(0)[0]
+            vp = np.asarray(vps[v], dtype=np.float32).reshape(16)
+            a, b = ref.instance_mvp(vp, rec), o.instance_mvp(vp, rec)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"view {v}: mvp bits differ"
+            total += rec.size
+    assert total > 500
+
+
+def test_set_active_matches_reference(oracle_built):
+    """f3: TransformComponent::setActive sequences through the real ECS vs the restatement on a copy of the pool bytes:
+    selfActive / ancestorsActive of every transform after every call."""
+    scene = mixed_scene(seed=5, n=1200, max_depth=12, with_ui=False, with_ready=False)
+    rng = np.random.default_rng(17)
+    o = reflib.Oracle()
+    with reflib.RefEngine("parity", threads=0) as ref:
+        ref.load_scene(scene)
+        _, tstride, tocc = ref.transform_pool()
+        mine = ref.transform_bytes().reshape(tocc, tstride).copy()
+        ents = mine[:, 0:4].copy().view(np.uint32).reshape(-1)
+        live = np.nonzero(ents)[0]
+        for step in range(12):
+            pick = rng.choice(live, size=int(rng.integers(1, 40)), replace=True)  # duplicates included
+            active = bool(step % 3 == 2) if step < 8 else bool(rng.integers(0, 2))
+            ref.set_active(ents[pick] - 1, active)          # harness takes 0-based creation indices == id - 1
+            assert o.set_active(mine, tstride, tocc, ents[pick], active) == 0
+            theirs = ref.transform_bytes().reshape(tocc, tstride)
+            assert np.array_equal(theirs[:, 72:74], mine[:, 72:74]), f"step {step}: active flags differ"
+        assert 0 < int(mine[live, 73].sum()) < live.size  # both states occur
