@@ -37,13 +37,27 @@ WORKLOADS = {
     "C4": ("C4", 16_000_000, "16M instances, depth-8 hierarchy, camera + 4 CSM cascades"),
     "C2": ("C2", 1_000_000, "1M entities, depth-4 hierarchy, camera + 4 CSM cascades"),
     "C3": ("C3", 4_000_000, "4M entities, depth-8, opaque + translucent, 1 view"),
+    # configs[4]: 64M entities over 8 GPUs = 8M per GPU (weak-scaling shard), 16 independent views
+    "C5": ("C5", 8_000_000, "64M entities / 8 GPUs (8M per GPU), depth-8, 16 independent views (2 cube probes + 4 split-screen)"),
 }
+CUBE_FACES = [(0.0, 0.0), (1.5707964, 0.0), (3.1415927, 0.0), (-1.5707964, 0.0), (0.0, 1.5), (0.0, -1.5)]  # (yaw, pitch)
+
+
+def frame_views_vps(workload: str):
+    """(views, viewProj matrices) of one frame of the workload."""
+    if workload == "C3":
+        return V.perspective_views([(0.6, -0.05)], 1.2, 16 / 9, 0.01)
+    if workload == "C5":
+        # two cube-map probes (6 faces each, 90 degree fov, aspect 1; the second rotated by 0.4 rad) + 4 split-screen cameras
+        a, va = V.perspective_views(CUBE_FACES, 1.5707964, 1.0, 0.01)
+        b, vb = V.perspective_views([(y + 0.4, p * 0.9) for y, p in CUBE_FACES], 1.5707964, 1.0, 0.01)
+        c, vc = V.perspective_views([(0.3, -0.1), (1.9, -0.05), (3.6, -0.12), (5.1, -0.08)], 1.2, 16 / 9, 0.01)
+        return np.concatenate([a, b, c]), list(va) + list(vb) + list(vc)
+    return V.camera_and_cascades(0.6, -0.12, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
 
 
 def frame_views(workload: str):
-    if workload == "C3":
-        return V.perspective_views([(0.6, -0.05)], 1.2, 16 / 9, 0.01)[0]
-    return V.camera_and_cascades(0.6, -0.12, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))[0]
+    return frame_views_vps(workload)[0]
 
 
 def camera_pos():
@@ -326,9 +340,7 @@ def run_b200_arm(args):
         _, main_draw, _ = sp.get_unsorted_device(vi, 0)
         if main_draw:
             inst = torch.empty(main_draw * 16, dtype=torch.float32, device="cuda")
-            vp0 = np.asarray(V.camera_and_cascades(0.6, -0.12, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))[1][vi]
-                             if args.workload != "C3" else V.perspective_views([(0.6, -0.05)], 1.2, 16 / 9, 0.01)[1][vi],
-                             dtype=np.float32).reshape(16)
+            vp0 = np.asarray(frame_views_vps(args.workload)[1][vi], dtype=np.float32).reshape(16)
             sp.run_async()
             for _ in range(3):
                 sp.emit_instances_device(vi, 0, 0, vp0, inst.data_ptr(), main_draw)
