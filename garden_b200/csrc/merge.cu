@@ -50,34 +50,64 @@ __device__ __forceinline__ uint32_t upperBound(const uint32_t* __restrict__ a, u
 	return lo;
 }
 
-// One thread per (list, run): the sub-range of the run inside my key range [splitLo, splitHi).
+// Warp-cooperative bound: all 32 lanes call it with the same arguments. Every round probes 32 evenly spaced positions of the
+// remaining range and keeps the 1/33 of it that contains the answer, so a run of millions of keys takes 4-5 dependent
+// memory round trips instead of 22 (the searches that bracket a chunk are pure latency).
+// kUpper: first index with a[i] > key, else first index with a[i] >= key.
+template<bool kUpper>
+__device__ __forceinline__ uint32_t warpBound(const uint32_t* __restrict__ a, uint32_t n, uint32_t key)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t lo = 0, hi = n; // the answer lies in [lo, hi]
+	while (hi - lo > 32)
+	{
+		const uint64_t span = hi - lo;
+		const uint32_t p = lo + (uint32_t)(((uint64_t)(lane + 1) * span) / 33); // lo < p < hi, increasing with the lane
+		const uint32_t v = a[p];
+		const uint32_t before = __ballot_sync(0xffffffffu, kUpper ? v <= key : v < key); // a prefix of the lanes
+		const uint32_t t = __popc(before);
+		const uint32_t pPrev = __shfl_sync(0xffffffffu, p, t ? t - 1 : 0), pNext = __shfl_sync(0xffffffffu, p, t < 32 ? t : 31);
+		if (t) lo = pPrev + 1;
+		if (t < 32) hi = pNext;
+	}
+	const uint32_t i = lo + lane;
+	const uint32_t v = i < hi ? a[i] : 0u;
+	const uint32_t before = __ballot_sync(0xffffffffu, i < hi && (kUpper ? v <= key : v < key));
+	return lo + __popc(before);
+}
+
+// One WARP per (list, run): the sub-range of the run inside my key range [splitLo, splitHi).
 // Splitter k = key at position k * count / ranks of the longest run (k = 1..ranks-1); range 0 starts at -inf, the last
 // ends at +inf. (If every run is empty there is nothing to split.)
-__global__ void kMergeBounds(const __grid_constant__ MergeArgs A)
+__global__ void __launch_bounds__(1024) kMergeBounds(const __grid_constant__ MergeArgs A)
 {
-	const uint32_t list = blockIdx.x, run = threadIdx.x;
-	if (run >= A.ranks)
-		return;
-	// splitter source: the longest run of this list (lowest rank on ties); every rank sees the same counts
-	uint32_t src = 0;
-	for (uint32_t r = 1; r < A.ranks; r++)
-		if (A.counts[r * A.lists + list] > A.counts[src * A.lists + list]) src = r;
-	const uint32_t count0 = A.counts[src * A.lists + list];
-	const uint32_t* run0 = A.keys + (size_t)src * A.rankStride + A.offsets[src * A.lists + list];
-	const uint32_t me = A.myRank;
-	bool hasLo = me > 0 && count0 > 0, hasHi = me + 1 < A.ranks && count0 > 0;
-	const uint32_t keyLo = hasLo ? run0[(uint64_t)me * count0 / A.ranks] : 0u;
-	const uint32_t keyHi = hasHi ? run0[(uint64_t)(me + 1) * count0 / A.ranks] : 0u;
-	const uint32_t n = A.counts[run * A.lists + list];
-	const uint32_t* a = A.keys + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
-	// a key equal to a splitter belongs to the range that starts at the splitter
-	uint32_t lo = hasLo ? lowerBound(a, n, keyLo) : 0u;
-	uint32_t hi = hasHi ? lowerBound(a, n, keyHi) : n;
-	if (hi < lo) hi = lo; // equal splitters
-	A.bounds[(list * A.ranks + run) * 2 + 0] = lo;
-	A.bounds[(list * A.ranks + run) * 2 + 1] = hi;
+	const uint32_t list = blockIdx.x, run = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (run < A.ranks) // (whole warps)
+	{
+		// splitter source: the longest run of this list (lowest rank on ties); every rank sees the same counts
+		uint32_t src = 0;
+		for (uint32_t r = 1; r < A.ranks; r++)
+			if (A.counts[r * A.lists + list] > A.counts[src * A.lists + list]) src = r;
+		const uint32_t count0 = A.counts[src * A.lists + list];
+		const uint32_t* run0 = A.keys + (size_t)src * A.rankStride + A.offsets[src * A.lists + list];
+		const uint32_t me = A.myRank;
+		const bool hasLo = me > 0 && count0 > 0, hasHi = me + 1 < A.ranks && count0 > 0;
+		const uint32_t keyLo = hasLo ? run0[(uint64_t)me * count0 / A.ranks] : 0u;
+		const uint32_t keyHi = hasHi ? run0[(uint64_t)(me + 1) * count0 / A.ranks] : 0u;
+		const uint32_t n = A.counts[run * A.lists + list];
+		const uint32_t* a = A.keys + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
+		// a key equal to a splitter belongs to the range that starts at the splitter
+		uint32_t lo = hasLo ? warpBound<false>(a, n, keyLo) : 0u;
+		uint32_t hi = hasHi ? warpBound<false>(a, n, keyHi) : n;
+		if (hi < lo) hi = lo; // equal splitters
+		if (lane == 0)
+		{
+			A.bounds[(list * A.ranks + run) * 2 + 0] = lo;
+			A.bounds[(list * A.ranks + run) * 2 + 1] = hi;
+		}
+	}
 	__syncthreads();
-	if (run == 0)
+	if (threadIdx.x == 0)
 	{
 		uint32_t start = 0, length = 0;
 		for (uint32_t r = 0; r < A.ranks; r++)
@@ -97,6 +127,26 @@ __global__ void kMergeBounds(const __grid_constant__ MergeArgs A)
 //    first element and then only advances (a few steps on average; a fresh bracketed binary search when the advance is long).
 // Cost per element: O(ranks) short advances instead of O(ranks * log(run length)) dependent loads.
 constexpr uint32_t kMergeItems = 8, kMergeThreads = 128, kMergeChunk = kMergeItems * kMergeThreads;
+// Brackets a chunk [firstKey, lastKey] of run `run` in every other run: the block's warps share the 2 * (ranks - 1)
+// searches, each done cooperatively by a whole warp. Lower ranks win ties (they hold lower global entity indices), so
+// runs below `run` are searched with the upper bound.
+__device__ __forceinline__ void bracketChunk(const MergeArgs& A, uint32_t list, uint32_t run, uint32_t firstKey, uint32_t lastKey,
+	uint32_t* sLo, uint32_t* sHi)
+{
+	const uint32_t warp = threadIdx.x >> 5, warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+	for (uint32_t job = warp; job < 2 * A.ranks; job += warps)
+	{
+		const uint32_t r = job >> 1;
+		if (r == run)
+			continue;
+		const uint32_t n = A.counts[r * A.lists + list];
+		const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
+		const uint32_t key = (job & 1) ? lastKey : firstKey;
+		const uint32_t pos = r < run ? warpBound<true>(a, n, key) : warpBound<false>(a, n, key);
+		if (lane == 0)
+			((job & 1) ? sHi : sLo)[r] = pos;
+	}
+}
 template<bool kUpper> // kUpper: count elements <= key (ties go to the other run), else elements < key
 __device__ __forceinline__ uint32_t boundIn(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t key)
 {
@@ -153,16 +203,7 @@ __global__ void __launch_bounds__(kMergeThreads) kMergeSliceWide(const __grid_co
 			sKey[stagedIndex(j)] = myKeys[i0 + j];
 			sPay[stagedIndex(j)] = myPays[i0 + j];
 		}
-		if (threadIdx.x < A.ranks && threadIdx.x != run)
-		{
-			const uint32_t r = threadIdx.x;
-			const uint32_t n = A.counts[r * A.lists + list];
-			const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
-			const uint32_t firstKey = myKeys[i0], lastKey = myKeys[i1 - 1];
-			// lower ranks win ties (they hold lower global entity indices)
-			sLo[r] = r < run ? upperBound(a, n, firstKey) : lowerBound(a, n, firstKey);
-			sHi[r] = r < run ? upperBound(a, n, lastKey) : lowerBound(a, n, lastKey);
-		}
+		bracketChunk(A, list, run, myKeys[i0], myKeys[i1 - 1], sLo, sHi);
 		__syncthreads();
 		const uint32_t local = threadIdx.x * kMergeItems, first = i0 + local;
 		if (first >= i1)
@@ -214,15 +255,7 @@ __global__ void __launch_bounds__(256) kMergeSlice(const __grid_constant__ Merge
 	{
 		const uint32_t i1 = min(i0 + kMergeChunk, hi);
 		__syncthreads();
-		if (threadIdx.x < A.ranks && threadIdx.x != run)
-		{
-			const uint32_t r = threadIdx.x;
-			const uint32_t n = A.counts[r * A.lists + list];
-			const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
-			const uint32_t firstKey = myKeys[i0], lastKey = myKeys[i1 - 1];
-			sLo[r] = r < run ? upperBound(a, n, firstKey) : lowerBound(a, n, firstKey);
-			sHi[r] = r < run ? upperBound(a, n, lastKey) : lowerBound(a, n, lastKey);
-		}
+		bracketChunk(A, list, run, myKeys[i0], myKeys[i1 - 1], sLo, sHi);
 		__syncthreads();
 		for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
 		{
@@ -247,7 +280,7 @@ uint32_t launchMerge(cudaStream_t stream, const MergeArgs& A, uint32_t maxRunLen
 {
 	if (A.lists == 0 || A.ranks == 0)
 		return 0;
-	kMergeBounds<<<A.lists, 32, 0, stream>>>(A);
+	kMergeBounds<<<A.lists, 32 * A.ranks, 0, stream>>>(A);
 	const uint32_t blocks = std::max(1u, std::min((maxRunLength / A.ranks + kMergeChunk - 1u) / kMergeChunk + 1u, 148u * 8u / std::max(1u, A.ranks)));
 	if (A.ranks <= 3)
 		kMergeSlice<<<dim3(blocks, A.ranks, A.lists), 256, 0, stream>>>(A);
