@@ -53,6 +53,8 @@ SYMBOLS = {
     "gsp_merge_gathered_packed": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "gsp_emit_instances": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _u32, _u32, _u32]),
     "gsp_emit_instances_device": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _u32, _u32, _u32]),
+    "gsp_frustum_planes": (None, [_vp, _vp]),
+    "gsp_view_from_viewproj": (_i32, [_vp, _vp, _i32, _vp]),
     "gsp_set_active": (_i32, [_vp, _vp, _u32, _i32]),
     "gsp_writeback_active": (_i32, [_vp, _vp, _u32]),
     "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),

@@ -951,6 +951,39 @@ int gsp_emit_instances_device(gsp_context* ctx, uint32_t view, int listKind, uin
 	return emitInstances(ctx, view, listKind, buffer, viewProj, dInstances, stride, mvpOffset, capacity, true);
 }
 
+// f4 (host part): Frustum(viewProj), libraries/math/include/math/frustum.hpp:51-61 — Gribb & Hartmann on the transposed
+// matrix with the Vulkan Y flip; planes stay unnormalised, exactly what prepareMeshes receives (mesh.cpp:815,869,902).
+void gsp_frustum_planes(const float* viewProj, float* planes)
+{
+	if (!viewProj || !planes)
+		return;
+	const volatile float* m = viewProj; // (volatile: every sum below is one separately rounded float operation)
+	for (int l = 0; l < 4; l++)
+	{
+		// t = transpose4x4(viewProj): lane l of t.c_i = lane i of viewProj.c_l
+		const float t0 = m[l * 4 + 0], t1 = m[l * 4 + 1], t2 = m[l * 4 + 2], t3 = m[l * 4 + 3];
+		planes[0 * 4 + l] = t3 + t0;
+		planes[1 * 4 + l] = t3 - t0;
+		planes[2 * 4 + l] = t3 - t1;
+		planes[3 * 4 + l] = t3 + t1;
+		planes[4 * 4 + l] = t2;
+		planes[5 * 4 + l] = t3 - t2;
+	}
+}
+
+int gsp_view_from_viewproj(const float* viewProj, const float* cameraOffset, int32_t shadowPass, gsp_view* view)
+{
+	if (!viewProj || !view)
+		return GSP_ERR_INVALID;
+	memset(view, 0, sizeof(*view));
+	gsp_frustum_planes(viewProj, &view->planes[0][0]);
+	view->planeCount = 6;
+	if (cameraOffset)
+		memcpy(view->cameraOffset, cameraOffset, sizeof(view->cameraOffset));
+	view->shadowPass = shadowPass;
+	return GSP_OK;
+}
+
 int gsp_set_active(gsp_context* ctx, const uint32_t* entityIds, uint32_t count, int active)
 {
 	if (!ctx || (!entityIds && count))

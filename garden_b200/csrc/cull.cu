@@ -626,7 +626,9 @@ __global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constan
 	const uint32_t units = A.chunks * P.viewCount;
 	for (uint32_t u = blockIdx.x * kScatterWarps + warp; u < units; u += gridDim.x * kScatterWarps)
 	{
-		const uint32_t v = u % P.viewCount, chunk = u / P.viewCount;
+		// chunks are walked from the END of the pool: the world matrices kCull wrote last are still in L2 when this kernel
+		// starts, the ones it wrote first were evicted long ago either way (list positions come from the scan, not the order)
+		const uint32_t v = u % P.viewCount, chunk = A.chunks - 1 - u / P.viewCount;
 		const ViewConst& V = P.views[v];
 		if (!V.enabled) // warp-uniform
 			continue;
@@ -817,7 +819,9 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	{
 		cudaFuncSetAttribute(kCull<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(kCull<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(kCull<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -827,7 +831,9 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	// the view loop is unrolled at compile time (plane constants become direct constant-bank operands)
 	if (P.viewCount <= 1) kCull<1><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
 	else if (P.viewCount <= 2) kCull<2><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	else if (P.viewCount <= 3) kCull<3><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
 	else if (P.viewCount <= 4) kCull<4><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	else if (P.viewCount <= 5) kCull<5><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A); // camera + 4 cascades
 	else if (P.viewCount <= 6) kCull<6><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
 	else if (P.viewCount <= 8) kCull<8><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
 	else kCull<16><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);

@@ -121,12 +121,23 @@ __global__ void __launch_bounds__(1024) kMergeBounds(const __grid_constant__ Mer
 }
 
 // grid (blocks, ranks, lists): a block takes chunks of kMergeChunk consecutive elements of one run's sub-range and places
-// them into my slice. Positions inside the other runs are monotone along the run, so
-//  * the block first brackets the chunk in every other run (two full binary searches per run, one thread each);
-//  * a thread owns kMergeItems CONSECUTIVE elements: per other run it does one binary search inside the bracket for its
-//    first element and then only advances (a few steps on average; a fresh bracketed binary search when the advance is long).
-// Cost per element: O(ranks) short advances instead of O(ranks * log(run length)) dependent loads.
-constexpr uint32_t kMergeItems = 8, kMergeThreads = 128, kMergeChunk = kMergeItems * kMergeThreads;
+// them into my slice. Positions inside the other runs are monotone along the run, so the block first brackets the chunk in
+// every other run (warp-cooperative searches), then copies the bracketed windows — together about ranks x chunk keys —
+// into shared memory with coalesced loads, and every element ranks itself in every window by a binary search in SHARED
+// memory (a scattered global search costs one L1 wavefront per lane, a shared one roughly one per warp). A chunk whose
+// windows do not fit (very uneven key densities between ranks) searches the brackets in global memory instead.
+constexpr uint32_t kMergeThreads = 256, kMergeChunk = 1024, kMergeWindow = 10240; // window keys staged per chunk (40 KB)
+template<bool kUpper> // kUpper: count elements <= key (ties go to the other run), else elements < key
+__device__ __forceinline__ uint32_t boundIn(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t key)
+{
+	while (lo < hi)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		const uint32_t v = a[mid];
+		if (kUpper ? v <= key : v < key) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
 // Brackets a chunk [firstKey, lastKey] of run `run` in every other run: the block's warps share the 2 * (ranks - 1)
 // searches, each done cooperatively by a whole warp. Lower ranks win ties (they hold lower global entity indices), so
 // runs below `run` are searched with the upper bound.
@@ -147,47 +158,13 @@ __device__ __forceinline__ void bracketChunk(const MergeArgs& A, uint32_t list, 
 			((job & 1) ? sHi : sLo)[r] = pos;
 	}
 }
-template<bool kUpper> // kUpper: count elements <= key (ties go to the other run), else elements < key
-__device__ __forceinline__ uint32_t boundIn(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t key)
+// kStage = false (2-3 ranks): the brackets are searched in global memory — with one or two other runs the windows stay in
+// L1 and that measured faster than staging them (N=2: 0.07 vs 0.09 ms); kStage = true (>= 4 ranks) stages as described.
+template<bool kStage>
+__global__ void __launch_bounds__(kMergeThreads) kMergeSlice(const __grid_constant__ MergeArgs A)
 {
-	while (lo < hi)
-	{
-		const uint32_t mid = (lo + hi) >> 1;
-		const uint32_t v = a[mid];
-		if (kUpper ? v <= key : v < key) lo = mid + 1; else hi = mid;
-	}
-	return lo;
-}
-template<bool kUpper>
-__device__ __forceinline__ void rankItems(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, const uint32_t (&key)[kMergeItems],
-	uint32_t count, uint32_t (&pos)[kMergeItems])
-{
-	uint32_t p = boundIn<kUpper>(a, lo, hi, key[0]);
-	pos[0] += p;
-	#pragma unroll
-	for (uint32_t e = 1; e < kMergeItems; e++)
-	{
-		if (e < count)
-		{
-			uint32_t steps = 0;
-			while (p < hi && steps < 4)
-			{
-				const uint32_t v = a[p];
-				if (!(kUpper ? v <= key[e] : v < key[e]))
-					break;
-				p++; steps++;
-			}
-			if (steps == 4)
-				p = boundIn<kUpper>(a, p, hi, key[e]);
-			pos[e] += p;
-		}
-	}
-}
-__device__ __forceinline__ uint32_t stagedIndex(uint32_t i) { return i + (i >> 5); } // conflict-free for stride-8 readers
-__global__ void __launch_bounds__(kMergeThreads) kMergeSliceWide(const __grid_constant__ MergeArgs A)
-{
-	__shared__ uint32_t sLo[32], sHi[32];
-	__shared__ uint32_t sKey[kMergeChunk + kMergeChunk / 32], sPay[kMergeChunk + kMergeChunk / 32];
+	__shared__ uint32_t sLo[32], sHi[32], sOff[33];
+	__shared__ uint32_t sWin[kStage ? kMergeWindow : 1];
 	const uint32_t list = blockIdx.z, run = blockIdx.y;
 	const uint32_t lo = A.bounds[(list * A.ranks + run) * 2 + 0], hi = A.bounds[(list * A.ranks + run) * 2 + 1];
 	const uint32_t sliceStart = A.sliceInfo[list * 2 + 0];
@@ -197,67 +174,36 @@ __global__ void __launch_bounds__(kMergeThreads) kMergeSliceWide(const __grid_co
 	for (uint32_t i0 = lo + blockIdx.x * kMergeChunk; i0 < hi; i0 += gridDim.x * kMergeChunk)
 	{
 		const uint32_t i1 = min(i0 + kMergeChunk, hi);
+		__syncthreads(); // the previous chunk's readers are done with the shared arrays
+		if (threadIdx.x < A.ranks)
+			sLo[threadIdx.x] = sHi[threadIdx.x] = 0; // (the own run keeps an empty window)
 		__syncthreads();
-		for (uint32_t j = threadIdx.x; j < i1 - i0; j += kMergeThreads) // coalesced staging of the chunk
-		{
-			sKey[stagedIndex(j)] = myKeys[i0 + j];
-			sPay[stagedIndex(j)] = myPays[i0 + j];
-		}
 		bracketChunk(A, list, run, myKeys[i0], myKeys[i1 - 1], sLo, sHi);
 		__syncthreads();
-		const uint32_t local = threadIdx.x * kMergeItems, first = i0 + local;
-		if (first >= i1)
-			continue;
-		const uint32_t count = min(kMergeItems, i1 - first);
-		uint32_t key[kMergeItems], pos[kMergeItems];
-		#pragma unroll
-		for (uint32_t e = 0; e < kMergeItems; e++)
+		if (threadIdx.x == 0)
 		{
-			key[e] = e < count ? sKey[stagedIndex(local + e)] : 0xFFFFFFFFu;
-			pos[e] = first + e;
-		}
-		for (uint32_t r = 0; r < A.ranks; r++)
-		{
-			if (r == run)
-				continue;
-			const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
-			if (r < run)
-				rankItems<true>(a, sLo[r], sHi[r], key, count, pos);
-			else
-				rankItems<false>(a, sLo[r], sHi[r], key, count, pos);
-		}
-		#pragma unroll
-		for (uint32_t e = 0; e < kMergeItems; e++)
-		{
-			if (e < count)
+			uint32_t running = 0;
+			for (uint32_t r = 0; r < A.ranks; r++)
 			{
-				const uint32_t o = outBase + (pos[e] - sliceStart);
-				A.outKeys[o] = key[e];
-				A.outPayloads[o] = sPay[stagedIndex(local + e)];
-				A.outRanks[o] = (uint8_t)run;
+				sOff[r] = running;
+				running += sHi[r] - sLo[r];
 			}
+			sOff[A.ranks] = running;
 		}
-	}
-}
-
-// Few ranks (2 or 3): one element per thread, consecutive threads on consecutive elements (coalesced reads, neighbouring
-// writes); each element runs a binary search inside the chunk's bracket of every other run.
-__global__ void __launch_bounds__(256) kMergeSlice(const __grid_constant__ MergeArgs A)
-{
-	__shared__ uint32_t sLo[32], sHi[32];
-	const uint32_t list = blockIdx.z, run = blockIdx.y;
-	const uint32_t lo = A.bounds[(list * A.ranks + run) * 2 + 0], hi = A.bounds[(list * A.ranks + run) * 2 + 1];
-	const uint32_t sliceStart = A.sliceInfo[list * 2 + 0];
-	const uint32_t* myKeys = A.keys + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
-	const uint32_t* myPays = A.payloads + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
-	const uint32_t outBase = A.outOffsets[list];
-	for (uint32_t i0 = lo + blockIdx.x * kMergeChunk; i0 < hi; i0 += gridDim.x * kMergeChunk)
-	{
-		const uint32_t i1 = min(i0 + kMergeChunk, hi);
 		__syncthreads();
-		bracketChunk(A, list, run, myKeys[i0], myKeys[i1 - 1], sLo, sHi);
-		__syncthreads();
-		for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+		const bool staged = kStage && sOff[A.ranks] <= kMergeWindow; // block-uniform
+		if (staged)
+		{
+			for (uint32_t r = 0; r < A.ranks; r++)
+			{
+				const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list] + sLo[r];
+				const uint32_t w = sHi[r] - sLo[r];
+				for (uint32_t j = threadIdx.x; j < w; j += kMergeThreads)
+					sWin[sOff[r] + j] = a[j];
+			}
+			__syncthreads();
+		}
+		for (uint32_t i = i0 + threadIdx.x; i < i1; i += kMergeThreads)
 		{
 			const uint32_t key = myKeys[i];
 			uint32_t pos = i;
@@ -265,8 +211,16 @@ __global__ void __launch_bounds__(256) kMergeSlice(const __grid_constant__ Merge
 			{
 				if (r == run)
 					continue;
-				const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
-				pos += r < run ? boundIn<true>(a, sLo[r], sHi[r], key) : boundIn<false>(a, sLo[r], sHi[r], key);
+				if (staged)
+				{
+					const uint32_t w = sHi[r] - sLo[r];
+					pos += sLo[r] + (r < run ? boundIn<true>(sWin + sOff[r], 0, w, key) : boundIn<false>(sWin + sOff[r], 0, w, key));
+				}
+				else
+				{
+					const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
+					pos += r < run ? boundIn<true>(a, sLo[r], sHi[r], key) : boundIn<false>(a, sLo[r], sHi[r], key);
+				}
 			}
 			const uint32_t o = outBase + (pos - sliceStart);
 			A.outKeys[o] = key;
@@ -283,9 +237,9 @@ uint32_t launchMerge(cudaStream_t stream, const MergeArgs& A, uint32_t maxRunLen
 	kMergeBounds<<<A.lists, 32 * A.ranks, 0, stream>>>(A);
 	const uint32_t blocks = std::max(1u, std::min((maxRunLength / A.ranks + kMergeChunk - 1u) / kMergeChunk + 1u, 148u * 8u / std::max(1u, A.ranks)));
 	if (A.ranks <= 3)
-		kMergeSlice<<<dim3(blocks, A.ranks, A.lists), 256, 0, stream>>>(A);
+		kMergeSlice<false><<<dim3(blocks, A.ranks, A.lists), kMergeThreads, 0, stream>>>(A);
 	else
-		kMergeSliceWide<<<dim3(blocks, A.ranks, A.lists), kMergeThreads, 0, stream>>>(A);
+		kMergeSlice<true><<<dim3(blocks, A.ranks, A.lists), kMergeThreads, 0, stream>>>(A);
 	return 2;
 }
 

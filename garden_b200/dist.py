@@ -212,10 +212,10 @@ class PipelinedRunMerger:
         """Enqueues one frame: scene preparation, export, all-gather, merge. Returns the buffer set that will hold the result."""
         torch, dist, sp = self.torch, self.dist, self.sp
         s = self.sets[self.frame_index & 1]
-        sp.run_async()
         if s["used"]:
             self.compute.wait_event(s["done"])  # the exchange that last read this set's block has finished
         timing = self.timing
+        sp.run_async()
         if timing is not None:
             t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             t[0].record(self.compute)

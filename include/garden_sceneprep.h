@@ -187,6 +187,11 @@ int gsp_emit_instances(gsp_context* ctx, uint32_t view, int listKind, uint32_t b
 	uint32_t stride, uint32_t mvpOffset, uint32_t capacity);
 int gsp_emit_instances_device(gsp_context* ctx, uint32_t view, int listKind, uint32_t buffer, const float* viewProj,
 	void* dInstances, uint32_t stride, uint32_t mvpOffset, uint32_t capacity);
+/* View setup helpers (host code, no context): Frustum(viewProj) (libraries/math/include/math/frustum.hpp:51-61) — the six
+ * unnormalised planes [6][4] of a column-major view-projection matrix, Vulkan Y flip included — and a gsp_view filled from a
+ * viewProj the way the callers of prepareMeshes build their arguments (mesh.cpp:815,869,902; no UI frustum). */
+void gsp_frustum_planes(const float* viewProj, float* planes);
+int gsp_view_from_viewproj(const float* viewProj, const float* cameraOffset, int32_t shadowPass, gsp_view* view);
 /* TransformComponent::setActive(active) (source/system/transform.cpp:75-127) for `count` entities (1-based ECS ids) on the
  * staged hierarchy: selfActive is set, ancestorsActive is re-derived for every transform (AND of its ancestors' selfActive,
  * the invariant every setActive call maintains), and the next gsp_run filters on the new isActive() values.

@@ -15,3 +15,31 @@ def test_library_exports_every_declared_symbol(sceneprep_lib):
         assert hasattr(lib, name), f"{name} is declared in include/garden_sceneprep.h but not exported"
     assert declared == set(SYMBOLS), f"binding and header disagree: {declared ^ set(SYMBOLS)}"
     assert b"sm_100a" in lib.gsp_version()
+
+
+def test_view_setup_helpers_match_oracle(sceneprep_lib, oracle_built):
+    """gsp_frustum_planes / gsp_view_from_viewproj (host code in the product library, no device needed) against the oracle's
+    Frustum(viewProj) restatement, which tests/test_oracle_vs_ref.py pins against the reference's math library."""
+    import numpy as np
+    import reflib
+    from garden_b200 import views as V
+    from garden_b200.binding import load_library
+    from garden_b200.layout import VIEW_DTYPE
+    lib = load_library()
+    o = reflib.Oracle()
+    views, vps = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    rng = np.random.default_rng(2)
+    mats = [np.asarray(vp, dtype=np.float32).reshape(16) for vp in vps] + [rng.standard_normal(16).astype(np.float32) * 7 for _ in range(50)]
+    for i, m in enumerate(mats):
+        got = np.zeros((6, 4), np.float32)
+        lib.gsp_frustum_planes(m.ctypes.data, got.ctypes.data)
+        want = o.frustum_planes(m)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"matrix {i}"
+    # the filled gsp_view equals what the Python view builder packs for the same matrix
+    for v in range(views.size):
+        out = np.zeros(1, dtype=VIEW_DTYPE)
+        off = np.ascontiguousarray(views[v]["cameraOffset"], dtype=np.float32)
+        assert lib.gsp_view_from_viewproj(mats[v].ctypes.data, off.ctypes.data, int(views[v]["shadowPass"]), out.ctypes.data) == 0
+        assert out[0]["planeCount"] == 6 and out[0]["uiPlaneCount"] == 0 and out[0]["shadowPass"] == views[v]["shadowPass"]
+        assert np.array_equal(out[0]["cameraOffset"], off)
+        assert np.array_equal(out[0]["planes"].view(np.uint32), o.frustum_planes(mats[v]).view(np.uint32))

@@ -117,7 +117,7 @@ def _shards(whole, ranks, chains, depth):
     return out, starts
 
 
-@pytest.mark.parametrize("ranks", [2, 4])
+@pytest.mark.parametrize("ranks", [2, 4, 8])
 def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks):
     """The host-synchronisation-free exchange (gsp_export_runs_packed -> [all-gather] -> gsp_merge_gathered_packed):
     blocks are exported right after gsp_run_async (no gsp_sync), laid out as the all-gather would, merged per rank, and
