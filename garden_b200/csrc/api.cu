@@ -347,7 +347,7 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		GSP_CUDA(cudaMalloc((void**)&p.tslot, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&p.flags, (size_t)cap));
 		GSP_CUDA(cudaMalloc((void**)&p.ready, (size_t)cap));
-		GSP_CUDA(cudaMalloc((void**)&p.world, (size_t)cap * 3 * sizeof(float4)));
+		GSP_CUDA(cudaMalloc((void**)&p.world, (size_t)cap * kWorldStride * sizeof(float4)));
 		GSP_CUDA(cudaMalloc((void**)&p.visible, (size_t)cap));
 		p.cullTilesCap = (cap + kCullTile - 1) / kCullTile;
 		GSP_CUDA(cudaMalloc((void**)&p.cullStatus, (size_t)p.cullTilesCap * kMaxViews * sizeof(uint32_t)));
@@ -1193,7 +1193,8 @@ int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out)
 	if (p.occupancy == 0)
 		return GSP_OK;
 	GSP_CUDA(cudaSetDevice(c.device));
-	GSP_CUDA(cudaMemcpyAsync(out, p.world, (size_t)p.occupancy * 12 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaMemcpy2DAsync(out, 12 * sizeof(float), p.world, kWorldStride * sizeof(float4), 12 * sizeof(float), p.occupancy,
+		cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
 	return GSP_OK;
 }

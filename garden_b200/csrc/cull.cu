@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		}
 		if (mask) // bakedModel = (float4x3)model (mesh.cpp:171,249)
 		{
-			float4* w = A.world + (size_t)wslot * 3;
+			float4* w = A.world + (size_t)wslot * kWorldStride;
 			w[0] = make_float4(M.c[0][0], M.c[0][1], M.c[0][2], M.c[1][0]);
 			w[1] = make_float4(M.c[1][1], M.c[1][2], M.c[2][0], M.c[2][1]);
 			w[2] = make_float4(M.c[2][2], M.c[3][0], M.c[3][1], M.c[3][2]);
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constan
 			{
 				const uint32_t j = j0 + 32 * b;
 				slot[b] = chunk * (kChunkWords * 32) + (j < total ? sList[warp][j] : sList[warp][j0]);
-				w2[b] = A.world[(size_t)slot[b] * 3 + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
+				w2[b] = A.world[(size_t)slot[b] * kWorldStride + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
 			}
 			#pragma unroll
 			for (uint32_t b = 0; b < kGatherBatch; b++)

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kEmitThreads) kEmit(const __grid_constant__ Em
 			const uint32_t pool = payload[r] >> 28, slot = payload[r] & 0x0FFFFFFFu;
 			w[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (j < count && q < 3)
-				w[r] = A.world[pool][(size_t)slot * 3 + q];
+				w[r] = A.world[pool][(size_t)slot * kWorldStride + q];
 		}
 		#pragma unroll
 		for (uint32_t r = 0; r < kEmitUnroll; r++)

@@ -72,9 +72,10 @@ __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* sWa
 	return offset + inc - v;
 }
 
+constexpr uint32_t kSortBlocksPerSM = kSortItems >= 16 ? 3 : 5; // resident blocks the pass is sized for
 constexpr uint32_t kLookbackBatch = 8; // predecessor tiles inspected per step (independent loads in flight)
 
-__global__ void __launch_bounds__(kSortThreads, 3) kSortPass(const __grid_constant__ SortArgs A, uint32_t pass, uint32_t epoch,
+__global__ void __launch_bounds__(kSortThreads, kSortBlocksPerSM) kSortPass(const __grid_constant__ SortArgs A, uint32_t pass, uint32_t epoch,
 	const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ payIn,
 	uint32_t* __restrict__ keysOut, uint32_t* __restrict__ payOut)
 {
@@ -272,7 +273,7 @@ uint32_t launchSort(Context& c, cudaEvent_t afterHistogram)
 	A.tickets = c.sortTickets; A.segTileOffset = c.segTileOffset; A.epoch = 0;
 	A.segmentCountTotal = nseg;
 	// sort passes are persistent (tiles claimed by ticket): 3 resident blocks per SM, split over the segments
-	dim3 passGrid(std::min<uint32_t>(totalCapTiles, 148u * 3u));
+	dim3 passGrid(std::min<uint32_t>(totalCapTiles, 148u * kSortBlocksPerSM));
 	uint32_t launches = 0;
 	for (uint32_t pass = 0; pass < kPasses; pass++)
 	{
