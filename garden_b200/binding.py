@@ -29,6 +29,7 @@ SYMBOLS = {
     "gsp_set_stream": (_i32, [_vp, _vp]),
     "gsp_set_transforms": (_i32, [_vp, _vp, _u32, _u32]),
     "gsp_update_transforms": (_i32, [_vp, _vp, _u32, _u32, _u32]),
+    "gsp_update_transforms_indexed": (_i32, [_vp, _vp, _u32, _vp, _u32]),
     "gsp_set_pool_count": (_i32, [_vp, _u32]),
     "gsp_set_mesh_pool": (_i32, [_vp, _u32, _u32, _u32, _vp, _u32, _u32, _u32, _vp]),
     "gsp_set_views": (_i32, [_vp, _u32, _vp, _vp]),
@@ -154,6 +155,10 @@ class ScenePrep:
 
     def update_transforms(self, aos, stride: int, first: int, count: int):
         self._check(self.lib.gsp_update_transforms(self.h, _ptr(aos), stride, first, count))
+
+    def update_transforms_indexed(self, aos, stride: int, slots):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        self._check(self.lib.gsp_update_transforms_indexed(self.h, _ptr(aos), stride, slots.ctypes.data, slots.size))
 
     def set_pool_count(self, n: int):
         self._check(self.lib.gsp_set_pool_count(self.h, n))

@@ -28,6 +28,7 @@ static std::string gCreateError;
 	} while (0)
 
 extern "C" { static int fetchWait(Context& c); }
+template<class F> static void parallelFor(uint32_t n, F fn);
 
 static int fail(Context& c, int code, const char* message)
 {
@@ -138,7 +139,7 @@ void gsp_destroy(gsp_context* ctx)
 	cudaFree(c.dSegments); cudaFree(c.keys[0]); cudaFree(c.keys[1]); cudaFree(c.payloads[0]); cudaFree(c.payloads[1]);
 	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortHist); cudaFree(c.sortStatus); cudaFree(c.sortTickets);
 	cudaFree(c.segTileOffset); cudaFree(c.dAosScratch);
-	cudaFreeHost(c.hCounters); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible); cudaFree(c.dVisScratch);
+	cudaFreeHost(c.hCounters); cudaFreeHost(c.hGather); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible); cudaFree(c.dVisScratch);
 	if (c.phaseEventsCreated)
 	{
 		for (auto& e : c.phaseEvents)
@@ -301,6 +302,50 @@ int gsp_update_transforms(gsp_context* ctx, const void* aos, uint32_t stride, ui
 	if (rc) return rc;
 	launchStageTransforms(c, src, stride, first, count, false, nullptr);
 	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the scratch buffer and the caller's memory are free again
+	GSP_CUDA(cudaGetLastError());
+	c.resultsValid = false; c.frameEnqueued = false;
+	return GSP_OK;
+}
+
+int gsp_update_transforms_indexed(gsp_context* ctx, const void* aos, uint32_t stride, const uint32_t* slots, uint32_t count)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (((!aos || !slots) && count) || stride < kTfMinStride || (stride & 3))
+		return fail(c, GSP_ERR_INVALID, "gsp_update_transforms_indexed: bad pointer or stride");
+	if (count == 0)
+		return GSP_OK;
+	for (uint32_t i = 0; i < count; i++)
+		if (slots[i] >= c.tf.occupancy)
+			return fail(c, GSP_ERR_INVALID, "gsp_update_transforms_indexed: slot index out of range");
+	GSP_CUDA(cudaSetDevice(c.device));
+	// the dirty components are packed back to back behind their slot list in pinned memory and travel as ONE copy
+	const size_t listBytes = ((size_t)count * sizeof(uint32_t) + 15) & ~(size_t)15;
+	const size_t bytes = listBytes + (size_t)count * stride;
+	if (c.hGatherCap < bytes)
+	{
+		GSP_CUDA(cudaStreamSynchronize(c.stream));
+		cudaFreeHost(c.hGather); c.hGather = nullptr; c.hGatherCap = 0;
+		const size_t cap = bytes + bytes / 2;
+		GSP_CUDA(cudaMallocHost((void**)&c.hGather, cap));
+		c.hGatherCap = cap;
+	}
+	memcpy(c.hGather, slots, (size_t)count * sizeof(uint32_t));
+	const uint8_t* src = (const uint8_t*)aos;
+	uint8_t* packed = c.hGather + listBytes;
+	parallelFor(count, [=](uint32_t first, uint32_t last)
+	{
+		for (uint32_t i = first; i < last; i++)
+			memcpy(packed + (size_t)i * stride, src + (size_t)slots[i] * stride, stride);
+	});
+	size_t cap = c.dAosScratchCap;
+	uint8_t* ptr = (uint8_t*)c.dAosScratch;
+	GSP_CUDA(ensureDevice(ptr, cap, bytes, false, c.stream));
+	c.dAosScratch = ptr; c.dAosScratchCap = cap;
+	GSP_CUDA(cudaMemcpyAsync(c.dAosScratch, c.hGather, bytes, cudaMemcpyHostToDevice, c.stream));
+	launchStageTransforms(c, (const uint8_t*)c.dAosScratch + listBytes, stride, 0, count, false, nullptr, (const uint32_t*)c.dAosScratch);
+	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the pinned gather buffer is free again
 	GSP_CUDA(cudaGetLastError());
 	c.resultsValid = false; c.frameEnqueued = false;
 	return GSP_OK;

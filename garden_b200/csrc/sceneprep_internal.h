@@ -161,6 +161,7 @@ struct Context
 
 	// host staging
 	void* dAosScratch = nullptr; size_t dAosScratchCap = 0;
+	uint8_t* hGather = nullptr; size_t hGatherCap = 0; // pinned: scattered dirty components packed for one upload
 	uint64_t zeroCopyBytes = 0; // bytes the staging kernels read straight from pinned host memory
 	gsp_record* hRecords = nullptr; size_t hRecordsCap = 0; // pinned download area (arena-shaped)
 	std::vector<uint8_t> segDownloaded;
@@ -195,7 +196,7 @@ constexpr uint32_t kExMagic = 0x47535031u; // "GSP1"
 
 // ---- kernel launchers (each returns the number of kernels it launched, or throws nothing; errors via cudaGetLastError) ----
 uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full,
-	uint32_t* dMaxEntity);
+	uint32_t* dMaxEntity, const uint32_t* dSlotMap = nullptr);
 uint32_t launchBuildHierarchy(Context& c);
 uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy);
 uint32_t launchLink(Context& c);

@@ -69,7 +69,7 @@ __device__ __forceinline__ void loadTile(uint8_t* sTile, const uint8_t* __restri
 __global__ void __launch_bounds__(kStageThreads) kStageTransforms(const uint8_t* __restrict__ aos, uint32_t stride,
 	uint32_t first, uint32_t count, int full, uint32_t tileSlots, float4* __restrict__ rot, float4* __restrict__ posSx,
 	float2* __restrict__ sYZ, uint16_t* __restrict__ flags, uint32_t* __restrict__ entity,
-	uint32_t* __restrict__ parentEntity, uint32_t* __restrict__ maxEntity)
+	uint32_t* __restrict__ parentEntity, uint32_t* __restrict__ maxEntity, const uint32_t* __restrict__ slotMap)
 {
 	extern __shared__ __align__(16) uint8_t sTile[];
 	const uint32_t tileFirst = blockIdx.x * tileSlots;
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kStageThreads) kStageTransforms(const uint8_t*
 	uint32_t emax = 0;
 	for (uint32_t j = threadIdx.x; j < n; j += kStageThreads)
 	{
-		const uint32_t slot = first + tileFirst + j;
+		// slotMap: the j-th staged component belongs to slot slotMap[j] (scattered dirty set), else to first + j (a range)
+		const uint32_t slot = slotMap ? slotMap[tileFirst + j] : first + tileFirst + j;
 		const uint8_t* t = sTile + (size_t)j * stride;
 		const uint32_t e = ldU32(t + kTfEntity);
 		const float4 q = make_float4(ldF32(t + kTfRot), ldF32(t + kTfRot + 4), ldF32(t + kTfRot + 8), ldF32(t + kTfRot + 12));
@@ -215,7 +216,7 @@ static uint32_t tileSlotsFor(uint32_t stride, size_t& smemBytes)
 }
 
 uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, uint32_t first, uint32_t count, bool full,
-	uint32_t* dMaxEntity)
+	uint32_t* dMaxEntity, const uint32_t* dSlotMap)
 {
 	if (count == 0)
 		return 0;
@@ -224,7 +225,7 @@ uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, ui
 	const uint32_t tileSlots = tileSlotsFor(stride, smem);
 	cudaFuncSetAttribute(kStageTransforms, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	kStageTransforms<<<blocksFor(count, tileSlots), kStageThreads, smem, c.stream>>>((const uint8_t*)dAos, stride, first, count,
-		full ? 1 : 0, tileSlots, t.rot, t.posSx, t.sYZ, t.flags, t.entity, t.parentEntity, dMaxEntity);
+		full ? 1 : 0, tileSlots, t.rot, t.posSx, t.sYZ, t.flags, t.entity, t.parentEntity, dMaxEntity, dSlotMap);
 	return 1;
 }
 

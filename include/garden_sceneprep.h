@@ -92,6 +92,9 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
  * (entity and parent fields) must be unchanged since the last gsp_set_transforms. The ECS has no dirty tracking
  * (transform.hpp:74-104 are plain stores), so the range comes from the caller. */
 int gsp_update_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint32_t first, uint32_t count);
+/* Same for a SCATTERED dirty set (e.g. the animated tenth of configuration C3): `slots[count]` are transform-pool slot
+ * indices, `aos` is the pool base. Only those components travel (packed into one pinned upload by the library). */
+int gsp_update_transforms_indexed(gsp_context* ctx, const void* aos, uint32_t stride, const uint32_t* slots, uint32_t count);
 /* Declares how many mesh systems the frame has (meshSystems.size() after prepareSystems, mesh.cpp:69-108). */
 int gsp_set_pool_count(gsp_context* ctx, uint32_t poolCount);
 /* Replaces reading IMeshRenderSystem::{getMeshRenderType,getMeshComponentPool,getMeshComponentSize,isDrawReady}

@@ -122,6 +122,34 @@ def test_dirty_range_updates_and_view_changes(oracle_built, sceneprep_lib):
     sp.close()
 
 
+def test_indexed_updates_match_full_restage(oracle_built, sceneprep_lib):
+    """C3's animated tenth as a SCATTERED dirty set (gsp_update_transforms_indexed): only the listed components travel; the
+    frame equals the oracle on the fully updated pool. Also: duplicates in the list, an out-of-range slot."""
+    from garden_b200.binding import ScenePrep, ScenePrepError
+    scene = scenes.config_scene("C3", n=60_000)
+    t, pools = aos_inputs(scene, strides=[64, 48])
+    rts = [p.render_type for p in scene.pools]
+    sp = ScenePrep(0)
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(len(pools))
+    for k, m in enumerate(pools):
+        sp.set_mesh_pool(k, rts[k], m, m.dtype.itemsize, m.size)
+    for frame in range(3):
+        sel, p, r, s = scenes.animate_trs(scene, frame, 41)
+        t["position"][sel] = p; t["rotation"][sel] = r; t["scale"][sel] = s
+        slots = sel if frame != 1 else np.concatenate([sel, sel[:100]])  # (entity index == transform slot in this scene)
+        sp.update_transforms_indexed(t, t.dtype.itemsize, slots)
+        cam = np.array([1.0 + frame, 0.5, -2.0 * frame], np.float32)
+        views, _ = V.perspective_views([(0.2 + 0.4 * frame, 0.0)], 1.3, 16 / 9, 0.01)
+        sp.set_views(views, cam)
+        sp.run()
+        orun = OracleRun((t, t.dtype.itemsize, t.size), [(m, m.dtype.itemsize, m.size) for m in pools], rts, views, cam)
+        compare_gpu_to_oracle(sp, orun, rts, views, f"indexed frame {frame}")
+    with pytest.raises(ScenePrepError):
+        sp.update_transforms_indexed(t, t.dtype.itemsize, np.array([t.size], np.uint32))
+    sp.close()
+
+
 def test_world_matrices_within_2ulp(oracle_built, sceneprep_lib):
     """north_star: world matrices within 2 ulp of the reference's calcModel — they are in fact bit-identical."""
     import reflib
