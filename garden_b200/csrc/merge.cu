@@ -126,8 +126,7 @@ __global__ void __launch_bounds__(1024) kMergeBounds(const __grid_constant__ Mer
 // into shared memory with coalesced loads, and every element ranks itself in every window by a binary search in SHARED
 // memory (a scattered global search costs one L1 wavefront per lane, a shared one roughly one per warp). A chunk whose
 // windows do not fit (very uneven key densities between ranks) searches the brackets in global memory instead.
-constexpr uint32_t kMergeThreads = 256, kMergeItems = 4, kMergeChunk = kMergeThreads * kMergeItems;
-constexpr uint32_t kMergeWindow = 16384; // window keys staged per chunk (64 KB of dynamic shared memory; avg need: ranks x chunk)
+constexpr uint32_t kMergeThreads = 256, kMergeChunk = 1024, kMergeWindow = 10240; // window keys staged per chunk (40 KB)
 template<bool kUpper> // kUpper: count elements <= key (ties go to the other run), else elements < key
 __device__ __forceinline__ uint32_t boundIn(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t key)
 {
@@ -165,7 +164,7 @@ template<bool kStage>
 __global__ void __launch_bounds__(kMergeThreads) kMergeSlice(const __grid_constant__ MergeArgs A)
 {
 	__shared__ uint32_t sLo[32], sHi[32], sOff[33];
-	extern __shared__ uint32_t sWin[]; // kMergeWindow keys when kStage
+	__shared__ uint32_t sWin[kStage ? kMergeWindow : 1];
 	const uint32_t list = blockIdx.z, run = blockIdx.y;
 	const uint32_t lo = A.bounds[(list * A.ranks + run) * 2 + 0], hi = A.bounds[(list * A.ranks + run) * 2 + 1];
 	const uint32_t sliceStart = A.sliceInfo[list * 2 + 0];
@@ -204,80 +203,29 @@ __global__ void __launch_bounds__(kMergeThreads) kMergeSlice(const __grid_consta
 			}
 			__syncthreads();
 		}
-		if (staged)
+		for (uint32_t i = i0 + threadIdx.x; i < i1; i += kMergeThreads)
 		{
-			// kMergeItems CONSECUTIVE elements per thread: one binary search per window for the first, then short advances
-			// (a window is about as dense as the chunk), a fresh binary search when an advance gets long
-			const uint32_t first = i0 + threadIdx.x * kMergeItems;
-			if (first < i1)
+			const uint32_t key = myKeys[i];
+			uint32_t pos = i;
+			for (uint32_t r = 0; r < A.ranks; r++)
 			{
-				const uint32_t count = min(kMergeItems, i1 - first);
-				uint32_t key[kMergeItems], pos[kMergeItems];
-				#pragma unroll
-				for (uint32_t e = 0; e < kMergeItems; e++)
+				if (r == run)
+					continue;
+				if (staged)
 				{
-					key[e] = e < count ? myKeys[first + e] : 0xFFFFFFFFu;
-					pos[e] = first + e;
+					const uint32_t w = sHi[r] - sLo[r];
+					pos += sLo[r] + (r < run ? boundIn<true>(sWin + sOff[r], 0, w, key) : boundIn<false>(sWin + sOff[r], 0, w, key));
 				}
-				for (uint32_t r = 0; r < A.ranks; r++)
+				else
 				{
-					if (r == run)
-						continue;
-					const uint32_t* win = sWin + sOff[r];
-					const uint32_t w = sHi[r] - sLo[r], base = sLo[r];
-					const bool upper = r < run;
-					uint32_t p = upper ? boundIn<true>(win, 0, w, key[0]) : boundIn<false>(win, 0, w, key[0]);
-					pos[0] += base + p;
-					#pragma unroll
-					for (uint32_t e = 1; e < kMergeItems; e++)
-					{
-						if (e < count)
-						{
-							uint32_t steps = 0;
-							while (p < w && steps < 6)
-							{
-								const uint32_t v = win[p];
-								if (!(upper ? v <= key[e] : v < key[e]))
-									break;
-								p++; steps++;
-							}
-							if (steps == 6)
-								p = upper ? boundIn<true>(win, p, w, key[e]) : boundIn<false>(win, p, w, key[e]);
-							pos[e] += base + p;
-						}
-					}
-				}
-				#pragma unroll
-				for (uint32_t e = 0; e < kMergeItems; e++)
-				{
-					if (e < count)
-					{
-						const uint32_t o = outBase + (pos[e] - sliceStart);
-						A.outKeys[o] = key[e];
-						A.outPayloads[o] = myPays[first + e];
-						A.outRanks[o] = (uint8_t)run;
-					}
-				}
-			}
-		}
-		else
-		{
-			for (uint32_t i = i0 + threadIdx.x; i < i1; i += kMergeThreads)
-			{
-				const uint32_t key = myKeys[i];
-				uint32_t pos = i;
-				for (uint32_t r = 0; r < A.ranks; r++)
-				{
-					if (r == run)
-						continue;
 					const uint32_t* a = A.keys + (size_t)r * A.rankStride + A.offsets[r * A.lists + list];
 					pos += r < run ? boundIn<true>(a, sLo[r], sHi[r], key) : boundIn<false>(a, sLo[r], sHi[r], key);
 				}
-				const uint32_t o = outBase + (pos - sliceStart);
-				A.outKeys[o] = key;
-				A.outPayloads[o] = myPays[i];
-				A.outRanks[o] = (uint8_t)run;
 			}
+			const uint32_t o = outBase + (pos - sliceStart);
+			A.outKeys[o] = key;
+			A.outPayloads[o] = myPays[i];
+			A.outRanks[o] = (uint8_t)run;
 		}
 	}
 }
@@ -291,15 +239,7 @@ uint32_t launchMerge(cudaStream_t stream, const MergeArgs& A, uint32_t maxRunLen
 	if (A.ranks <= 3)
 		kMergeSlice<false><<<dim3(blocks, A.ranks, A.lists), kMergeThreads, 0, stream>>>(A);
 	else
-	{
-		static bool attrSet = false;
-		if (!attrSet)
-		{
-			cudaFuncSetAttribute(kMergeSlice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeWindow * sizeof(uint32_t));
-			attrSet = true;
-		}
-		kMergeSlice<true><<<dim3(blocks, A.ranks, A.lists), kMergeThreads, kMergeWindow * sizeof(uint32_t), stream>>>(A);
-	}
+		kMergeSlice<true><<<dim3(blocks, A.ranks, A.lists), kMergeThreads, 0, stream>>>(A);
 	return 2;
 }
 
