@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* sWa
 }
 
 constexpr uint32_t kSortBlocksPerSM = kSortItems >= 16 ? 3 : 5; // resident blocks the pass is sized for
-constexpr uint32_t kLookbackBatch = 8; // predecessor tiles inspected per step (independent loads in flight)
+constexpr uint32_t kLookbackBatch = 4; // predecessor tiles inspected per step (independent loads in flight; 16 measured slower, 8 / 4 / 2 within 2 %)
 
 __global__ void __launch_bounds__(kSortThreads, kSortBlocksPerSM) kSortPass(const __grid_constant__ SortArgs A, uint32_t pass, uint32_t epoch,
 	const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ payIn,
