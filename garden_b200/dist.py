@@ -30,6 +30,55 @@ def plan_gather(counts: np.ndarray):
     return offsets.astype(np.uint32), rank_stride, out_offsets.astype(np.uint32), totals.astype(np.uint32)
 
 
+# ---- the packed exchange block (garden_b200/csrc/merge.cu: kExportPacked / kMergePlan), stated in numpy -----------------
+EX_HEADER_WORDS, EX_HEADER_FIXED, EX_MAGIC = 256, 8, 0x47535031
+
+
+def pack_block(list_keys, list_payloads, capacity: int) -> np.ndarray:
+    """What kExportPacked writes for one rank: header {magic, lists, total, capacity, overflow, 0, 0, 0, count[lists]} |
+    keys[capacity] | payloads[capacity]. An overflowing rank (total > capacity) carries zero counts and no elements."""
+    lists = len(list_keys)
+    assert lists <= EX_HEADER_WORDS - EX_HEADER_FIXED
+    block = np.zeros(EX_HEADER_WORDS + 2 * capacity, dtype=np.uint32)
+    counts = np.array([len(k) for k in list_keys], dtype=np.int64)
+    total = int(counts.sum())
+    overflow = total > capacity
+    block[0:5] = [EX_MAGIC, lists, total, capacity, 1 if overflow else 0]
+    if not overflow:
+        block[EX_HEADER_FIXED:EX_HEADER_FIXED + lists] = counts
+        if total:
+            block[EX_HEADER_WORDS:EX_HEADER_WORDS + total] = np.concatenate(list_keys)
+            block[EX_HEADER_WORDS + capacity:EX_HEADER_WORDS + capacity + total] = np.concatenate(list_payloads)
+    return block
+
+
+def plan_from_blocks(gathered: np.ndarray, ranks: int, lists: int, capacity: int, out_capacity: int):
+    """What kMergePlan derives from the gathered blocks: (offsets [ranks, lists], counts [ranks, lists], out_offsets [lists],
+    flags [8]) with flags = {error bits (1 overflow, 2 bad header, 4 merged lists exceed out_capacity), merged total,
+    largest per-rank total, 0...}. With a non-zero error word every count is zero (nothing may be merged)."""
+    words = EX_HEADER_WORDS + 2 * capacity
+    hdr = np.asarray(gathered, dtype=np.uint32).reshape(ranks, words)[:, :EX_HEADER_WORDS]
+    error = 0
+    for r in range(ranks):
+        if hdr[r, 0] != EX_MAGIC or hdr[r, 1] != lists:
+            error |= 2
+        if hdr[r, 4]:
+            error |= 1
+    counts = np.zeros((ranks, lists), dtype=np.int64) if error else hdr[:, EX_HEADER_FIXED:EX_HEADER_FIXED + lists].astype(np.int64)
+    offsets = np.zeros_like(counts)
+    offsets[:, 1:] = np.cumsum(counts, axis=1)[:, :-1]
+    totals = counts.sum(axis=0)
+    out_offsets = np.zeros(lists, dtype=np.int64)
+    out_offsets[1:] = np.cumsum(totals)[:-1]
+    merged = int(totals.sum())
+    if merged > out_capacity:
+        error |= 4
+        counts = np.zeros_like(counts)
+    flags = np.zeros(8, dtype=np.int64)
+    flags[0], flags[1], flags[2] = error, merged, int(hdr[:, 2].max())
+    return offsets, counts, out_offsets, flags
+
+
 def merge_reference(runs_keys, runs_payloads, my_rank: int | None = None):
     """numpy statement of the merge for ONE list: runs_* are per-rank arrays (sorted by key, ties by payload).
     Returns (keys, payloads, ranks) of the full merged list, or of rank `my_rank`'s key-range slice plus its start."""

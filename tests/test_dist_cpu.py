@@ -5,7 +5,8 @@ import socket
 import numpy as np
 import pytest
 
-from garden_b200.dist import exchange_counts, merge_reference, plan_gather
+from garden_b200.dist import (EX_HEADER_FIXED, EX_HEADER_WORDS, exchange_counts, merge_reference, pack_block, plan_from_blocks,
+                              plan_gather)
 
 
 def _runs(rng, ranks, n_max, key_bits=10):
@@ -79,3 +80,80 @@ def test_exchange_counts_gloo_world2(tmp_path):
     assert a[:6].tolist() == [10, 0, 7, 20, 1, 7]
     assert a[12] == 28  # rank stride = longest packed block
     assert a[13:].tolist() == [30, 1, 14]
+
+
+def _lists_for_rank(rank, lists=3):
+    rng = np.random.default_rng(100 + rank)
+    keys, pays = _runs(rng, lists, 300, key_bits=10)  # one sorted run per LIST of this rank
+    return keys, pays
+
+
+def _gloo_block_worker(rank, world, port, out_dir, capacity):
+    """The packed exchange over gloo: every rank packs its lists into one fixed-capacity block, ONE all-gather of equal
+    blocks, every rank plans the merge from the gathered headers and merges its key range of every list."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    keys, pays = _lists_for_rank(rank)
+    block = pack_block(keys, pays, capacity)
+    mine = torch.from_numpy(block.view(np.int32))
+    gathered = torch.empty(world * mine.numel(), dtype=torch.int32)
+    dist.all_gather_into_tensor(gathered, mine)
+    g = gathered.numpy().view(np.uint32)
+    lists = len(keys)
+    offsets, counts, out_offsets, flags = plan_from_blocks(g, world, lists, capacity, out_capacity=capacity * world)
+    words = EX_HEADER_WORDS + 2 * capacity
+    out = {"flags": flags, "counts": counts, "out_offsets": out_offsets}
+    if flags[0] == 0:
+        for l in range(lists):
+            rk = [g[r * words + EX_HEADER_WORDS + offsets[r, l]: r * words + EX_HEADER_WORDS + offsets[r, l] + counts[r, l]] for r in range(world)]
+            rp = [g[r * words + EX_HEADER_WORDS + capacity + offsets[r, l]: r * words + EX_HEADER_WORDS + capacity + offsets[r, l] + counts[r, l]]
+                  for r in range(world)]
+            k, p, s, start = merge_reference(rk, rp, my_rank=rank)
+            out[f"k{l}"], out[f"p{l}"], out[f"s{l}"], out[f"start{l}"] = k, p, s, np.array([start])
+    np.savez(os.path.join(out_dir, f"b{rank}.npz"), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_block_exchange_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    world, lists = 2, 3
+    per_rank = [_lists_for_rank(r, lists) for r in range(world)]
+    need = max(sum(len(k) for k in keys) for keys, _ in per_rank)
+    mp.spawn(_gloo_block_worker, args=(world, _free_port(), str(tmp_path), need + 7), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"b{r}.npz") for r in range(world)]
+    for r in range(world):
+        assert res[r]["flags"][0] == 0 and res[r]["flags"][2] == need
+        assert np.array_equal(res[r]["counts"], [[len(k) for k in keys] for keys, _ in per_rank])
+    for l in range(lists):
+        full_k, full_p, full_r = merge_reference([per_rank[r][0][l] for r in range(world)], [per_rank[r][1][l] for r in range(world)])
+        pos = 0
+        for r in range(world):  # the ranks' slices tile the full merge of the list, in rank order
+            assert int(res[r][f"start{l}"][0]) == pos
+            n = res[r][f"k{l}"].size
+            assert np.array_equal(res[r][f"k{l}"], full_k[pos:pos + n]) and np.array_equal(res[r][f"p{l}"], full_p[pos:pos + n])
+            assert np.array_equal(res[r][f"s{l}"], full_r[pos:pos + n])
+            pos += n
+        assert pos == full_k.size
+    # overflow protocol: a capacity one rank cannot meet is flagged by every rank, nothing is planned, the need is reported
+    mp.spawn(_gloo_block_worker, args=(world, _free_port(), str(tmp_path), need - 1), nprocs=world, join=True)
+    for r in range(world):
+        z = np.load(tmp_path / f"b{r}.npz")
+        assert z["flags"][0] & 1 and z["flags"][2] == need and not z["counts"].any()
+
+
+def test_plan_from_blocks_flags():
+    cap = 16
+    a = pack_block([np.arange(3, dtype=np.uint32), np.arange(2, dtype=np.uint32)], [np.arange(3, dtype=np.uint32), np.arange(2, dtype=np.uint32)], cap)
+    b = pack_block([np.arange(5, dtype=np.uint32), np.zeros(0, np.uint32)], [np.arange(5, dtype=np.uint32), np.zeros(0, np.uint32)], cap)
+    g = np.concatenate([a, b])
+    offsets, counts, out_offsets, flags = plan_from_blocks(g, 2, 2, cap, out_capacity=32)
+    assert counts.tolist() == [[3, 2], [5, 0]] and offsets.tolist() == [[0, 3], [0, 5]] and out_offsets.tolist() == [0, 8]
+    assert flags[:3].tolist() == [0, 10, 5]
+    assert plan_from_blocks(g, 2, 2, cap, out_capacity=9)[3][0] == 4 and not plan_from_blocks(g, 2, 2, cap, out_capacity=9)[1].any()
+    bad = g.copy(); bad[0] = 1
+    assert plan_from_blocks(bad, 2, 2, cap, out_capacity=32)[3][0] == 2
+    assert plan_from_blocks(g, 2, 3, cap, out_capacity=32)[3][0] == 2  # list count mismatch

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from garden_b200 import scenes, views as V
-from garden_b200.dist import merge_reference, plan_gather
+from garden_b200.dist import merge_reference, plan_from_blocks, plan_gather
 
 pytestmark = pytest.mark.gpu
 
@@ -171,6 +171,10 @@ def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks):
         pl = plan.cpu().numpy().view(np.uint32)
         assert pl[-8] == 0 and pl[-7] == total and pl[-6] == all_counts.sum(axis=1).max()
         assert np.array_equal(pl[2 * ranks * lists: 2 * ranks * lists + lists], out_offsets)
+        # the device plan equals the numpy statement of kMergePlan (which the gloo CPU test exercises)
+        e_off, e_cnt, e_out, e_flags = plan_from_blocks(gathered.cpu().numpy().view(np.uint32), ranks, lists, cap, total)
+        assert np.array_equal(pl[:ranks * lists].reshape(ranks, lists), e_off) and np.array_equal(pl[ranks * lists:2 * ranks * lists].reshape(ranks, lists), e_cnt)
+        assert np.array_equal(pl[2 * ranks * lists: 2 * ranks * lists + lists], e_out) and np.array_equal(pl[-8:].astype(np.int64), e_flags)
         info = sinfo.cpu().numpy().reshape(lists, 2)
         ok, op, orr = out_k.cpu().numpy().view(np.uint32), out_p.cpu().numpy().view(np.uint32), out_r.cpu().numpy()
         for l in range(lists):
