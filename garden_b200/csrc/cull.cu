@@ -1,5 +1,5 @@
 // Fused hot loop: world matrix (leaf-first parent-chain product) -> AABB-vs-frustum test for EVERY view of the frame ->
-// distance key -> deterministic stream compaction (warp ballot + block scan + decoupled look-back across tiles).
+// visibility ballots -> deterministic stream compaction (per-chunk counts, one scan, warp-per-chunk scatter with keys).
 //
 // Replaces prepareUnsortedMeshes / prepareSortedMeshes (source/system/render/mesh.cpp:111-184,187-262) and what they call:
 //   TransformComponent::calcModel        include/garden/system/transform.hpp:197-214
@@ -48,18 +48,6 @@ struct CullArgs
 
 constexpr uint32_t kChunkTiles = 8;                                // tiles per compaction chunk
 constexpr uint32_t kChunkWords = kChunkTiles * (kCullTile / 32);   // ballot words per chunk (one warp of kScatter per chunk)
-constexpr uint32_t kFlagAggregate = 1u << 30, kFlagInclusive = 2u << 30, kValueMask = (1u << 30) - 1;
-
-__device__ __forceinline__ uint32_t ldVolatile(const uint32_t* p)
-{
-	uint32_t v;
-	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v)
-{
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
 
 // ---- shared-memory cache of local matrices ----------------------------------------------------------------------------------
 // Leaf-first association (transform.hpp:204-210) forces every entity to multiply its own chain, but the chain's factors —

@@ -28,28 +28,6 @@ struct MergeArgs
 	uint32_t rankStride, ranks, lists, myRank;
 };
 
-// first index in [0, n) with a[i] >= key (lower) or a[i] > key (upper)
-__device__ __forceinline__ uint32_t lowerBound(const uint32_t* __restrict__ a, uint32_t n, uint32_t key)
-{
-	uint32_t lo = 0, hi = n;
-	while (lo < hi)
-	{
-		const uint32_t mid = (lo + hi) >> 1;
-		if (a[mid] < key) lo = mid + 1; else hi = mid;
-	}
-	return lo;
-}
-__device__ __forceinline__ uint32_t upperBound(const uint32_t* __restrict__ a, uint32_t n, uint32_t key)
-{
-	uint32_t lo = 0, hi = n;
-	while (lo < hi)
-	{
-		const uint32_t mid = (lo + hi) >> 1;
-		if (a[mid] <= key) lo = mid + 1; else hi = mid;
-	}
-	return lo;
-}
-
 // Warp-cooperative bound: all 32 lanes call it with the same arguments. Every round probes 32 evenly spaced positions of the
 // remaining range and keeps the 1/33 of it that contains the answer, so a run of millions of keys takes 4-5 dependent
 // memory round trips instead of 22 (the searches that bracket a chunk are pure latency).
