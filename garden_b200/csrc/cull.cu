@@ -803,8 +803,9 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	A.chunks = (A.tiles + kChunkTiles - 1) / kChunkTiles;
 	p.visibleValid = A.visibleView != kNone;
 
-	static bool carveoutSet = false;
-	if (!carveoutSet) // 4 resident blocks x 37 KB of shared memory need the large carve-out
+	// 8 resident blocks x 27 KB of shared memory need the large carve-out (function attributes are per device, and one
+	// context = one device, so the flag lives in the context)
+	if (!c.cullAttrsSet)
 	{
 		cudaFuncSetAttribute(kCull<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -814,7 +815,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 		cudaFuncSetAttribute(kCull<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		cudaFuncSetAttribute(kCull<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		carveoutSet = true;
+		c.cullAttrsSet = true;
 	}
 	cudaMemsetAsync(p.cullStatus, 0, (size_t)A.chunks * kMaxViews * sizeof(uint32_t), c.stream);
 	// the view loop is unrolled at compile time (plane constants become direct constant-bank operands)
@@ -833,11 +834,10 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 		const uint32_t units = A.chunks * P.viewCount;
 		const uint32_t blocks = std::max(1u, std::min((units + kScatterWarps - 1) / kScatterWarps, 148u * 4u));
 		const size_t histBytes = (size_t)P.viewCount * 4 * 256 * sizeof(uint32_t);
-		static bool attrSet = false;
-		if (!attrSet)
+		if (!c.scatterAttrSet)
 		{
 			cudaFuncSetAttribute(kScatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxViews * 4 * 256 * sizeof(uint32_t));
-			attrSet = true;
+			c.scatterAttrSet = true;
 		}
 		kScatter<<<blocks, kScatterThreads, histBytes, c.stream>>>(P, A);
 	}

@@ -132,6 +132,7 @@ struct Context
 	std::vector<gsp_view> views;
 	float cameraPos[3] = {0, 0, 0};
 	bool viewsSet = false, linkDirty = true, layoutDirty = true, resultsValid = false;
+	bool cullAttrsSet = false, scatterAttrSet = false; // kernel function attributes applied on this context's device
 	bool frameEnqueued = false; // a frame has been enqueued since the last structural change (its results may still be in flight)
 
 	// segments
