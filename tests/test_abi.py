@@ -43,3 +43,36 @@ def test_view_setup_helpers_match_oracle(sceneprep_lib, oracle_built):
         assert out[0]["planeCount"] == 6 and out[0]["uiPlaneCount"] == 0 and out[0]["shadowPass"] == views[v]["shadowPass"]
         assert np.array_equal(out[0]["cameraOffset"], off)
         assert np.array_equal(out[0]["planes"].view(np.uint32), o.frustum_planes(mats[v]).view(np.uint32))
+
+
+def test_no_cpu_fallback(sceneprep_lib, monkeypatch, tmp_path):
+    """The product path fails loudly: without a CUDA device gsp_create reports GSP_ERR_CUDA (no CPU fallback), and without the
+    built library the binding raises instead of routing anywhere else. Nothing under garden_b200/ loads anything from oracle/."""
+    import garden_b200.binding as B
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        try:
+            B.ScenePrep(0)
+            raise AssertionError("gsp_create succeeded without a CUDA device")
+        except B.ScenePrepError as e:
+            assert e.code == B.GSP_ERR_CUDA and "no CPU fallback" in str(e)
+    monkeypatch.setattr(B, "LIB_PATH", tmp_path / "missing.so")
+    monkeypatch.setattr(B, "_lib", None)
+    try:
+        B.load_library()
+        raised = False
+    except FileNotFoundError as e:
+        raised = "no CPU fallback" in str(e)
+    assert raised, "a missing libgarden_sceneprep.so must raise"
+    # the product never imports, links or opens the checkers
+    for path in (ROOT / "garden_b200").rglob("*"):
+        if path.suffix not in (".py", ".cu", ".cuh", ".h"):
+            continue
+        for ln in path.read_text().splitlines():
+            low = ln.lower()
+            if "oracle" in low or "reflib" in low:
+                assert not any(tok in low for tok in ("import ", "#include", "cdll", "dlopen")), f"{path}: {ln.strip()}"
