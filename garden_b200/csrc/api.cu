@@ -255,7 +255,7 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 		GSP_CUDA(cudaMalloc((void**)&t.parent, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.entity, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.parentEntity, (size_t)cap * sizeof(uint32_t)));
-		GSP_CUDA(cudaMalloc((void**)&t.flags, (size_t)cap * sizeof(uint16_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.flags, (((size_t)cap + 1) & ~(size_t)1) * sizeof(uint16_t))); // whole 32-bit words: gsp_set_active updates a flag entry through the word that holds it
 		t.capacity = cap;
 	}
 	t.occupancy = occupancy;
