@@ -76,3 +76,17 @@ def test_no_cpu_fallback(sceneprep_lib, monkeypatch, tmp_path):
             low = ln.lower()
             if "oracle" in low or "reflib" in low:
                 assert not any(tok in low for tok in ("import ", "#include", "cdll", "dlopen")), f"{path}: {ln.strip()}"
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and as C++ with no other include (plain pointers and sizes only)."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "garden_sceneprep.h"\nint main(void) { gsp_view v; gsp_record r; (void)v; (void)r; return sizeof(gsp_record) == 64 ? 0 : 1; }\n')
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        res = subprocess.run([cc, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{ROOT / 'include'}", "-x",
+                              "c" if cc == "gcc" else "c++", str(src)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+    exe = tmp_path / "use"
+    subprocess.run(["gcc", "-std=c99", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0, "gsp_record must be 64 bytes (UnsortedMesh / SortedMesh, mesh.hpp:191-205)"
