@@ -90,3 +90,37 @@ def test_header_is_plain_c(tmp_path):
     exe = tmp_path / "use"
     subprocess.run(["gcc", "-std=c99", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
     assert subprocess.run([str(exe)]).returncode == 0, "gsp_record must be 64 bytes (UnsortedMesh / SortedMesh, mesh.hpp:191-205)"
+
+
+def test_cpp_host_links_the_library(sceneprep_lib, tmp_path):
+    """A C++ host (what the reference is) links libgarden_sceneprep.so directly: view setup works without a device, and
+    gsp_create either succeeds (GPU box) or reports GSP_ERR_CUDA with a message (here) — never a silent fallback."""
+    import subprocess
+    src = tmp_path / "host.cpp"
+    src.write_text(r'''
+#include "garden_sceneprep.h"
+#include <cstdio>
+#include <cstring>
+int main()
+{
+    float vp[16] = { 1, 0, 0, 0,  0, 2, 0, 0,  0, 0, 0.5f, 1,  3, 4, 5, 1 }, off[4] = { 1, 2, 3, 0 };
+    gsp_view view;
+    if (gsp_view_from_viewproj(vp, off, 2, &view) != GSP_OK || view.planeCount != 6 || view.shadowPass != 2) return 10;
+    // Frustum(viewProj), frustum.hpp:53-60: plane 0 = t.c3 + t.c0 with t = transpose(viewProj)
+    if (view.planes[0][0] != vp[3] + vp[0] || view.planes[0][3] != vp[15] + vp[12] || view.planes[4][2] != vp[10]) return 11;
+    gsp_context* ctx = nullptr;
+    int rc = gsp_create(0, &ctx);
+    if (rc == GSP_OK) { std::printf("created\n"); gsp_destroy(ctx); return 0; }
+    if (rc != GSP_ERR_CUDA || ctx != nullptr) return 12;
+    const char* msg = gsp_last_error(nullptr);
+    if (!msg || !std::strstr(msg, "no CPU fallback")) return 13;
+    std::printf("no device: %s\n", msg);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    lib_dir = ROOT / "garden_b200"
+    subprocess.run(["g++", "-std=c++17", f"-I{ROOT / 'include'}", str(src), "-o", str(exe), f"-L{lib_dir}", "-lgarden_sceneprep",
+                    f"-Wl,-rpath,{lib_dir}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
