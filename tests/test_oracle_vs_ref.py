@@ -175,3 +175,16 @@ def test_set_active_matches_reference(oracle_built):
             theirs = ref.transform_bytes().reshape(tocc, tstride)
             assert np.array_equal(theirs[:, 72:74], mine[:, 72:74]), f"step {step}: active flags differ"
         assert 0 < int(mine[live, 73].sum()) < live.size  # both states occur
+
+
+@pytest.mark.parametrize("seed", list(range(20, 60)))
+def test_fuzz_mixed_scenes(oracle_built, seed):
+    """Differential fuzzing of the pin: random forests (depth up to 3..40), random filter states, render-type buckets, ready
+    counts, camera yaw and thread mode per seed — the oracle must reproduce the reference's lists bit for bit every time."""
+    rng = np.random.default_rng(seed)
+    threads = 0 if seed % 3 == 0 else -1
+    scene = mixed_scene(seed=seed, n=int(rng.integers(300, 2500)), max_depth=int(rng.integers(3, 40)),
+                        with_ui=bool(seed % 2), with_ready=bool((seed // 2) % 2), box_half=float(rng.uniform(20.0, 120.0)),
+                        single_translucent=threads == 0)
+    scene.camera_pos = rng.uniform(-30.0, 30.0, 3).astype(np.float32)
+    _check(scene, mixed_views(yaw=float(rng.uniform(-3.0, 3.0)), with_ui=bool(seed % 2)), threads=threads)
