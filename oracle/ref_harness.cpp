@@ -403,6 +403,29 @@ void ref_instance_mvp(const float* viewProj, const void* records, uint32_t count
 	}
 }
 
+// f2: TransformSystem::animateAsync (source/system/transform.cpp:609-623) for `count` entities, through the real system and
+// the real TransformFrame type. flags[i]: bit0 animatePosition, bit1 animateScale, bit2 animateRotation, bit3 animateIsActive,
+// bit4 frameA.isActive, bit5 frameB.isActive. frameA / frameB: [count][10] = position xyz, scale xyz, rotation xyzw.
+void ref_animate(uint32_t count, const uint32_t* entityIndex, const uint8_t* flags, const float* frameA, const float* frameB,
+	const float* t)
+{
+	for (uint32_t i = 0; i < count; i++)
+	{
+		TransformFrame a, b;
+		const float* fa = frameA + (size_t)i * 10; const float* fb = frameB + (size_t)i * 10;
+		a.animatePosition = b.animatePosition = (flags[i] >> 0) & 1;
+		a.animateScale = b.animateScale = (flags[i] >> 1) & 1;
+		a.animateRotation = b.animateRotation = (flags[i] >> 2) & 1;
+		a.animateIsActive = b.animateIsActive = (flags[i] >> 3) & 1;
+		a.isActive = (flags[i] >> 4) & 1; b.isActive = (flags[i] >> 5) & 1;
+		a.position = f32x4(fa[0], fa[1], fa[2], 0.0f); b.position = f32x4(fb[0], fb[1], fb[2], 0.0f);
+		a.scale = f32x4(fa[3], fa[4], fa[5], 0.0f); b.scale = f32x4(fb[3], fb[4], fb[5], 0.0f);
+		a.rotation = quat(fa[6], fa[7], fa[8], fa[9]); b.rotation = quat(fb[6], fb[7], fb[8], fb[9]);
+		auto transformView = manager->get<TransformComponent>(entityIDs[entityIndex[i]]);
+		transformSystem->animateAsync(View<Component>(transformView), View<AnimationFrame>(&a), View<AnimationFrame>(&b), t[i]);
+	}
+}
+
 // Times `frames` frames; one frame = viewCount serial prepareMeshes calls (mesh.cpp:795-847,893-903 order:
 // shadow passes first, main view last is the caller's choice of ordering in the arrays).
 // planes: [viewCount][6][4], cameraOffsets: [viewCount][4], shadowPasses: [viewCount]. Writes per-frame ms.

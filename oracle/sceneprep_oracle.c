@@ -579,3 +579,77 @@ int oracle_set_active(void* transforms, uint32_t stride, uint32_t occupancy, con
 	free(slotOf); free(childStart); free(childList); free(stack);
 	return rc;
 }
+
+/* f2. TransformSystem::animateAsync, source/system/transform.cpp:609-623.
+ * lerp(f32x4 a, f32x4 b, float t) = a * (1.0f - t) + b * t (simd/vector/float.hpp:1469): two lane-wise muls and an add, no FMA
+ * (intrinsics, dialect B). slerp (quaternion.hpp:175-193): dot4 (dpps 0xff: (x*x + y*y) + (z*z + w*w)), shortest path by
+ * negating b, lerp when cosTheta > 1 - FLT_EPSILON, else (a * sin((1 - t) * angle) + c * sin(t * angle)) / sin(angle) with
+ * std::acos / std::sin on floats = acosf / sinf. setPosition / setScale keep lane W (childCount / childCapacity bits). */
+static void lerp3(const float* a, const float* b, float t, float* out)
+{
+	const float s = 1.0f - t;
+	for (int l = 0; l < 3; l++)
+		out[l] = a[l] * s + b[l] * t;
+}
+int oracle_animate(void* transforms, uint32_t stride, uint32_t occupancy, uint32_t count, const uint32_t* entityIds,
+	const uint8_t* flags, const float* frameA, const float* frameB, const float* t)
+{
+	uint8_t* base = (uint8_t*)transforms;
+	if (!base || stride < 80)
+		return -1;
+	int rc = 0;
+	for (uint32_t i = 0; i < count; i++)
+	{
+		uint8_t* self = NULL;
+		for (uint32_t sl = 0; sl < occupancy; sl++) /* Manager::get<TransformComponent>(entity) */
+			if (ld_u32(base + (size_t)sl * stride + T_ENTITY) == entityIds[i] && entityIds[i])
+			{
+				self = base + (size_t)sl * stride;
+				break;
+			}
+		if (!self) { rc = -1; continue; }
+		const float* a = frameA + (size_t)i * 10; const float* b = frameB + (size_t)i * 10;
+		const float ti = t[i];
+		float v[4];
+		if (flags[i] & 1)
+		{
+			lerp3(a, b, ti, v);
+			memcpy(self + T_POS, v, 12);
+		}
+		if (flags[i] & 2)
+		{
+			lerp3(a + 3, b + 3, ti, v);
+			memcpy(self + T_SCALE, v, 12);
+		}
+		if (flags[i] & 4)
+		{
+			const float* qa = a + 6; const float* qb = b + 6;
+			float c[4] = { qb[0], qb[1], qb[2], qb[3] };
+			float cosTheta = (qa[0] * qb[0] + qa[1] * qb[1]) + (qa[2] * qb[2] + qa[3] * qb[3]);
+			if (cosTheta < 0.0f)
+			{
+				for (int l = 0; l < 4; l++) c[l] = -qb[l];
+				cosTheta = -cosTheta;
+			}
+			if (cosTheta > 1.0f - 1.1920928955078125e-07f)
+			{
+				const float s = 1.0f - ti;
+				for (int l = 0; l < 4; l++) v[l] = qa[l] * s + c[l] * ti;
+			}
+			else
+			{
+				const float angle = acosf(cosTheta);
+				const float s0 = sinf((1.0f - ti) * angle), s1 = sinf(ti * angle), s2 = sinf(angle);
+				for (int l = 0; l < 4; l++) v[l] = (qa[l] * s0 + c[l] * s1) / s2;
+			}
+			memcpy(self + T_ROT, v, 16);
+		}
+		if (flags[i] & 8)
+		{
+			const int active = roundf(ti) != 0.0f ? ((flags[i] >> 5) & 1) : ((flags[i] >> 4) & 1);
+			if (oracle_set_active(transforms, stride, occupancy, &entityIds[i], 1, active) != 0)
+				rc = -1;
+		}
+	}
+	return rc;
+}

@@ -87,6 +87,14 @@ void oracle_instance_mvp(const float viewProj[16], const OracleRecord* records, 
 int oracle_set_active(void* transforms, uint32_t stride, uint32_t occupancy, const uint32_t* entityIds, uint32_t count,
 	int active);
 
+/* f2 (oracle only so far — no CUDA counterpart yet): TransformSystem::animateAsync (source/system/transform.cpp:609-623) for
+ * `count` entities on the AoS transform pool in place: position / scale = lerp(a, b, t) (simd/vector/float.hpp:1469),
+ * rotation = slerp(a, b, t) (quaternion.hpp:175-193; acosf / sinf come from the host libm exactly as in the reference),
+ * isActive = round(t) ? b : a through setActive. flags[i]: bit0 position, bit1 scale, bit2 rotation, bit3 isActive animated,
+ * bit4 frameA.isActive, bit5 frameB.isActive; frameA / frameB: [count][10] = position xyz, scale xyz, rotation xyzw. */
+int oracle_animate(void* transforms, uint32_t stride, uint32_t occupancy, uint32_t count, const uint32_t* entityIds,
+	const uint8_t* flags, const float* frameA, const float* frameB, const float* t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,7 @@ class RefEngine:
         L.ref_calc_model.argtypes = [_u32, _vp, _vp]
         L.ref_time_frames.argtypes = [_u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp]
         L.ref_instance_mvp.argtypes = [_vp, _vp, _u32, _vp]
+        L.ref_animate.argtypes = [_u32, _vp, _vp, _vp, _vp, _vp]
         if L.ref_init(threads, 1 if use_oit else 0) != 0:
             raise RuntimeError("reference engine is already initialised in this process")
         self.pool_strides = []
@@ -130,6 +131,14 @@ class RefEngine:
         """TransformComponent::setActive for the given entity INDICES (0-based creation order), in order."""
         idx = np.ascontiguousarray(indices, dtype=np.uint32)
         self.lib.ref_set_active(idx.size, idx.ctypes.data, 1 if active else 0)
+
+    def animate(self, indices, flags, frame_a, frame_b, t):
+        """TransformSystem::animateAsync for entity INDICES (0-based); frames [n, 10] = position, scale, rotation."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8)
+        fa = np.ascontiguousarray(frame_a, dtype=np.float32); fb = np.ascontiguousarray(frame_b, dtype=np.float32)
+        tt = np.ascontiguousarray(t, dtype=np.float32)
+        self.lib.ref_animate(idx.size, idx.ctypes.data, fl.ctypes.data, fa.ctypes.data, fb.ctypes.data, tt.ctypes.data)
 
     def instance_mvp(self, view_proj, records: np.ndarray) -> np.ndarray:
         """(float4x4)(viewProj * f32x4x4(bakedModel, (0,0,0,1))) per record, by the reference's own math library."""
@@ -272,6 +281,8 @@ class Oracle:
         L.oracle_instance_mvp.argtypes = [_vp, _vp, _u32, _vp]
         L.oracle_set_active.argtypes = [_vp, _u32, _u32, _vp, _u32, _i32]
         L.oracle_set_active.restype = _i32
+        L.oracle_animate.argtypes = [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]
+        L.oracle_animate.restype = _i32
         self.h = L.oracle_create()
         self._keep = []
         self.occupancy = {}
@@ -364,6 +375,15 @@ class Oracle:
         if rec.size:
             self.lib.oracle_instance_mvp(vp.ctypes.data, rec.ctypes.data, rec.size, out.ctypes.data)
         return out
+
+    def animate(self, transforms: np.ndarray, stride: int, occupancy: int, entity_ids, flags, frame_a, frame_b, t) -> int:
+        """TransformSystem::animateAsync on AoS transform bytes IN PLACE (entity ids are 1-based)."""
+        ids = np.ascontiguousarray(entity_ids, dtype=np.uint32)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8)
+        fa = np.ascontiguousarray(frame_a, dtype=np.float32); fb = np.ascontiguousarray(frame_b, dtype=np.float32)
+        tt = np.ascontiguousarray(t, dtype=np.float32)
+        return self.lib.oracle_animate(transforms.ctypes.data, stride, occupancy, ids.size, ids.ctypes.data, fl.ctypes.data,
+                                       fa.ctypes.data, fb.ctypes.data, tt.ctypes.data)
 
     def set_active(self, transforms: np.ndarray, stride: int, occupancy: int, entity_ids, active: bool) -> int:
         """TransformComponent::setActive on AoS transform bytes IN PLACE (entity ids are 1-based)."""

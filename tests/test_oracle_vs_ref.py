@@ -188,3 +188,36 @@ def test_fuzz_mixed_scenes(oracle_built, seed):
                         single_translucent=threads == 0)
     scene.camera_pos = rng.uniform(-30.0, 30.0, 3).astype(np.float32)
     _check(scene, mixed_views(yaw=float(rng.uniform(-3.0, 3.0)), with_ui=bool(seed % 2)), threads=threads)
+
+
+def test_animate_matches_reference(oracle_built):
+    """f2 (oracle side): TransformSystem::animateAsync through the real system vs the restatement on a copy of the pool bytes —
+    lerp of position / scale, slerp of rotation (both branches, both hemispheres), isActive switching at t = 0.5, bit for bit
+    (the host libm serves both sides, as it serves the reference)."""
+    scene = mixed_scene(seed=31, n=900, max_depth=8, with_ui=False, with_ready=False)
+    rng = np.random.default_rng(5)
+    o = reflib.Oracle()
+    with reflib.RefEngine("parity", threads=0) as ref:
+        ref.load_scene(scene)
+        _, tstride, tocc = ref.transform_pool()
+        mine = ref.transform_bytes().reshape(tocc, tstride).copy()
+        ents = mine[:, 0:4].copy().view(np.uint32).reshape(-1)
+        live = np.nonzero(ents)[0]
+        for step in range(6):
+            n = 150
+            pick = rng.choice(live, size=n, replace=False)
+            flags = rng.integers(0, 64, n).astype(np.uint8)
+            fa = rng.uniform(-5, 5, (n, 10)).astype(np.float32); fb = rng.uniform(-5, 5, (n, 10)).astype(np.float32)
+            for f in (fa, fb):  # unit quaternions; some pairs nearly parallel (lerp branch), some in opposite hemispheres
+                f[:, 6:] /= np.linalg.norm(f[:, 6:], axis=1, keepdims=True).astype(np.float32)
+            near = rng.random(n) < 0.25
+            fb[near, 6:] = fa[near, 6:] * np.where(rng.random(near.sum()) < 0.5, 1.0, -1.0)[:, None].astype(np.float32)
+            fb[near, 6] = np.nextafter(fb[near, 6], np.float32(2.0))
+            t = rng.random(n).astype(np.float32)
+            t[:8] = [0.0, 1.0, 0.5, 0.49999997, 0.50000006, 0.25, 0.75, 1.0]
+            ref.animate(ents[pick] - 1, flags, fa, fb, t)
+            assert o.animate(mine, tstride, tocc, ents[pick], flags, fa, fb, t) == 0
+            theirs = ref.transform_bytes().reshape(tocc, tstride)
+            for lo, hi, what in ((16, 28, "position"), (32, 44, "scale"), (48, 64, "rotation"), (72, 74, "active flags")):
+                assert np.array_equal(theirs[:, lo:hi], mine[:, lo:hi]), f"step {step}: {what} differs"
+            assert np.array_equal(theirs[:, 28:32], mine[:, 28:32]) and np.array_equal(theirs[:, 44:48], mine[:, 44:48]), "lane W"
