@@ -139,6 +139,44 @@ def f_rows():
     print(f"f_rows -> {path.stat().st_size / 1024:.0f} KiB")
 
 
+def f2_animate():
+    """Golden vectors of TransformSystem::animateAsync (SURVEY.md 8f.2) from the reference itself -> frows/f2_animate.npz:
+    transform pool bytes, per step the animated entity ids / flags / frames / t, and the pool's TRS + active bytes after it."""
+    out = {}
+    scene = mixed_scene(seed=31, n=900, max_depth=8, with_ui=False, with_ready=False)
+    rng = np.random.default_rng(77)
+    with reflib.RefEngine("parity", threads=0) as ref:
+        ref.load_scene(scene)
+        _, tstride, tocc = ref.transform_pool()
+        tbytes = ref.transform_bytes().reshape(tocc, tstride).copy()
+        tbytes[:, 8:16] = 0    # uid
+        tbytes[:, 64:72] = 0   # childs
+        out["transforms"] = tbytes
+        ents = tbytes[:, 0:4].copy().view(np.uint32).reshape(-1)
+        live = np.nonzero(ents)[0]
+        steps = 4
+        for step in range(steps):
+            n = 120
+            pick = rng.choice(live, size=n, replace=False)
+            flags = rng.integers(0, 64, n).astype(np.uint8)
+            fa = rng.uniform(-5, 5, (n, 10)).astype(np.float32); fb = rng.uniform(-5, 5, (n, 10)).astype(np.float32)
+            for f in (fa, fb):
+                f[:, 6:] /= np.linalg.norm(f[:, 6:], axis=1, keepdims=True).astype(np.float32)
+            near = rng.random(n) < 0.25
+            fb[near, 6:] = fa[near, 6:] * np.where(rng.random(near.sum()) < 0.5, 1.0, -1.0)[:, None].astype(np.float32)
+            t = rng.random(n).astype(np.float32)
+            t[:6] = [0.0, 1.0, 0.5, 0.49999997, 0.50000006, 0.75]
+            ref.animate(ents[pick] - 1, flags, fa, fb, t)
+            after = ref.transform_bytes().reshape(tocc, tstride)
+            out[f"ids{step}"], out[f"flags{step}"], out[f"a{step}"], out[f"b{step}"], out[f"t{step}"] = ents[pick].astype(np.uint32), flags, fa, fb, t
+            out[f"after{step}"] = np.concatenate([after[:, 16:64], after[:, 72:74]], axis=1).copy()
+        out["steps"] = np.array([steps], np.uint32)
+    path = HERE / "frows" / "f2_animate.npz"
+    np.savez_compressed(path, **out)
+    print(f"f2_animate -> {path.stat().st_size / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     main()
     f_rows()
+    f2_animate()
