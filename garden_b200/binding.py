@@ -32,6 +32,7 @@ SYMBOLS = {
     "gsp_update_transforms_indexed": (_i32, [_vp, _vp, _u32, _vp, _u32]),
     "gsp_set_pool_count": (_i32, [_vp, _u32]),
     "gsp_set_mesh_pool": (_i32, [_vp, _u32, _u32, _u32, _vp, _u32, _u32, _u32, _vp]),
+    "gsp_set_pool_view_mask": (_i32, [_vp, _u32, _u32]),
     "gsp_set_views": (_i32, [_vp, _u32, _vp, _vp]),
     "gsp_run": (_i32, [_vp]),
     "gsp_run_async": (_i32, [_vp]),
@@ -172,6 +173,10 @@ class ScenePrep:
             assert ready_counts.size >= occupancy
         self._check(self.lib.gsp_set_mesh_pool(self.h, pool, render_type, 1 if draw_ready else 0, _ptr(aos), stride,
                                                occupancy, count, _ptr(ready_counts)))
+
+    def set_pool_view_mask(self, pool: int, view_mask: int):
+        """bit v = isDrawReady(views[v].shadowPass) of the pool's mesh system (mesh.cpp:426,482)."""
+        self._check(self.lib.gsp_set_pool_view_mask(self.h, pool, view_mask & 0xFFFFFFFF))
 
     def set_views(self, views: np.ndarray, camera_pos):
         views = np.ascontiguousarray(views, dtype=VIEW_DTYPE)

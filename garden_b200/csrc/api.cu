@@ -101,6 +101,7 @@ int gsp_create(int device, gsp_context** out)
 		return GSP_ERR_NOMEM;
 	Context& c = ctx->c;
 	c.device = device;
+	c.smCount = (uint32_t)std::max(1, prop.multiProcessorCount);
 	memset(c.segOf, -1, sizeof(c.segOf));
 	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -419,6 +420,22 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 	return GSP_OK;
 }
 
+int gsp_set_pool_view_mask(gsp_context* ctx, uint32_t pool, uint32_t viewMask)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	if (pool >= (uint32_t)kMaxPools)
+		return fail(c, GSP_ERR_INVALID, "gsp_set_pool_view_mask: bad pool index");
+	auto& p = c.pools[pool];
+	if (p.viewMask != viewMask)
+	{
+		p.viewMask = viewMask;
+		c.layoutDirty = true; c.resultsValid = false; c.frameEnqueued = false;
+	}
+	return GSP_OK;
+}
+
 int gsp_set_views(gsp_context* ctx, uint32_t viewCount, const gsp_view* views, const float cameraPosition[3])
 {
 	if (!ctx)
@@ -466,7 +483,7 @@ static int rebuildLayout(Context& c)
 				c.error = "pool " + std::to_string(p) + " was declared by gsp_set_pool_count but never set";
 				return GSP_ERR_STATE;
 			}
-			const bool active = pool.count > 0 && pool.drawReady && pool.occupancy > 0; // mesh.cpp:426,482
+			const bool active = pool.count > 0 && pool.drawReady && ((pool.viewMask >> v) & 1u) && pool.occupancy > 0; // isDrawReady(shadowPass) per view, mesh.cpp:426,482
 			if (pool.renderType == GSP_RT_TRANSLUCENT || pool.renderType == GSP_RT_UI)
 			{
 				const bool isUI = pool.renderType == GSP_RT_UI;
@@ -652,6 +669,10 @@ int gsp_sync(gsp_context* ctx)
 	GSP_CUDA(cudaSetDevice(c.device));
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
 	GSP_CUDA(cudaGetLastError());
+	// results only exist for a frame enqueued AFTER the last change of transforms / pools / views (anything else would hand
+	// out the counters and segments of an older frame, possibly of an older layout)
+	if (!c.frameEnqueued || c.layoutDirty)
+		return fail(c, GSP_ERR_STATE, "gsp_sync: no frame has been enqueued (gsp_run_async) since the last change");
 	if (c.hCounters[kCtrError])
 		return fail(c, GSP_ERR_HIERARCHY, "gsp_run: transform hierarchy is cyclic or deeper than 4096");
 	c.resultsValid = true;

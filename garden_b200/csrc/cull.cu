@@ -754,6 +754,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 {
 	auto& p = c.pools[pool];
 	c.poolLaunched[pool] = false;
+	p.visibleValid = false; // only a frame whose main view processed this pool owns its isVisible bytes (mesh.cpp:426,482)
 	if (!p.set || p.occupancy == 0)
 		return 0;
 	CullParams P = {};
@@ -832,7 +833,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	{
 		// persistent grid: one wave of blocks, every warp strides over (chunk, view) units
 		const uint32_t units = A.chunks * P.viewCount;
-		const uint32_t blocks = std::max(1u, std::min((units + kScatterWarps - 1) / kScatterWarps, 148u * 4u));
+		const uint32_t blocks = std::max(1u, std::min((units + kScatterWarps - 1) / kScatterWarps, c.smCount * 4u));
 		const size_t histBytes = (size_t)P.viewCount * 4 * 256 * sizeof(uint32_t);
 		if (!c.scatterAttrSet)
 		{

@@ -137,7 +137,7 @@ uint32_t launchEmit(Context& c)
 	uint64_t capGroups = 0;
 	for (auto& sgm : c.segments)
 		capGroups += (sgm.capacity + kEmitRecordsPerIter * kEmitUnroll - 1) / (kEmitRecordsPerIter * kEmitUnroll);
-	dim3 grid((uint32_t)std::min<uint64_t>(capGroups, 148u * 8u));
+	dim3 grid((uint32_t)std::min<uint64_t>(capGroups, c.smCount * 8u));
 	kEmit<<<grid, kEmitThreads, 0, c.stream>>>(A);
 	return 1;
 }

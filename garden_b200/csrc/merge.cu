@@ -307,7 +307,7 @@ uint32_t launchExportPacked(Context& c, uint32_t* dBlock, uint32_t capacity)
 	ExportArgs A;
 	A.segments = c.dSegments; A.counters = c.dCounters; A.keys = c.keys[0]; A.payloads = c.payloads[0];
 	A.block = dBlock; A.lists = (uint32_t)c.segments.size(); A.capacity = capacity;
-	kExportPacked<<<148 * 4, 256, 0, c.stream>>>(A);
+	kExportPacked<<<c.smCount * 4, 256, 0, c.stream>>>(A);
 	return 1;
 }
 

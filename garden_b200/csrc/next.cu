@@ -54,7 +54,7 @@ uint32_t launchInstances(Context& c, int seg, const float* viewProj, void* dDst,
 	const uint32_t groups = (A.capacity + 63) / 64;
 	if (groups == 0)
 		return 0;
-	kInstances<<<std::min<uint32_t>(groups, 148u * 8u), 256, 0, c.stream>>>(A);
+	kInstances<<<std::min<uint32_t>(groups, c.smCount * 8u), 256, 0, c.stream>>>(A);
 	return 1;
 }
 

@@ -55,6 +55,7 @@ struct TransformsDev
 struct PoolDev
 {
 	uint32_t occupancy = 0, capacity = 0, count = 0, stride = 0, renderType = 0, drawReady = 0;
+	uint32_t viewMask = 0xFFFFFFFFu; // bit v: isDrawReady(views[v].shadowPass) (gsp_set_pool_view_mask)
 	bool hasReady = false, set = false;
 	float4* aabbA = nullptr;  // min xyz, max x
 	float2* aabbB = nullptr;  // max y, z
@@ -120,6 +121,7 @@ struct SegmentDev // device-visible part
 struct Context
 {
 	int device = 0;
+	uint32_t smCount = 148; // cudaDevAttrMultiProcessorCount of `device` (grid sizes of the persistent kernels)
 	cudaStream_t ownStream = nullptr, stream = nullptr;
 	cudaStream_t copyStream = nullptr; cudaEvent_t copyEvent = nullptr; // list downloads overlap the caller / the write-back
 	bool fetchInFlight = false;

@@ -273,7 +273,7 @@ uint32_t launchSort(Context& c, cudaEvent_t afterHistogram)
 	A.tickets = c.sortTickets; A.segTileOffset = c.segTileOffset; A.epoch = 0;
 	A.segmentCountTotal = nseg;
 	// sort passes are persistent (tiles claimed by ticket): 3 resident blocks per SM, split over the segments
-	dim3 passGrid(std::min<uint32_t>(totalCapTiles, 148u * kSortBlocksPerSM));
+	dim3 passGrid(std::min<uint32_t>(totalCapTiles, c.smCount * kSortBlocksPerSM));
 	uint32_t launches = 0;
 	for (uint32_t pass = 0; pass < kPasses; pass++)
 	{

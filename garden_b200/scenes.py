@@ -41,6 +41,7 @@ class PoolDesc:
     ready: np.ndarray | None = None     # [M] u8 ready instance counts (None = frustum-only predicate)
     stride: int = 48
     draw_ready: bool = True
+    draw_ready_shadow: bool | None = None  # isDrawReady(shadowPass >= 0); None = same as draw_ready
 
 
 @dataclass

@@ -103,6 +103,13 @@ int gsp_set_pool_count(gsp_context* ctx, uint32_t poolCount);
  * getReadyMeshesAsync override beyond the frustum test (e.g. sprite.cpp:90-97): ready instance count per slot. */
 int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint32_t drawReady, const void* aos,
 	uint32_t stride, uint32_t occupancy, uint32_t count, const uint8_t* readyCounts);
+/* IMeshRenderSystem::isDrawReady(shadowPass) is asked once per prepareMeshes call, i.e. per VIEW (mesh.cpp:426,482), and
+ * systems answer per kind of pass: InstanceRenderSystem checks the base pipeline for shadowPass < 0 and the shadow pipeline
+ * otherwise (source/system/render/instance.cpp:61-113; createShadowPipeline() returns {} by default), UiLabelSystem returns
+ * false for every shadow pass (source/system/ui/label.cpp:262-265). Bit v of `viewMask` = isDrawReady(views[v].shadowPass)
+ * for the views of gsp_set_views; a pool takes part in view v iff drawReady (gsp_set_mesh_pool) != 0 AND bit v is set.
+ * The mask persists across gsp_set_mesh_pool calls until it is set again; the default is all ones. */
+int gsp_set_pool_view_mask(gsp_context* ctx, uint32_t pool, uint32_t viewMask);
 
 /* Page-locks and maps `bytes` of caller memory (e.g. a LinearPool's storage after it (re)allocates, linear-pool.hpp:620-628)
  * so that gsp_set_* / gsp_update_transforms read it in place. Already-registered ranges are accepted. Process-wide. */

@@ -45,7 +45,8 @@ template<> struct HarnessMeshComponent<3> final : public MeshRenderComponent { }
 struct IHarnessPool
 {
 	MeshRenderType renderType = MeshRenderType::Opaque;
-	bool drawReady = true;
+	bool drawReady = true;       // isDrawReady(shadowPass < 0): the base pipeline (instance.cpp:61-87)
+	bool drawReadyShadow = true; // isDrawReady(shadowPass >= 0): the shadow pipeline (none by default; UI: label.cpp:262-265)
 	std::vector<uint8> readyCounts; // per slot; empty = default behaviour (mesh.hpp:142-146)
 	virtual ~IHarnessPool() { }
 	virtual void* data() = 0;
@@ -63,7 +64,7 @@ public:
 	using C = HarnessMeshComponent<K>;
 	HarnessMeshSystem() { Manager::Instance::get()->addGroupSystem<IMeshRenderSystem>(this); }
 
-	bool isDrawReady(int8 shadowPass) override { return drawReady; }
+	bool isDrawReady(int8 shadowPass) override { return shadowPass < 0 ? drawReady : drawReadyShadow; }
 	void drawAsync(MeshRenderComponent*, const f32x4x4&, const f32x4x4&, uint32, int32) override { }
 	MeshRenderType getMeshRenderType() const override { return renderType; }
 	MeshRenderPool& getMeshComponentPool() const override { return *((MeshRenderPool*)&this->components); }
@@ -191,7 +192,12 @@ int ref_add_pool(int renderType)
 	return poolCount++;
 }
 
-void ref_set_pool_draw_ready(int pool, int ready) { pools[pool]->drawReady = ready != 0; }
+void ref_set_pool_draw_ready(int pool, int ready) { pools[pool]->drawReady = pools[pool]->drawReadyShadow = ready != 0; }
+// readiness per kind of pass, the distinction the reference's systems make (instance.cpp:61-113, label.cpp:262-265)
+void ref_set_pool_draw_ready2(int pool, int readyMain, int readyShadow)
+{
+	pools[pool]->drawReady = readyMain != 0; pools[pool]->drawReadyShadow = readyShadow != 0;
+}
 
 // Entities are created in order; entity i gets ID i + 1 + (entities created earlier).
 // position/scale: [count][3], rotation: [count][4] xyzw, parent: [count] index into all entities created so far

@@ -22,7 +22,7 @@ enum { M_ENTITY = 0, M_ENABLED = 14, M_VISIBLE = 15, M_AABB_MIN = 16, M_AABB_MAX
 typedef struct
 {
 	uint8_t* data;
-	uint32_t stride, occupancy, count, renderType, drawReady;
+	uint32_t stride, occupancy, count, renderType, drawReady, drawReadyShadow;
 	const uint8_t* readyCounts;
 	uint32_t readyCountsSize;
 	uint8_t* visible;
@@ -339,7 +339,7 @@ int oracle_set_pool(OracleScene* s, uint32_t index, uint32_t renderType, uint32_
 	if (index >= ORACLE_MAX_POOLS) return -1;
 	Pool* p = &s->pools[index];
 	p->data = (uint8_t*)data; p->stride = stride; p->occupancy = occupancy; p->count = count;
-	p->renderType = renderType; p->drawReady = drawReady;
+	p->renderType = renderType; p->drawReady = p->drawReadyShadow = drawReady;
 	p->readyCounts = readyCountsSize ? readyCounts : NULL; p->readyCountsSize = readyCountsSize;
 	if (p->visibleCap < occupancy)
 	{
@@ -350,6 +350,11 @@ int oracle_set_pool(OracleScene* s, uint32_t index, uint32_t renderType, uint32_
 	return 0;
 }
 void oracle_set_pool_count(OracleScene* s, uint32_t poolCount) { s->poolCount = poolCount; }
+void oracle_set_pool_draw_ready(OracleScene* s, uint32_t pool, uint32_t readyMain, uint32_t readyShadow)
+{
+	if (pool >= ORACLE_MAX_POOLS) return;
+	s->pools[pool].drawReady = readyMain; s->pools[pool].drawReadyShadow = readyShadow;
+}
 void oracle_set_camera(OracleScene* s, const float cameraPos[3]) { memcpy(s->cameraPos, cameraPos, 12); }
 
 /* MeshRenderSystem::prepareMeshes, source/system/render/mesh.cpp:331-553. */
@@ -379,7 +384,7 @@ int oracle_prepare(OracleScene* s, const OracleView* view, int writeVisible)
 			if (p->renderType == ORACLE_RT_UI && !isNotShadowPass) continue;
 			uint32_t bufferIndex = sortedIndex++;
 			s->sortedDraw[bufferIndex] = s->sortedInst[bufferIndex] = 0;
-			if (p->count == 0 || !p->drawReady) continue;
+			if (p->count == 0 || !(isNotShadowPass ? p->drawReady : p->drawReadyShadow)) continue; /* isDrawReady(shadowPass), mesh.cpp:426,482 */
 			int rc;
 			if (p->renderType == ORACLE_RT_TRANSLUCENT)
 				rc = prepare_pool(s, p, view->planes, view->planeCount, s->cameraPos, view->cameraOffset, isNotShadowPass,
@@ -396,7 +401,7 @@ int oracle_prepare(OracleScene* s, const OracleView* view, int writeVisible)
 		{
 			Buffer* b = &s->unsorted[unsortedIndex++];
 			b->drawCount = b->instanceCount = 0; b->pool = i;
-			if (p->count == 0 || !p->drawReady) continue;
+			if (p->count == 0 || !(isNotShadowPass ? p->drawReady : p->drawReadyShadow)) continue; /* isDrawReady(shadowPass), mesh.cpp:426,482 */
 			buffer_reserve(b, p->occupancy);
 			uint32_t draw = 0;
 			int rc = prepare_pool(s, p, view->planes, view->planeCount, s->cameraPos, view->cameraOffset, isNotShadowPass,

@@ -53,6 +53,10 @@ int oracle_set_transforms(OracleScene* s, const void* data, uint32_t stride, uin
 int oracle_set_pool(OracleScene* s, uint32_t index, uint32_t renderType, uint32_t drawReady, void* data,
 	uint32_t stride, uint32_t occupancy, uint32_t count, const uint8_t* readyCounts, uint32_t readyCountsSize);
 void oracle_set_pool_count(OracleScene* s, uint32_t poolCount);
+/* IMeshRenderSystem::isDrawReady(shadowPass) is asked once per prepareMeshes call (mesh.cpp:426,482) and systems answer
+ * per kind of pass (instance.cpp:61-113: base pipeline for shadowPass < 0, shadow pipeline otherwise; label.cpp:262-265):
+ * readiness oracle_prepare uses for main views / for shadow passes. oracle_set_pool sets both to its drawReady argument. */
+void oracle_set_pool_draw_ready(OracleScene* s, uint32_t pool, uint32_t readyMain, uint32_t readyShadow);
 void oracle_set_camera(OracleScene* s, const float cameraPos[3]);
 
 /* One MeshRenderSystem::prepareMeshes call (mesh.cpp:331-553) including sortMeshes (mesh.cpp:265-328).

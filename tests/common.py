@@ -48,13 +48,16 @@ class OracleRun:
     """Oracle results of a whole frame (all views), in the shape the GPU results are compared against."""
 
     def __init__(self, tf, pools, render_types, views, camera_pos, ready=None, draw_ready=None, counts=None,
-                 write_visible=False):
+                 write_visible=False, draw_ready_shadow=None):
         self.o = Oracle()
         t_addr, t_stride, t_occ = tf
         self.o.set_transforms(t_addr, t_stride, t_occ)
         for k, (addr, stride, occ) in enumerate(pools):
             self.o.set_pool(k, render_types[k], addr, stride, occ, None if counts is None else counts[k],
                             True if draw_ready is None else draw_ready[k], None if ready is None else ready[k])
+        if draw_ready_shadow is not None:
+            for k in range(len(pools)):
+                self.o.set_pool_draw_ready(k, True if draw_ready is None else draw_ready[k], draw_ready_shadow[k])
         self.o.set_pool_count(len(pools))
         self.o.set_camera(camera_pos)
         self.views = []
@@ -199,18 +202,30 @@ class GoldenCase:
                 res["visible"] = [z[f"v{v}_visible{k}"] for k in range(len(self.meta))]
             self.frames.append(res)
 
+    def draw_ready_shadow(self):
+        """isDrawReady(shadowPass >= 0) per pool (7th meta column; older files: same as the main-pass readiness)."""
+        return [bool(m[6]) if len(m) > 6 else bool(m[4]) for m in self.meta]
+
     def oracle_run(self):
         t = self.transforms
         return OracleRun((t, t.shape[1], t.shape[0]), [(p, int(m[1]), int(m[2])) for p, m in zip(self.pools, self.meta)],
                          self.render_types, self.views, self.camera_pos, ready=self.ready,
-                         draw_ready=[bool(m[4]) for m in self.meta], counts=[int(m[3]) for m in self.meta])
+                         draw_ready=[bool(m[4]) for m in self.meta], counts=[int(m[3]) for m in self.meta],
+                         draw_ready_shadow=self.draw_ready_shadow())
 
     def stage(self, sp):
         t = self.transforms
         sp.set_transforms(t, t.shape[1], t.shape[0])
         sp.set_pool_count(len(self.pools))
         for k, (p, m) in enumerate(zip(self.pools, self.meta)):
-            sp.set_mesh_pool(k, int(m[0]), p, int(m[1]), int(m[2]), int(m[3]), bool(m[4]), self.ready[k])
+            # readiness per view, the way the shim asks isDrawReady(view.shadowPass) (INTEGRATION.md)
+            main_ready, shadow_ready = bool(m[4]), self.draw_ready_shadow()[k]
+            sp.set_mesh_pool(k, int(m[0]), p, int(m[1]), int(m[2]), int(m[3]), main_ready or shadow_ready, self.ready[k])
+            mask = 0
+            for v in range(self.views.size):
+                if (main_ready if int(self.views[v]["shadowPass"]) < 0 else shadow_ready):
+                    mask |= 1 << v
+            sp.set_pool_view_mask(k, mask)
         sp.set_views(self.views, self.camera_pos)
 
 

@@ -13,6 +13,38 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _device_usable() -> bool:
+    """True when gsp_create(0) succeeds, i.e. an sm_100 device is usable by the product library."""
+    try:
+        import ctypes as C
+        from garden_b200.build import build_library
+        build_library()
+        from garden_b200.binding import load_library
+        lib = load_library()
+        h = C.c_void_p()
+        if lib.gsp_create(0, C.byref(h)) != 0:
+            return False
+        lib.gsp_destroy(h)
+        return True
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a box without a usable sm_100 device skips the gpu-marked tests instead of failing them
+    (tests/test_abi.py::test_no_cpu_fallback stays the one place that asserts the loud failure). With `-m gpu` — how the
+    GPU box runs them — nothing is skipped: a missing device must fail there, not pass silently."""
+    markexpr = config.getoption("-m", default="") or ""
+    if "gpu" in markexpr and "not gpu" not in markexpr:
+        return
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items or _device_usable():
+        return
+    skip = pytest.mark.skip(reason="no usable sm_100 CUDA device (the scene-preparation path has no CPU fallback)")
+    for it in gpu_items:
+        it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle_built():
     from reflib import build_oracle

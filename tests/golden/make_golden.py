@@ -45,12 +45,24 @@ def cases():
     leaves = np.ones(s.entity_count, bool)
     leaves[s.parent[s.parent >= 0]] = False
     yield "freed_slots_few_planes", s, few_planes_views(), np.nonzero(leaves)[0][::7].astype(np.uint32)
+    # isDrawReady(shadowPass) differs between the main pass and the shadow passes (instance.cpp:61-113, label.cpp:262-265):
+    # pool 0 has no shadow pipeline, pool 2's base pipeline is not ready yet but its shadow pipeline is, pool 1 (translucent,
+    # shared list) is shadow-only, pool 4 main-only
+    s = mixed_scene(seed=13, n=1800)
+    s.pools[0].draw_ready_shadow = False
+    s.pools[2].draw_ready = False; s.pools[2].draw_ready_shadow = True
+    s.pools[1].draw_ready = False; s.pools[1].draw_ready_shadow = True
+    s.pools[4].draw_ready_shadow = False
+    yield "shadow_readiness_differs", s, mixed_views(), None
 
 
 def main():
     if not reflib.ref_available("parity"):
         raise SystemExit("oracle/_ref/libgarden_ref_parity.so is missing: run `make -C oracle ref` where /root/reference exists")
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, scene, views, victims in cases():
+        if only and name not in only:
+            continue
         rts = [p.render_type for p in scene.pools]
         unsorted_types = [rt for rt in rts if rt not in (RT_TRANSLUCENT, RT_UI)]
         with reflib.RefEngine("parity", threads=-1) as ref:
@@ -71,7 +83,10 @@ def main():
                 out[f"pool{k}"] = mb
                 rc = ref.pool_ready_counts(k)
                 out[f"ready{k}"] = np.zeros(0, np.uint8) if rc is None else np.pad(rc, (0, max(0, occ - rc.size)), constant_values=1)[:occ]
-                meta.append([rts[k], stride, occ, count, 1 if scene.pools[k].draw_ready else 0, 0 if rc is None else 1])
+                pd = scene.pools[k]
+                shadow_ready = pd.draw_ready if pd.draw_ready_shadow is None else pd.draw_ready_shadow
+                meta.append([rts[k], stride, occ, count, 1 if pd.draw_ready else 0, 0 if rc is None else 1,
+                             1 if shadow_ready else 0])
             out["pool_meta"] = np.array(meta, dtype=np.uint32)
             out["views"] = views
             out["camera_pos"] = np.asarray(scene.camera_pos, np.float32)
@@ -177,6 +192,7 @@ def f2_animate():
 
 
 if __name__ == "__main__":
-    main()
-    f_rows()
-    f2_animate()
+    main()  # (names on the command line: only those cases)
+    if len(sys.argv) == 1:
+        f_rows()
+        f2_animate()

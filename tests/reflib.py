@@ -60,6 +60,7 @@ class RefEngine:
         L.ref_init.argtypes = [_i32, _i32]
         L.ref_add_pool.argtypes = [_i32]
         L.ref_set_pool_draw_ready.argtypes = [_i32, _i32]
+        L.ref_set_pool_draw_ready2.argtypes = [_i32, _i32, _i32]
         L.ref_create_entities.argtypes = [_u32, _vp, _vp, _vp, _vp, _vp]
         L.ref_update_trs.argtypes = [_u32, _vp, _vp, _vp, _vp]
         L.ref_set_active.argtypes = [_u32, _vp, _i32]
@@ -119,8 +120,9 @@ class RefEngine:
             rd = None if pd.ready is None else np.ascontiguousarray(pd.ready, dtype=np.uint8)
             self.lib.ref_add_meshes(k, ent.size, ent.ctypes.data, aabb.ctypes.data,
                                     None if en is None else en.ctypes.data, None if rd is None else rd.ctypes.data)
-            if not pd.draw_ready:
-                self.lib.ref_set_pool_draw_ready(k, 0)
+            shadow_ready = pd.draw_ready if pd.draw_ready_shadow is None else pd.draw_ready_shadow
+            if not pd.draw_ready or not shadow_ready:
+                self.lib.ref_set_pool_draw_ready2(k, 1 if pd.draw_ready else 0, 1 if shadow_ready else 0)
         if scene.inactive is not None and len(scene.inactive):
             idx = np.ascontiguousarray(scene.inactive, dtype=np.uint32)
             self.lib.ref_set_active(idx.size, idx.ctypes.data, 0)
@@ -263,6 +265,7 @@ class Oracle:
         L.oracle_set_transforms.argtypes = [_vp, _vp, _u32, _u32]
         L.oracle_set_pool.argtypes = [_vp, _u32, _u32, _u32, _vp, _u32, _u32, _u32, _vp, _u32]
         L.oracle_set_pool_count.argtypes = [_vp, _u32]
+        L.oracle_set_pool_draw_ready.argtypes = [_vp, _u32, _u32, _u32]
         L.oracle_set_camera.argtypes = [_vp, _vp]
         L.oracle_prepare.argtypes = [_vp, _vp, _i32]
         L.oracle_unsorted_buffer_count.argtypes = [_vp]
@@ -318,6 +321,9 @@ class Oracle:
 
     def set_pool_count(self, n: int):
         self.lib.oracle_set_pool_count(self.h, n)
+
+    def set_pool_draw_ready(self, pool: int, ready_main: bool, ready_shadow: bool):
+        self.lib.oracle_set_pool_draw_ready(self.h, pool, 1 if ready_main else 0, 1 if ready_shadow else 0)
 
     def set_camera(self, cam):
         cam = np.ascontiguousarray(cam, dtype=np.float32)

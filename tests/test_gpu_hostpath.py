@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from garden_b200 import scenes, views as V
+from garden_b200.layout import RT_OPAQUE
 
 from common import OracleRun, aos_inputs, compare_gpu_to_oracle
 
@@ -142,4 +143,50 @@ def test_wide_component_stride(oracle_built, sceneprep_lib):
     sp = ScenePrep(0)
     _stage_and_run(sp, t, pools, rts, views, scene.camera_pos)
     compare_gpu_to_oracle(sp, orun, rts, views, "stride 1024")
+    sp.close()
+
+
+def test_sync_and_writeback_follow_the_frame_state(oracle_built, sceneprep_lib):
+    """gsp_sync only validates results of a frame enqueued after the last change (no stale counters / segments), and a pool
+    the new frame's main view did not process keeps its isVisible bytes (the reference would not touch them, mesh.cpp:426,482)."""
+    from garden_b200.binding import GSP_ERR_STATE, ScenePrep, ScenePrepError
+    scene = scenes.config_scene("C2", n=20_000)
+    t, pools = aos_inputs(scene)
+    views, _ = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    sp = ScenePrep(0)
+    with pytest.raises(ScenePrepError) as e:
+        sp.sync()  # nothing enqueued yet
+    assert e.value.code == GSP_ERR_STATE
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(1)
+    sp.set_mesh_pool(0, RT_OPAQUE, pools[0], 48, pools[0].size)
+    sp.set_views(views, scene.camera_pos)
+    sp.run()
+    m = pools[0]
+    sp.writeback_visible(0, m, 48)
+    seen = int(m["isVisible"].sum())
+    assert seen > 0
+    # a change invalidates the frame: sync without a new gsp_run_async must not resurrect the old results
+    sp.set_views(views[:4], scene.camera_pos)  # shadow passes only
+    with pytest.raises(ScenePrepError) as e:
+        sp.sync()
+    assert e.value.code == GSP_ERR_STATE
+    with pytest.raises(ScenePrepError):
+        sp.get_unsorted(0, 0)
+    sp.run()
+    m["isVisible"][:] = 7
+    sp.writeback_visible(0, m, 48)        # no main view in this frame: bytes untouched
+    assert (m["isVisible"] == 7).all()
+    assert sp.writeback_visible_delta(0, m, 48) == 0 and (m["isVisible"] == 7).all()
+    # the pool is shadow-ready only: the main view of a full frame skips it, the cascades keep their lists
+    sp.set_views(views, scene.camera_pos)
+    sp.set_pool_view_mask(0, 0b01111)
+    sp.run()
+    assert sp.get_unsorted(4, 0)[1] == 0 and sum(sp.get_unsorted(v, 0)[1] for v in range(4)) > 0
+    sp.writeback_visible(0, m, 48)
+    assert (m["isVisible"] == 7).all()
+    sp.set_pool_view_mask(0, 0xFFFFFFFF)
+    sp.run()
+    sp.writeback_visible(0, m, 48)
+    assert int(m["isVisible"].sum()) == seen
     sp.close()

@@ -232,71 +232,62 @@ def test_empty_inputs(sceneprep_lib):
     sp.close()
 
 
-# ---- full BASELINE sizes: size-independent properties -----------------------------------------------------------------
+# ---- full BASELINE sizes: EVERY list of EVERY view against the reference build ----------------------------------------
 @pytest.mark.parametrize("workload,n", [("C2", 1_000_000), ("C3", 4_000_000), ("C4", 16_000_000)])
-def test_full_size_properties(sceneprep_lib, workload, n):
-    """At BASELINE.json's sizes the oracle would take minutes, so check what must hold for ANY correct result:
-    every list sorted by key with ties in ascending (pool, slot); a slot appears at most once per list; the main view's
-    list is exactly the set of slots with isVisible; cascades + camera lists are consistent with a second run (idempotence);
-    a 1/64 sample of the records is recomputed by the oracle (world matrix bits, key bits)."""
+def test_full_size_vs_reference(sceneprep_lib, oracle_built, workload, n):
+    """At BASELINE.json's sizes: the scene is built through the reference's real ECS (oracle/_ref parity build: the
+    reference's own mesh.cpp / transform.cpp), the CUDA path consumes the raw bytes of the reference's live
+    pools, and every draw list of every view is compared with the reference's — key bits, draw order (the reference's
+    order canonicalised inside equal-key runs, ours must already be canonical), bakedModel bits, counts — plus isVisible of
+    every slot. A wrongly culled entity anywhere in the scene fails this test. Without oracle/_ref (never the case on the
+    GPU box: it travels with the snapshot) the pinned C oracle takes the reference's place. Then idempotence: a second
+    frame over the same state gives identical lists."""
     import bench
     import reflib
+    from common import assert_frames_equal, gpu_frame, ref_frame
     from garden_b200.binding import ScenePrep
     scene = scenes.config_scene(workload, n=n)
     scene.camera_pos = bench.camera_pos()
     views = bench.frame_views(workload)
-    t, pools = scenes.build_aos(scene)
     rts = [p.render_type for p in scene.pools]
+    if reflib.ref_available("parity"):
+        ref = reflib.RefEngine("parity", threads=-1)
+        ref.load_scene(scene)
+        _, tstride, tocc = ref.transform_pool()
+        t = ref.transform_bytes().reshape(tocc, tstride).copy()
+        pools = []
+        for k in range(len(rts)):
+            _, stride, occ, cnt = ref.mesh_pool(k)
+            pools.append((ref.pool_bytes(k).reshape(occ, stride).copy(), stride, occ, cnt))
+        want = ref_frame(ref, views)
+        ref.close()
+        canonicalise_want = True
+    else:
+        tt, pp = scenes.build_aos(scene)
+        t, tstride, tocc = tt.view(np.uint8).reshape(tt.size, 80), 80, tt.size
+        pools = [(m.view(np.uint8).reshape(m.size, m.dtype.itemsize), m.dtype.itemsize, m.size, m.size) for m in pp]
+        orun = OracleRun((t, tstride, tocc), [(p[0], p[1], p[2]) for p in pools], rts, views, scene.camera_pos)
+        want = orun.views
+    del scene
     sp = ScenePrep(0)
-    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_transforms(t, tstride, tocc)
     sp.set_pool_count(len(pools))
-    for k, m in enumerate(pools):
-        sp.set_mesh_pool(k, rts[k], m, m.dtype.itemsize, m.size)
-    sp.set_views(views, scene.camera_pos)
+    for k, (raw, stride, occ, cnt) in enumerate(pools):
+        sp.set_mesh_pool(k, rts[k], raw, stride, occ, cnt)
+    sp.set_views(views, bench.camera_pos())
     sp.run()
-    o = reflib.Oracle()
-    o.set_transforms(t, t.dtype.itemsize, t.size)
-    first = {}
-    total = 0
-    for v in range(views.size):
-        lists = [(sp.get_unsorted(v, b)[0], False, b) for b in range(sp.unsorted_buffer_count(v))]
-        lists.append((sp.get_sorted(v, 0)[0], True, -1))
-        for rec, desc, b in lists:
-            total += rec.size
-            key = rec["distanceSq"].astype(np.float64) * (-1.0 if desc else 1.0)
-            assert np.all(np.diff(key) >= 0), f"view {v}: list not sorted"
-            ties = np.nonzero(np.diff(key) == 0)[0]
-            assert np.all(rec["componentOffset"][ties] < rec["componentOffset"][ties + 1]), f"view {v}: tie order"
-            assert np.unique(rec["componentOffset"]).size == rec.size
-            first[(v, b)] = (rec["componentOffset"].copy(), rec["distanceSq"].view(np.uint32).copy())
-            # sampled recomputation by the oracle: world matrix and key of every 64th record (unsorted buffers: pool b)
-            if b >= 0 and rec.size:
-                pool_index = [k for k, rt in enumerate(rts) if rt != RT_TRANSLUCENT][b]
-                stride = pools[pool_index].dtype.itemsize
-                off = views[v]["cameraOffset"]
-                for r in rec[:: max(64, rec.size // 300)]:
-                    slot = int(r["componentOffset"]) // stride
-                    ent = int(pools[pool_index]["entity"][slot])
-                    m = o.calc_model(ent - 1, scene.camera_pos).reshape(4, 4)  # transform slot == entity index here
-                    assert np.array_equal(m[:, :3].reshape(12).view(np.uint32), r["bakedModel"].view(np.uint32))
-                    u = (m[3, :3] + off[:3]).astype(np.float32)
-                    k32 = np.float32(np.float32(u[0] * u[0]) + np.float32(u[1] * u[1])) + np.float32(np.float32(u[2] * u[2]) + np.float32(0))
-                    assert np.float32(k32).view(np.uint32) == r["distanceSq"].view(np.uint32)
+    got = gpu_frame(sp, views, [(p[0], p[1]) for p in pools])
+    total = sum(u[1] for f in got for u in f["unsorted"]) + sum(f["trans"][1] for f in got)
     assert total == sp.last_visible_total() and total > n // 50
-    # main view (last): list == isVisible set
-    main = views.size - 1
-    for b, k in enumerate([k for k, rt in enumerate(rts) if rt != RT_TRANSLUCENT]):
-        m = pools[k]
-        sp.writeback_visible(k, m, m.dtype.itemsize)
-        vis_slots = np.nonzero(m["isVisible"])[0]
-        assert np.array_equal(np.sort(first[(main, b)][0] // m.dtype.itemsize), vis_slots)
+    assert_frames_equal(got, want, rts, f"{workload} {n}", canonicalise_got=False)
+    del want
     # idempotence: a second frame over the same state gives identical lists
     sp.run()
-    for v in range(views.size):
-        for b in range(sp.unsorted_buffer_count(v)):
-            rec = sp.get_unsorted(v, b)[0]
-            assert np.array_equal(rec["componentOffset"], first[(v, b)][0])
-            assert np.array_equal(rec["distanceSq"].view(np.uint32), first[(v, b)][1])
+    again = gpu_frame(sp, views)
+    for v, (a, b) in enumerate(zip(got, again)):
+        for (ra, da, ia), (rb, db, ib) in zip(a["unsorted"], b["unsorted"]):
+            assert (da, ia) == (db, ib) and np.array_equal(ra, rb), f"view {v}: second frame differs"
+        assert a["trans"][1] == b["trans"][1] and np.array_equal(a["trans"][0], b["trans"][0])
     sp.close()
 
 
