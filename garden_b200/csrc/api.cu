@@ -131,11 +131,12 @@ void gsp_destroy(gsp_context* ctx)
 	if (c.copyStream) cudaStreamSynchronize(c.copyStream);
 	auto& t = c.tf;
 	cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);
-	cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.entityToSlot);
+	cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.bound); cudaFree(t.record); cudaFree(t.rho); cudaFree(t.chainRoot); cudaFree(t.rootW); cudaFree(t.entityToSlot);
 	for (auto& p : c.pools)
 	{
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
 		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus); cudaFree(p.visBits);
+		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount); cudaFree(p.bucketCount);
 	}
 	cudaFree(c.dSegments); cudaFree(c.keys[0]); cudaFree(c.keys[1]); cudaFree(c.payloads[0]); cudaFree(c.payloads[1]);
 	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortHist); cudaFree(c.sortStatus); cudaFree(c.sortTickets);
@@ -247,7 +248,8 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 		if (cap == 0) cap = 1;
 		GSP_CUDA(cudaStreamSynchronize(c.stream));
 		cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);
-		cudaFree(t.parentEntity); cudaFree(t.flags);
+		cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.bound); cudaFree(t.record); cudaFree(t.rho); cudaFree(t.chainRoot); cudaFree(t.rootW);
+		t.bound = nullptr; t.record = nullptr; t.rho = nullptr; t.chainRoot = nullptr; t.rootW = nullptr;
 		t.rot = nullptr; t.posSx = nullptr; t.sYZ = nullptr; t.parent = nullptr; t.entity = nullptr;
 		t.parentEntity = nullptr; t.flags = nullptr; t.capacity = 0;
 		GSP_CUDA(cudaMalloc((void**)&t.rot, (size_t)cap * sizeof(float4)));
@@ -256,11 +258,16 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 		GSP_CUDA(cudaMalloc((void**)&t.parent, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.entity, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.parentEntity, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.bound, (size_t)cap * sizeof(float2)));
+		GSP_CUDA(cudaMalloc((void**)&t.record, (size_t)cap * sizeof(float4)));
+		GSP_CUDA(cudaMalloc((void**)&t.rho, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.chainRoot, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.rootW, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.flags, (((size_t)cap + 1) & ~(size_t)1) * sizeof(uint16_t))); // whole 32-bit words: gsp_set_active updates a flag entry through the word that holds it
 		t.capacity = cap;
 	}
 	t.occupancy = occupancy;
-	c.linkDirty = true; c.resultsValid = false; c.frameEnqueued = false;
+	c.linkDirty = true; c.chainDirty = true; c.resultsValid = false; c.frameEnqueued = false;
 	if (occupancy == 0)
 		return GSP_OK;
 	const void* src = nullptr;
@@ -302,6 +309,7 @@ int gsp_update_transforms(gsp_context* ctx, const void* aos, uint32_t stride, ui
 	int rc = resolveSource(c, (const uint8_t*)aos + (size_t)first * stride, (size_t)stride * count, &src);
 	if (rc) return rc;
 	launchStageTransforms(c, src, stride, first, count, false, nullptr);
+	c.chainDirty = true;
 	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the scratch buffer and the caller's memory are free again
 	GSP_CUDA(cudaGetLastError());
 	c.resultsValid = false; c.frameEnqueued = false;
@@ -346,6 +354,7 @@ int gsp_update_transforms_indexed(gsp_context* ctx, const void* aos, uint32_t st
 	c.dAosScratch = ptr; c.dAosScratchCap = cap;
 	GSP_CUDA(cudaMemcpyAsync(c.dAosScratch, c.hGather, bytes, cudaMemcpyHostToDevice, c.stream));
 	launchStageTransforms(c, (const uint8_t*)c.dAosScratch + listBytes, stride, 0, count, false, nullptr, (const uint32_t*)c.dAosScratch);
+	c.chainDirty = true;
 	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the pinned gather buffer is free again
 	GSP_CUDA(cudaGetLastError());
 	c.resultsValid = false; c.frameEnqueued = false;
@@ -384,7 +393,8 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		GSP_CUDA(cudaStreamSynchronize(c.stream));
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
 		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus); cudaFree(p.visBits);
-		p.visBits = nullptr;
+		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount); cudaFree(p.bucketCount);
+		p.visBits = nullptr; p.radius = nullptr; p.surList = nullptr; p.surTs = nullptr; p.surBits = nullptr; p.blockCount = nullptr; p.bucketCount = nullptr;
 		p.aabbA = nullptr; p.aabbB = nullptr; p.entity = nullptr; p.tslot = nullptr; p.flags = nullptr; p.ready = nullptr;
 		p.world = nullptr; p.visible = nullptr; p.cullStatus = nullptr; p.capacity = 0;
 		GSP_CUDA(cudaMalloc((void**)&p.aabbA, (size_t)cap * sizeof(float4)));
@@ -395,6 +405,15 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		GSP_CUDA(cudaMalloc((void**)&p.ready, (size_t)cap));
 		GSP_CUDA(cudaMalloc((void**)&p.world, (size_t)cap * kWorldStride * sizeof(float4)));
 		GSP_CUDA(cudaMalloc((void**)&p.visible, (size_t)cap));
+		GSP_CUDA(cudaMalloc((void**)&p.radius, (size_t)cap * sizeof(float)));
+		GSP_CUDA(cudaMalloc((void**)&p.surList, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&p.surTs, (size_t)cap * sizeof(uint32_t)));
+		{
+			const size_t preBlocks = ((size_t)cap + kPreTile - 1) / kPreTile;
+			GSP_CUDA(cudaMalloc((void**)&p.surBits, preBlocks * (kPreTile / 32) * sizeof(uint32_t)));
+			GSP_CUDA(cudaMalloc((void**)&p.blockCount, preBlocks * sizeof(uint32_t)));
+			GSP_CUDA(cudaMalloc((void**)&p.bucketCount, (preBlocks / 64 + 1) * sizeof(uint32_t)));
+		}
 		p.cullTilesCap = (cap + kCullTile - 1) / kCullTile;
 		GSP_CUDA(cudaMalloc((void**)&p.cullStatus, (size_t)p.cullTilesCap * kMaxViews * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&p.visBits, (size_t)p.cullTilesCap * kMaxViews * (kCullTile / 32) * sizeof(uint32_t)));
@@ -406,7 +425,7 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 	p.occupancy = occupancy; p.count = count; p.stride = stride; p.renderType = renderType; p.drawReady = drawReady;
 	p.hasReady = readyCounts != nullptr; p.set = true; p.visibleValid = false;
 	if (pool >= c.poolCount) { c.poolCount = pool + 1; c.layoutDirty = true; }
-	c.linkDirty = true; c.resultsValid = false; c.frameEnqueued = false;
+	c.linkDirty = true; c.chainDirty = true; c.resultsValid = false; c.frameEnqueued = false;
 	if (occupancy == 0)
 		return GSP_OK;
 	const void* src = nullptr;
@@ -638,6 +657,11 @@ int gsp_run_async(gsp_context* ctx)
 		launches += launchLink(c);
 		c.linkDirty = false;
 	}
+	if (c.chainDirty)
+	{
+		launches += launchChainBounds(c); // prepass bounds of every transform (only after the transform pool changed)
+		c.chainDirty = false;
+	}
 	if (prof) cudaEventRecord(c.phaseEvents[1], c.stream);
 	GSP_CUDA(cudaMemsetAsync(c.dCounters, 0, kCtrCount * sizeof(uint32_t), c.stream));
 	if (!c.segments.empty())
@@ -646,7 +670,7 @@ int gsp_run_async(gsp_context* ctx)
 		GSP_CUDA(cudaMemsetAsync(c.sortTickets, 0, c.segments.size() * 4 * sizeof(uint32_t), c.stream));
 	}
 	for (uint32_t p = 0; p < c.poolCount; p++)
-		launches += launchCull(c, p, prof ? c.poolEvents[p][0] : nullptr, prof ? c.poolEvents[p][1] : nullptr);
+		launches += launchCull(c, p, prof ? c.poolEvents[p][0] : nullptr, prof ? c.poolEvents[p][1] : nullptr, prof ? c.poolEvents[p][2] : nullptr);
 	launches += launchSort(c, prof ? c.phaseEvents[2] : nullptr);
 	if (prof) cudaEventRecord(c.phaseEvents[3], c.stream);
 	launches += launchEmit(c);
@@ -1071,6 +1095,7 @@ int gsp_set_active(gsp_context* ctx, const uint32_t* entityIds, uint32_t count, 
 	}
 	GSP_CUDA(cudaMemsetAsync(c.dError, 0, sizeof(uint32_t), c.stream));
 	launchSetActive(c, dIds, count, active);
+	c.chainDirty = true; // the prepass records carry isActive()
 	uint32_t* hScalars = c.hCounters + kCtrCount;
 	GSP_CUDA(cudaMemcpyAsync(&hScalars[1], c.dError, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the caller's id array is free again
@@ -1259,9 +1284,18 @@ int gsp_download_models(gsp_context* ctx, uint32_t pool, float* out)
 	if (p.occupancy == 0)
 		return GSP_OK;
 	GSP_CUDA(cudaSetDevice(c.device));
-	GSP_CUDA(cudaMemcpy2DAsync(out, 12 * sizeof(float), p.world, kWorldStride * sizeof(float4), 12 * sizeof(float), p.occupancy,
+	// world matrices are stored per SURVIVOR of the prepass (compact, in slot order): scatter them back to slots here
+	const uint32_t survivors = c.hCounters[kCtrSurvivors + pool];
+	if (survivors == 0 || !c.poolLaunched[pool])
+		return GSP_OK;
+	std::vector<uint32_t> list(survivors);
+	std::vector<float> compact((size_t)survivors * 12);
+	GSP_CUDA(cudaMemcpyAsync(list.data(), p.surList, (size_t)survivors * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaMemcpy2DAsync(compact.data(), 12 * sizeof(float), p.world, kWorldStride * sizeof(float4), 12 * sizeof(float), survivors,
 		cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	for (uint32_t i = 0; i < survivors; i++)
+		memcpy(out + (size_t)list[i] * 12, compact.data() + (size_t)i * 12, 12 * sizeof(float));
 	return GSP_OK;
 }
 
@@ -1283,20 +1317,20 @@ int gsp_get_phase_times(gsp_context* ctx, float* ms)
 	if (!c.phaseTimesValid || !c.resultsValid)
 		return GSP_OK;
 	GSP_CUDA(cudaSetDevice(c.device));
-	// link | per pool: cull, then scan + scatter | sort histogram | sort passes | emission
+	// link | per pool: prepass, cull, then scan + scatter | sort passes | emission
 	GSP_CUDA(cudaEventElapsedTime(&ms[0], c.phaseEvents[0], c.phaseEvents[1]));
 	cudaEvent_t prev = c.phaseEvents[1];
 	for (uint32_t p = 0; p < c.poolCount; p++)
 	{
 		if (!c.poolLaunched[p])
 			continue;
-		float a = 0.0f, b = 0.0f;
-		GSP_CUDA(cudaEventElapsedTime(&a, prev, c.poolEvents[p][0]));
-		GSP_CUDA(cudaEventElapsedTime(&b, c.poolEvents[p][0], c.poolEvents[p][1]));
-		ms[1] += a; ms[2] += b;
-		prev = c.poolEvents[p][1];
+		float pre = 0.0f, a = 0.0f, b = 0.0f;
+		GSP_CUDA(cudaEventElapsedTime(&pre, prev, c.poolEvents[p][0]));
+		GSP_CUDA(cudaEventElapsedTime(&a, c.poolEvents[p][0], c.poolEvents[p][1]));
+		GSP_CUDA(cudaEventElapsedTime(&b, c.poolEvents[p][1], c.poolEvents[p][2]));
+		ms[3] += pre; ms[1] += a; ms[2] += b;
+		prev = c.poolEvents[p][2];
 	}
-	GSP_CUDA(cudaEventElapsedTime(&ms[3], prev, c.phaseEvents[2]));
 	GSP_CUDA(cudaEventElapsedTime(&ms[4], c.phaseEvents[2], c.phaseEvents[3]));
 	GSP_CUDA(cudaEventElapsedTime(&ms[5], c.phaseEvents[3], c.phaseEvents[4]));
 	return GSP_OK;

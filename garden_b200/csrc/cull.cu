@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <string.h>
+#include <stdlib.h>
 
 namespace gsp
 {
@@ -25,62 +26,359 @@ struct CullArgs
 	const float2* __restrict__ tSYZ;
 	const uint32_t* __restrict__ tParent;
 	const uint16_t* __restrict__ tFlags;
+	const float4* __restrict__ tRecord; // per transform: prepass sphere (centre xyz, radius; < 0: not a candidate)
 	const float4* __restrict__ aabbA;
 	const float2* __restrict__ aabbB;
 	const uint32_t* __restrict__ tslot;
 	const uint8_t* __restrict__ mflags;
 	const uint8_t* __restrict__ ready;
-	float4* __restrict__ world;
+	uint32_t* __restrict__ surList;  // survivor index -> slot (written by kCompactSurvivors in slot order)
+	uint32_t* __restrict__ surTs;    // survivor index -> transform slot of the owning entity
+	float4* __restrict__ world;      // [survivor][kWorldStride]
 	uint8_t* __restrict__ visible;
-	uint32_t* __restrict__ visBits;  // [kMaxViews][tiles * 8] one ballot word per warp and view: visibility bit per slot
-	uint32_t* __restrict__ chunkCount; // [kMaxViews][chunks] visible slots per chunk and view; scanned in place to list offsets
+	uint32_t* __restrict__ visBits;  // [kMaxViews][tiles * 8] one ballot word per 32 SURVIVORS and view
+	uint32_t* __restrict__ chunkCount; // [kMaxViews][chunks] visible survivors per chunk and view; scanned in place to list offsets
 	uint32_t* __restrict__ counters;
 	uint32_t* __restrict__ keys;
 	uint32_t* __restrict__ payloads;
 	uint32_t* __restrict__ sortHist; // [segment][4][256] digit histograms of the sort, accumulated by kScatter
+	uint32_t* __restrict__ surBits;     // [prepass blocks][32] survivor bit per slot
+	uint32_t* __restrict__ blockCount;  // [prepass blocks] survivors per prepass block
+	uint32_t* __restrict__ bucketCount; // [prepass blocks / kPreBucket] survivors per bucket of blocks (zeroed per frame)
 	uint32_t histOffset[kMaxViews];  // element offset of the list's histograms in sortHist (kNone = list is not sorted)
 	uint32_t segOffset[kMaxViews];   // arena offset of this pool's list in view v
 	uint32_t baseCounter[kMaxViews]; // counter index holding the list length before this pool (kNone = 0)
 	uint32_t visibleView;            // view whose result is stored to isVisible (kNone = none)
-	uint32_t tiles;
-	uint32_t chunks;
+	uint32_t tiles;                  // capacity in 256-survivor tiles (stride of visBits)
+	uint32_t chunks;                 // capacity in chunks (stride of chunkCount)
+	uint32_t prepassCull;            // 0: the prepass only applies the filter (GSP_PREPASS=0, for A/B measurements)
 };
 
-constexpr uint32_t kChunkTiles = 8;                                // tiles per compaction chunk
+constexpr uint32_t kChunkTiles = 8;                                // 256-survivor tiles per compaction chunk
 constexpr uint32_t kChunkWords = kChunkTiles * (kCullTile / 32);   // ballot words per chunk (one warp of kScatter per chunk)
+constexpr uint32_t kChunkItems = kChunkWords * 32;                 // survivors per chunk
+
+// ---- conservative classification -------------------------------------------------------------------------------------------
+// The reference culls an entity for a view iff some plane has all eight transformed corners at d < 0 (aabb.hpp:452-462).
+// All corners lie in a sphere (centre cw, radius r), so with unit-normal planes
+//   min_i (n_i . cw + d_i) < -(r + band)   =>  some plane has every corner certainly behind: culled;
+//   min_i (n_i . cw + d_i) >  (r + band)   =>  every plane has every corner certainly in front: visible;
+// anything else (the box straddles a plane, or NaN/Inf anywhere) runs the reference's exact 8-corner arithmetic, so the
+// boolean is identical by construction. `band` absorbs every rounding difference between this real-arithmetic argument
+// and the floats on either side: computed plane distances differ from real arithmetic by a few ulp of
+// |n|_1 * A + |d| (A bounds every |corner lane| and every partial sum of the corner transform); kBandR * A + kBandD * |d|
+// = 2^-15 * (sqrt(3) A + |d|) leaves a factor > 30 of head room over the ~2^-21 worst case.
+// Cost per plane: 3 FMA + 1 MIN (the view loop is unrolled, every plane constant is a constant-bank operand).
+constexpr float kBandR = 1.7321f / 32768.0f, kBandD = 1.0f / 32768.0f;
+
+__device__ __forceinline__ float sqrtApprox(float x)
+{
+	float r;
+	asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+// smallest unit-plane distance of the point c over the view's planes (slots past planeCount are neutral: +inf)
+__device__ __forceinline__ float minPlaneDistance(const ViewConst& V, float cx, float cy, float cz)
+{
+	// planes (2j, 2j+1) share one packed FMA chain
+	f32x2 d[3];
+	#pragma unroll
+	for (int j = 0; j < 3; j++)
+		d[j] = fma2(pack2(V.ux[j].x, V.ux[j].y), pack2(cx, cx), fma2(pack2(V.uy[j].x, V.uy[j].y), pack2(cy, cy),
+			fma2(pack2(V.uz[j].x, V.uz[j].y), pack2(cz, cz), pack2(V.ud[j].x, V.ud[j].y))));
+	return fminf(fminf(fminf(lo2(d[0]), hi2(d[0])), fminf(lo2(d[1]), hi2(d[1]))), fminf(lo2(d[2]), hi2(d[2])));
+}
+
+// ---- prepass: filter + hierarchical conservative culling + ordered compaction of the survivors ---------------------------
+// In a large scene most entities are outside every view, and the expensive part of the path — the leaf-first product of the
+// parent chain (transform.hpp:197-214) — is only needed for entities that might be visible. The prepass bounds the world box
+// of a slot WITHOUT any matrix: with sigma_i >= |linear part of L_i| and tau_i >= |translation of L_i| (staging.cu,
+// transformBound) for the chain e = n_0, n_1 = parent, ..., n_k = root, every corner x of the box satisfies
+//     | M x - p_k |  <=  u_k,     u_0 = sigma_0 * rho,   u_i = sigma_i * (tau_(i-1) + u_(i-1))
+// (rho >= |x|; p_k = the root's position, which IS the translation of its local matrix), so all eight corners lie in the
+// sphere (p_k - cam, u_k). u_k is linear in rho: u_k = D + S * rho with D_0 = 0, S_0 = sigma_0, D_i = sigma_i * (tau_(i-1) +
+// D_(i-1)), S_i = sigma_i * S_(i-1). Every step is inflated by 2^-8, far more than the rounding of the float product the
+// bound stands for (a 4x3 product perturbs its result by < 2^-20 of the same norms), so the bound also holds for the FLOAT
+// world matrix the exact path computes.
+// These are quantities of the transform pool alone, so they are computed when it CHANGES, not per frame: kChainBounds walks
+// every transform's chain once (D, S, root) and folds u = D + S * rho_t (rho_t = largest box of any mesh on the transform,
+// kLinkPool) into W[root] = max over the hierarchy; kChainRecords then gives every transform the sphere (position of its
+// root, W[root]). One sphere per hierarchy: it survives or is dropped as a whole, so the survivors' ancestors are survivors
+// too and sit right before them in the list. gsp_set_transforms / gsp_update_transforms* / gsp_set_mesh_pool /
+// gsp_set_active / gsp_animate mark the records stale; the next frame recomputes them before anything reads them.
+// Per frame, kPrepass only streams: a slot is dropped iff, for every view it takes part in, its sphere is certainly behind one
+// of the view's planes — then the reference's 8-corner test culls it too (all corners behind that plane). Everything else
+// "survives": kPrepass writes one survivor bit per slot and the survivor count of its block, kCompactSurvivors turns the
+// bits into surList (slot order, no inter-block dependency) and kCull does the exact work on the survivors alone.
+// Non-finite or out-of-range inputs make the bound infinite or NaN (survive).
+constexpr uint32_t kPreThreads = 256, kPreItems = kPreTile / kPreThreads, kPreWarps = kPreThreads / 32;
+constexpr uint32_t kPreWords = kPreTile / 32;      // survivor-bit words per prepass block
+constexpr uint32_t kPreBucket = 64;                // prepass blocks per bucket of the two-level survivor count
+constexpr uint32_t kPreMaxWalk = 255;
+static_assert(kPreWords == 32, "kCompactSurvivors handles one prepass block per warp, one word per lane");
+
+struct ChainArgs
+{
+	const float2* __restrict__ bound;
+	const uint32_t* __restrict__ parent;
+	const uint16_t* __restrict__ flags;
+	const float4* __restrict__ posSx;
+	const uint32_t* __restrict__ rho;
+	uint32_t* __restrict__ chainRoot;
+	uint32_t* __restrict__ rootW;
+	float4* __restrict__ record;
+	uint32_t count;
+};
+__global__ void __launch_bounds__(256) kChainBounds(const __grid_constant__ ChainArgs A)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= A.count)
+		return;
+	const float2 own = A.bound[t];
+	float D = 0.0f, S = own.x, tauPrev = own.y;
+	uint32_t root = t, p = A.parent[t], n = 0;
+	while (p != kNone && n < kPreMaxWalk)
+	{
+		const float2 b = A.bound[p];
+		const float d = b.x * (tauPrev + D), s = b.x * S;
+		D = fmaf(d, 0x1p-8f, d); S = fmaf(s, 0x1p-8f, s);
+		tauPrev = b.y; root = p; p = A.parent[p]; n++;
+	}
+	const float rho = __uint_as_float(A.rho[t]);
+	float u = rho == 0.0f ? D : fmaf(S, rho, D); // (0 * inf would poison a transform that carries no mesh)
+	if (p != kNone) // longer than the walk allows (or cyclic): nothing of this hierarchy is ever culled by the prepass
+		u = __int_as_float(0x7f800000);
+	A.chainRoot[t] = root;
+	// u >= +0, +inf or NaN: the bit patterns order like unsigned integers (NaN on top)
+	if ((A.flags[t] & kTfLive) && (A.flags[root] & kTfLive))
+		atomicMax(&A.rootW[root], __float_as_uint(u));
+}
+__global__ void __launch_bounds__(256) kChainRecords(const __grid_constant__ ChainArgs A)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= A.count)
+		return;
+	const uint16_t f = A.flags[t];
+	float4 rec = make_float4(0.f, 0.f, 0.f, -1.0f); // dead or inactive: never a candidate (mesh.cpp:149-155)
+	if ((f & kTfLive) && (f & kTfActive))
+	{
+		if (f & kTfAncestors)
+		{
+			const uint32_t root = A.chainRoot[t];
+			const float4 c = A.posSx[root];
+			rec = make_float4(c.x, c.y, c.z, __uint_as_float(A.rootW[root]));
+		}
+		else
+		{
+			// modelWithAncestors == false: the model is the local matrix alone (transform.hpp:200)
+			const float4 c = A.posSx[t];
+			const float rho = __uint_as_float(A.rho[t]);
+			rec = make_float4(c.x, c.y, c.z, rho == 0.0f ? 0.0f : A.bound[t].x * rho);
+		}
+	}
+	A.record[t] = rec;
+}
+
+template<uint32_t kViews>
+__global__ void __launch_bounds__(kPreThreads) kPrepass(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+{
+	__shared__ uint32_t sCount[kPreWarps];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t blockBase = blockIdx.x * kPreTile;
+
+	uint32_t slot[kPreItems], ts[kPreItems];
+	bool cand[kPreItems];
+	#pragma unroll
+	for (uint32_t k = 0; k < kPreItems; k++)
+	{
+		slot[k] = blockBase + k * kPreThreads + threadIdx.x;
+		const bool inRange = slot[k] < P.occupancy;
+		cand[k] = inRange && (A.mflags[slot[k]] & kMfCandidate);
+		ts[k] = inRange ? A.tslot[slot[k]] : kNone;
+		if (P.hasReady && inRange && A.ready[slot[k]] == 0) // a getReadyMeshesAsync override's extra predicate (e.g. sprite.cpp:90-97)
+			cand[k] = false;
+		// isVisible of the (last) main view is written for every slot like mesh.cpp:144-146,152-153,161-167: zero here,
+		// kCull stores the ones
+		if (A.visibleView != kNone && inRange)
+			A.visible[slot[k]] = 0;
+	}
+	float4 rec[kPreItems];
+	#pragma unroll
+	for (uint32_t k = 0; k < kPreItems; k++)
+	{
+		cand[k] = cand[k] && ts[k] != kNone;
+		rec[k] = make_float4(0.f, 0.f, 0.f, -1.0f);
+		if (cand[k])
+			rec[k] = A.tRecord[ts[k]];
+		cand[k] = cand[k] && !(rec[k].w < 0.0f); // live and active transform (NaN radius: candidate, never culled here)
+	}
+	uint32_t total = 0;
+	#pragma unroll
+	for (uint32_t k = 0; k < kPreItems; k++)
+	{
+		bool survive = cand[k];
+		if (cand[k] && A.prepassCull)
+		{
+			const float u = rec[k].w;
+			const float cx = rec[k].x - P.cam[0], cy = rec[k].y - P.cam[1], cz = rec[k].z - P.cam[2];
+			const float magnitude = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + u);
+			const float reach = fmaf(magnitude, kBandR, u * 1.0001f);
+			bool maybe = false;
+			#pragma unroll
+			for (uint32_t v = 0; v < kViews; v++)
+			{
+				if (v < P.viewCount) // warp-uniform
+				{
+					const ViewConst& V = P.views[v];
+					const float dmin = minPlaneDistance(V, cx, cy, cz);
+					const bool behind = dmin < -(reach + V.slack); // false for NaN / infinite bounds
+					if (V.enabled && !behind)
+						maybe = true;
+				}
+			}
+			survive = maybe;
+		}
+		// slots of a block are ordered (round, warp, lane): word k * kPreWarps + warp holds 32 consecutive slots
+		const uint32_t votes = __ballot_sync(0xffffffffu, survive);
+		if (lane == 0)
+			A.surBits[(size_t)blockIdx.x * kPreWords + k * kPreWarps + warp] = votes;
+		total += __popc(votes);
+	}
+	if (lane == 0)
+		sCount[warp] = total;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t sum = 0;
+		#pragma unroll
+		for (uint32_t w = 0; w < kPreWarps; w++)
+			sum += sCount[w];
+		A.blockCount[blockIdx.x] = sum;
+		if (sum)
+			atomicAdd(&A.bucketCount[blockIdx.x / kPreBucket], sum);
+	}
+}
+
+// Survivor bits -> surList (+ the survivors' transform slots) in slot order. One WARP per prepass block (lane = one word of
+// 32 slots). The block's position in the list = survivors of all earlier blocks = (sum of the earlier buckets) + (sum of
+// the earlier blocks of its own bucket): a few hundred L2-resident words read by the 32 lanes in parallel, so no block ever
+// waits for another one. The set bits are expanded into shared memory first, so that the list is written (and the
+// transform links are gathered) by whole warps.
+constexpr uint32_t kCompactWarps = 8;
+__global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A,
+	uint32_t preBlocks)
+{
+	__shared__ uint16_t sOffsets[kCompactWarps][kPreTile];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * kCompactWarps + warp;
+	if (b >= preBlocks)
+		return; // (whole warps; nothing below synchronises across warps)
+	uint32_t before = 0;
+	const uint32_t bucket = b / kPreBucket;
+	for (uint32_t j = lane; j < bucket; j += 32)
+		before += A.bucketCount[j];
+	for (uint32_t i = bucket * kPreBucket + lane; i < b; i += 32)
+		before += A.blockCount[i];
+	before = __reduce_add_sync(0xffffffffu, before);
+	const uint32_t bits = A.surBits[(size_t)b * kPreWords + lane];
+	const uint32_t c = __popc(bits);
+	uint32_t inc = c;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= (uint32_t)o) inc += t;
+	}
+	const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+	{
+		uint32_t pos = inc - c, rest = bits;
+		while (rest)
+		{
+			sOffsets[warp][pos++] = (uint16_t)(lane * 32 + __ffs(rest) - 1);
+			rest &= rest - 1;
+		}
+	}
+	__syncwarp();
+	for (uint32_t j = lane; j < total; j += 32)
+	{
+		const uint32_t slot = b * kPreTile + sOffsets[warp][j];
+		A.surList[before + j] = slot;
+		A.surTs[before + j] = A.tslot[slot];
+	}
+	if (b == preBlocks - 1 && lane == 0)
+		A.counters[kCtrSurvivors + P.poolIndex] = before + total;
+}
 
 // ---- shared-memory cache of local matrices ----------------------------------------------------------------------------------
 // Leaf-first association (transform.hpp:204-210) forces every entity to multiply its own chain, but the chain's factors —
-// the ancestors' LOCAL matrices — are shared. Each WARP owns a tile of kWarpTile consecutive mesh slots and a private slice
-// of shared memory; it computes the local matrix of every transform its tile touches once (bit-identical to recomputing
-// it) and parks it in a direct-mapped cache keyed by transform slot. After the fill, every entry resolves
-// its parent link to a CACHE INDEX once (kLinkEnd = root, kLinkMiss = parent not cached), so a chain step in the hot loop
-// is: one 16-bit link load, three 128-bit matrix loads, 24 packed multiply-adds. Ancestors outside the tile (or evicted
-// by a conflicting slot) are recomputed from the SoA streams by the slow path.
+// the ancestors' LOCAL matrices — are shared. Each WARP owns a tile of kWarpTile consecutive SURVIVORS and a private slice
+// of shared memory holding kEntries local matrices: entry i < kWarpTile is the own transform of the tile's i-th survivor,
+// the rest is the ANCESTOR CLOSURE of the tile — every lane walks up its parent links and the first lane to meet a transform
+// that has no entry yet computes its local matrix (bit-identical wherever it is computed), so chains whose
+// ancestors live in another pool, or anywhere else in the transform pool, still run out of shared memory. A small hash
+// table (transform slot -> entry) is only used while the tile is set up: every entry then resolves its parent link to an
+// ENTRY INDEX once (kLinkEnd = root, kLinkMiss = no entry: table full), so a chain step in the hot loop is one 16-bit
+// link load, three 128-bit matrix loads, 24 packed multiply-adds. Entries are handed out in survivor order, so the lanes
+// of a warp — which walk neighbouring chains — read neighbouring entries (no bank conflicts on the 128-bit loads).
 // Warps never synchronise with each other (only __syncwarp): while one warp waits for its loads, the others compute.
-constexpr uint32_t kWarpTile = 64, kWarpItems = kWarpTile / 32;       // slots per warp tile, slots per lane
-constexpr uint32_t kCacheSize = 80, kHalo = 16; // >= tile + halo distinct slots; index = slot % kCacheSize
+constexpr uint32_t kWarpTile = 64, kWarpItems = kWarpTile / 32;       // survivors per warp tile, survivors per lane
+constexpr uint32_t kEntries = 88;                                     // kWarpTile own transforms + closure
+constexpr uint32_t kHalo = 16;                                        // survivors before the tile that may get an entry speculatively
+constexpr uint32_t kHashBits = 7, kHashSize = 1u << kHashBits, kHashProbes = 16;
+constexpr uint32_t kEntryNone = 0xFFu;
 constexpr uint32_t kDepthBins = 32;
-constexpr uint32_t kLinkEnd = 0xFFFFu, kLinkMiss = 0xFFFEu;
+constexpr uint32_t kLinkEnd = 0xFFFFu, kLinkMiss = 0xFFFEu, kLinkTodo = 0xFFFDu;
 constexpr uint32_t kDepthUnknown = kTfDepthMax; // chain-length hint saturates here: such chains take the guarded slow path
 static_assert(kWarpItems == 2, "work items are dealt as a deep half and a shallow half");
-static_assert(kCacheSize <= 96, "three cache entries per lane at most");
+static_assert(kEntries >= kWarpTile && kEntries < kEntryNone, "entry indices fit a byte");
 
 struct CullShared // one per warp
 {
-	float4 L[kCacheSize][3];    // per entry: row l = (c0[l], c1[l], c2[l], c3[l]); 48-byte stride: 128-bit accesses conflict-free
-	uint32_t tag[kCacheSize];   // transform slot held by the entry (kNone = empty)
-	uint32_t par[kCacheSize];   // its parent slot
-	float4 aabbA[kWarpTile];    // per owner slot: min xyz, max x
-	float2 aabbB[kWarpTile];    //                 max y, z
-	uint32_t ownTs[kWarpTile];  // per owner slot: transform slot (kNone = not a candidate)
+	float4 L[kEntries][3];      // per entry: row l = (c0[l], c1[l], c2[l], c3[l]); 48-byte stride: 128-bit accesses conflict-free
+	uint32_t hkey[kHashSize];   // hash table: transform slot (kNone = empty) ...
+	uint32_t par[kEntries];     // per entry: parent transform slot
+	uint32_t closure[kEntries - kWarpTile]; // transform slot of each closure entry (until its matrix has been computed)
+	float4 aabbA[kWarpTile];    // per owner: min xyz, max x
+	float2 aabbB[kWarpTile];    //            max y, z
+	uint32_t slotOf[kWarpTile]; // per owner: pool slot (kNone = past the end of the survivor list)
 	uint32_t hist[kDepthBins];
 	uint32_t inst[kMaxViews];
-	uint16_t lnk[kCacheSize];   // cache index of the parent's entry, kLinkEnd or kLinkMiss
-	uint16_t maskOf[kWarpTile]; // per owner slot: visibility bit per view
-	uint8_t perm[kWarpTile];    // work item -> owner slot, ordered by chain length (deepest first)
-	uint8_t ownSteps[kWarpTile]; // per owner slot: ancestors to multiply in (0 when modelWithAncestors == false)
+	uint32_t nEntries;
+	uint16_t lnk[kEntries];     // entry index of the parent's entry, kLinkEnd or kLinkMiss
+	uint16_t maskOf[kWarpTile]; // per owner: visibility bit per view
+	uint8_t hval[kHashSize];    // ... -> entry index (kEntryNone: the transform is known to have no entry)
+	uint8_t perm[kWarpTile];    // work item -> owner, ordered by chain length (deepest first)
+	uint8_t ownSteps[kWarpTile]; // per owner: ancestors to multiply in (0 when modelWithAncestors == false)
 };
+
+__device__ __forceinline__ uint32_t hashOf(uint32_t t) { return (t * 0x9E3779B1u) >> (32 - kHashBits); }
+
+// entry index of transform slot t, or kEntryNone
+__device__ __forceinline__ uint32_t cacheFind(const CullShared& sh, uint32_t t)
+{
+	uint32_t h = hashOf(t);
+	for (uint32_t i = 0; i < kHashProbes; i++)
+	{
+		const uint32_t k = sh.hkey[h];
+		if (k == t) return sh.hval[h];
+		if (k == kNone) return kEntryNone;
+		h = (h + 1) & (kHashSize - 1);
+	}
+	return kEntryNone;
+}
+// 0: the key was inserted by this call (the caller owns sh.hval[h]); 1: it was there already; 2: no room
+__device__ __forceinline__ int cacheClaim(CullShared& sh, uint32_t t, uint32_t& h)
+{
+	h = hashOf(t);
+	for (uint32_t i = 0; i < kHashProbes; i++)
+	{
+		const uint32_t old = atomicCAS(&sh.hkey[h], kNone, t);
+		if (old == kNone) return 0;
+		if (old == t) return 1;
+		h = (h + 1) & (kHashSize - 1);
+	}
+	return 2;
+}
 
 __device__ __forceinline__ Mat43 loadLocal43(const CullArgs& a, uint32_t t)
 {
@@ -90,12 +388,8 @@ __device__ __forceinline__ Mat43 loadLocal43(const CullArgs& a, uint32_t t)
 	return localModel43(p.x, p.y, p.z, q.x, q.y, q.z, q.w, p.w, s.x, s.y, (a.tFlags[t] & kTfExactLocal) != 0);
 }
 
-__device__ __forceinline__ void cacheInsert(CullShared& sh, uint32_t t, uint32_t parent, const Mat43& L)
+__device__ __forceinline__ void entryStore(CullShared& sh, uint32_t e, uint32_t parent, const Mat43& L)
 {
-	const uint32_t e = t % kCacheSize;
-	// claim the entry first: two slots of one tile may collide, and only the winner may write the payload
-	if (atomicCAS(&sh.tag[e], kNone, t) != kNone)
-		return;
 	#pragma unroll
 	for (int l = 0; l < 3; l++)
 		sh.L[e][l] = make_float4(L.c[0][l], L.c[1][l], L.c[2][l], L.c[3][l]);
@@ -114,12 +408,12 @@ __device__ __forceinline__ Mat43 cachedLocal(const CullShared& sh, uint32_t e)
 	return L;
 }
 
-// Local matrix + parent link of transform slot t: from the cache when it holds t, else recomputed from the SoA streams.
+// Local matrix + parent link of transform slot t: from its entry when it has one, else recomputed from the SoA streams.
 __device__ __forceinline__ Mat43 fetchLocal(const CullShared& sh, const CullArgs& a, uint32_t t, uint32_t& parent)
 {
-	const uint32_t e = t % kCacheSize;
+	const uint32_t e = cacheFind(sh, t);
 	Mat43 L;
-	if (sh.tag[e] == t)
+	if (e != kEntryNone)
 	{
 		L = cachedLocal(sh, e);
 		parent = sh.par[e];
@@ -150,74 +444,59 @@ static __device__ __forceinline__ void walkChainSlow(const CullShared& sh, const
 	}
 }
 
-// ---- conservative classification -------------------------------------------------------------------------------------------
-// The reference culls an entity for a view iff some plane has all eight transformed corners at d < 0 (aabb.hpp:452-462).
-// All corners lie in a sphere (centre cw, radius r) around the transformed box centre, so with unit-normal planes
-//   min_i (n_i . cw + d_i) < -(r + band)   =>  some plane has every corner certainly behind: culled;
-//   min_i (n_i . cw + d_i) >  (r + band)   =>  every plane has every corner certainly in front: visible;
-// anything else (the box straddles a plane, or NaN/Inf anywhere) runs the reference's exact 8-corner arithmetic, so the
-// boolean is identical by construction. `band` absorbs every rounding difference between this real-arithmetic argument
-// and the floats on either side: computed plane distances differ from real arithmetic by a few ulp of
-// |n|_1 * A + |d| (A bounds every |corner lane| and every partial sum of the corner transform); kBandR * A + kBandD * |d|
-// = 2^-15 * (sqrt(3) A + |d|) leaves a factor > 30 of head room over the ~2^-21 worst case.
-// Cost per plane: 3 FMA + 1 MIN (the view loop is unrolled, every plane constant is a constant-bank operand).
-constexpr float kBandR = 1.7321f / 32768.0f, kBandD = 1.0f / 32768.0f;
-
-__device__ __forceinline__ float sqrtApprox(float x)
-{
-	float r;
-	asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-	return r;
-}
-
-// One block = kCullWarps independent warps = kCullTile consecutive slots. Inside a warp tile the work items are ordered by
-// chain length (deepest first); lane i takes item i of the deep half and item i of the shallow half, so the warp walks
-// chains of similar length together and every lane carries about the same total.
-constexpr uint32_t kCullThreads = 128, kCullWarps = kCullThreads / 32;
-static_assert(kCullWarps * kWarpTile == kCullTile, "a block covers one kCullTile");
+// One block = kCullWarps independent warps; every warp walks the survivor list in tiles of kWarpTile with a grid stride.
+// Inside a tile the work items are ordered by chain length (deepest first); lane i takes item i of the deep half and item i
+// of the shallow half, so the warp walks chains of similar length together and every lane carries about the same total.
+constexpr uint32_t kCullThreads = 128, kCullWarps = kCullThreads / 32, kCullBlocksPerSM = 7;
+static_assert(kCullWarps * kWarpTile == kCullTile, "a block covers one kCullTile per round");
 
 template<uint32_t kViews>
-__global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+__global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
 {
 	__shared__ CullShared shAll[kCullWarps];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t tile = blockIdx.x * kCullWarps + warp; // warp tile
-	const uint32_t tileBase = tile * kWarpTile;
-	if (tileBase >= P.occupancy)
-	{
-		// past the end of the pool (the block's last warps): kScatter still reads this tile's ballot words
-		if (lane < P.viewCount)
-			for (uint32_t r = 0; r < kWarpItems; r++)
-				A.visBits[(size_t)lane * (A.tiles * (kCullTile / 32)) + tile * kWarpItems + r] = 0;
-		return; // (whole warp; nothing below synchronises across warps)
-	}
 	CullShared& sh = shAll[warp];
 	constexpr uint32_t kFull = 0xffffffffu;
+	const uint32_t survivors = A.counters[kCtrSurvivors + P.poolIndex];
+	const uint32_t tileCount = (survivors + kWarpTile - 1) / kWarpTile;
+	const uint32_t words = A.tiles * (kCullTile / 32);
 
-	for (uint32_t i = lane; i < kCacheSize; i += 32)
-		sh.tag[i] = kNone;
+	#pragma unroll 1
+	for (uint32_t tile = blockIdx.x * kCullWarps + warp; tile < tileCount; tile += gridDim.x * kCullWarps)
+	{
+	const uint32_t tileBase = tile * kWarpTile;
+	__syncwarp(); // the previous tile's readers are done with this warp's slice
+	for (uint32_t i = lane; i < kHashSize; i += 32)
+		sh.hkey[i] = kNone;
 	sh.hist[lane] = 0;
 	if (lane < kMaxViews)
 		sh.inst[lane] = 0;
+	if (lane == 0)
+		sh.nEntries = kWarpTile;
 	__syncwarp();
 
-	// ---- filter (mesh.cpp:140-155) + phase 1: local matrix of the own transform into the cache ----
-	// Both slots of the lane move through the two dependent load levels together (two round trips to memory, not four),
-	// and their local matrices are computed by straight-line code so the two dependency chains interleave.
-	uint32_t depthKey[kWarpItems], rankInBin[kWarpItems];
-	uint32_t firstTs = kNone, haloNeed = 0;
+	// ---- phase 1: local matrix of the own transform into entry `own` (every survivor passed the filter, mesh.cpp:140-155) ----
+	// Both survivors of the lane move through the dependent load levels together, and their local matrices are computed by
+	// straight-line code so the two dependency chains interleave.
+	uint32_t depthKey[kWarpItems], rankInBin[kWarpItems], steps[kWarpItems], parentLink[kWarpItems];
+	bool valid[kWarpItems];
+	// halo: the survivors right before the tile. Hierarchies survive the prepass as a whole and are usually laid out
+	// parent-first, so the ancestors of the tile's first chains are exactly these; their links are fetched together with
+	// the tile's own loads and `haloNeed` of them get an entry below without any walk.
+	uint32_t haloTs = kNone, haloParent = kNone, haloNeed = 0;
 	{
 		uint32_t ts[kWarpItems];
-		bool cand[kWarpItems];
+		if (lane < kHalo && tileBase > lane)
+			haloTs = A.surTs[tileBase - 1 - lane];
 		#pragma unroll
 		for (uint32_t r = 0; r < kWarpItems; r++)
 		{
 			const uint32_t own = lane + r * 32;
-			const uint32_t slot = tileBase + own;
-			const bool inRange = slot < P.occupancy;
-			cand[r] = inRange && (A.mflags[slot] & kMfCandidate);
-			ts[r] = inRange ? A.tslot[slot] : kNone;
-			if (inRange)
+			valid[r] = tileBase + own < survivors;
+			const uint32_t slot = valid[r] ? A.surList[tileBase + own] : kNone;
+			ts[r] = valid[r] ? A.surTs[tileBase + own] : kNone;
+			sh.slotOf[own] = slot;
+			if (valid[r])
 			{
 				sh.aabbA[own] = A.aabbA[slot];
 				sh.aabbB[own] = A.aabbB[slot];
@@ -226,65 +505,121 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		uint16_t tf[kWarpItems];
 		float4 tq[kWarpItems], tp[kWarpItems];
 		float2 tsyz[kWarpItems];
-		uint32_t parentLink[kWarpItems];
 		#pragma unroll
 		for (uint32_t r = 0; r < kWarpItems; r++)
 		{
-			// flags, TRS and parent link depend only on `ts`: all loads of both slots are issued together
+			// flags, TRS and parent link depend only on `ts`: all loads of both survivors are issued together
 			tf[r] = 0; tq[r] = make_float4(0.f, 0.f, 0.f, 1.f); tp[r] = make_float4(0.f, 0.f, 0.f, 1.f);
 			tsyz[r] = make_float2(1.f, 1.f); parentLink[r] = kNone;
-			if (ts[r] != kNone)
+			if (valid[r])
 			{
 				tf[r] = A.tFlags[ts[r]]; tq[r] = A.tRot[ts[r]]; tp[r] = A.tPosSx[ts[r]]; tsyz[r] = A.tSYZ[ts[r]];
 				parentLink[r] = A.tParent[ts[r]];
 			}
 		}
+		if (haloTs != kNone)
+			haloParent = A.tParent[haloTs];
 		Mat43 L[kWarpItems];
 		#pragma unroll
 		for (uint32_t r = 0; r < kWarpItems; r++)
 			localModel43Fast<false>(tp[r].x, tp[r].y, tp[r].z, tq[r].x, tq[r].y, tq[r].z, tq[r].w, tp[r].w, tsyz[r].x, tsyz[r].y, L[r]);
-		uint32_t steps[kWarpItems];
-		uint32_t myFirst = kNone;
 		#pragma unroll
 		for (uint32_t r = 0; r < kWarpItems; r++)
 		{
 			const uint32_t own = lane + r * 32;
-			const bool liveTransform = (tf[r] & kTfLive) != 0;
-			const bool c = cand[r] && liveTransform && (tf[r] & kTfActive);
-			if (liveTransform)
+			// Survivors are in slot order and hierarchies are usually laid out parent-first, so the parent of a survivor's
+			// transform is very often the transform of the survivor right before it: its entry is then own - 1, no lookup.
+			uint32_t prevTs = __shfl_up_sync(kFull, ts[r], 1);
+			if (r != 0)
+			{
+				const uint32_t wrap = __shfl_sync(kFull, ts[0], 31);
+				if (lane == 0) prevTs = wrap;
+			}
+			else if (lane == 0)
+				prevTs = kNone;
+			const bool parentIsPrev = valid[r] && parentLink[r] != kNone && parentLink[r] == prevTs;
+			if (valid[r])
 			{
 				if (tf[r] & kTfExactLocal) // zero / subnormal entries, out-of-range inputs: the exact 4-lane code (rare)
 					L[r] = localModel43Slow(tp[r].x, tp[r].y, tp[r].z, tq[r].x, tq[r].y, tq[r].z, tq[r].w, tp[r].w, tsyz[r].x, tsyz[r].y);
-				cacheInsert(sh, ts[r], parentLink[r], L[r]);
-				myFirst = min(myFirst, ts[r]);
+				entryStore(sh, own, parentLink[r], L[r]);
+				uint32_t h;
+				if (cacheClaim(sh, ts[r], h) == 0)
+					sh.hval[h] = (uint8_t)own;
+				sh.lnk[own] = (uint16_t)(parentLink[r] == kNone ? kLinkEnd : parentIsPrev ? own - 1 : kLinkTodo);
+			}
+			else
+			{
+				sh.par[own] = kNone;
+				sh.lnk[own] = (uint16_t)kLinkEnd;
 			}
 			// chain length (capped) orders the tile's work; modelWithAncestors == false means no walk at all (transform.hpp:200)
-			const bool walk = c && (tf[r] & kTfAncestors);
+			const bool walk = valid[r] && (tf[r] & kTfAncestors);
 			steps[r] = walk ? (uint32_t)(tf[r] >> kTfDepthShift) : 0u;
+			if (!walk || parentIsPrev) parentLink[r] = kNone; // (nothing to look for above this lane's item)
+			if (walk && steps[r] != kDepthUnknown && steps[r] > own)
+				haloNeed = max(haloNeed, steps[r] - own); // ancestors of a chain that starts before the tile
 			depthKey[r] = min(steps[r], kDepthBins - 1);
-			sh.ownTs[own] = c ? ts[r] : kNone;
 			sh.ownSteps[own] = (uint8_t)steps[r];
 			rankInBin[r] = atomicAdd(&sh.hist[depthKey[r]], 1u);
 		}
-		// chains that start before the tile: when transforms are laid out in hierarchy order their ancestors sit right before
-		// the tile's lowest transform slot; `haloNeed` of them are worth caching (anything else takes the slow path)
-		firstTs = __reduce_min_sync(kFull, myFirst);
-		uint32_t need = 0;
-		#pragma unroll
-		for (uint32_t r = 0; r < kWarpItems; r++)
-			if (steps[r] && ts[r] != kNone)
-				need = max(need, steps[r] > ts[r] - firstTs ? steps[r] - (ts[r] - firstTs) : 0u);
-		haloNeed = min(__reduce_max_sync(kFull, need), kHalo);
 	}
 	__syncwarp();
-	if (lane < haloNeed && firstTs != kNone && firstTs >= lane + 1)
+	// ---- ancestor closure: transforms on the tile's chains that have no entry yet (ancestors outside the tile: another pool,
+	// a parent that was culled by the prepass, a hierarchy that is not laid out in order). The first lane to claim a
+	// transform computes its local matrix; a lane that meets a claimed one stops (its claimer walks on from there).
+	// Three steps, so that the matrices are computed by all lanes at once: (h) the halo survivors claim entries without any
+	// walk; (a) every lane whose parent is still unknown walks the links, claims entries and notes the transform slot of each
+	// new entry (with the halo in place this finds everything present in an ordered hierarchy); (b) one local matrix per lane.
+	haloNeed = min(__reduce_max_sync(kFull, haloNeed), kHalo);
+	if (lane < haloNeed && haloTs != kNone)
 	{
-		const uint32_t h = firstTs - 1 - lane;
-		if (sh.tag[h % kCacheSize] == kNone && (A.tFlags[h] & kTfLive)) // (racing claims are settled by the CAS)
+		uint32_t h;
+		if (cacheClaim(sh, haloTs, h) == 0)
 		{
-			Mat43 H = loadLocal43(A, h);
-			cacheInsert(sh, h, A.tParent[h], H);
+			const uint32_t e = atomicAdd(&sh.nEntries, 1u);
+			if (e < kEntries)
+			{
+				sh.hval[h] = (uint8_t)e;
+				sh.closure[e - kWarpTile] = haloTs;
+				sh.par[e] = haloParent;
+				sh.lnk[e] = (uint16_t)(haloParent == kNone ? kLinkEnd : kLinkTodo);
+			}
+			else
+				sh.hval[h] = (uint8_t)kEntryNone;
 		}
+	}
+	__syncwarp();
+	#pragma unroll 1
+	for (uint32_t r = 0; r < kWarpItems; r++)
+	{
+		uint32_t p = parentLink[r];
+		for (uint32_t budget = steps[r]; p != kNone && budget != 0; budget--)
+		{
+			uint32_t h;
+			if (cacheClaim(sh, p, h) != 0)
+				break;
+			const uint32_t e = atomicAdd(&sh.nEntries, 1u);
+			if (e >= kEntries)
+			{
+				sh.hval[h] = (uint8_t)kEntryNone; // known, but no room: chains through it finish on the generic path
+				break;
+			}
+			sh.hval[h] = (uint8_t)e;
+			sh.closure[e - kWarpTile] = p;
+			const uint32_t next = A.tParent[p];
+			sh.par[e] = next;
+			sh.lnk[e] = (uint16_t)(next == kNone ? kLinkEnd : kLinkTodo);
+			p = next;
+		}
+	}
+	__syncwarp();
+	for (uint32_t e = kWarpTile + lane; e < min(sh.nEntries, kEntries); e += 32)
+	{
+		const Mat43 H = loadLocal43(A, sh.closure[e - kWarpTile]);
+		#pragma unroll
+		for (int l = 0; l < 3; l++)
+			sh.L[e][l] = make_float4(H.c[0][l], H.c[1][l], H.c[2][l], H.c[3][l]);
 	}
 	{
 		// exclusive scan of the depth histogram, deepest chains first: lane i owns bin (kDepthBins - 1 - i)
@@ -305,20 +640,17 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		}
 	}
 	__syncwarp();
-	// parent links as cache indices (once per entry instead of once per chain step)
-	for (uint32_t e = lane; e < kCacheSize; e += 32)
+	// parent links as entry indices (once per entry instead of once per chain step)
 	{
-		uint32_t link = kLinkEnd;
-		if (sh.tag[e] != kNone)
+		const uint32_t n = min(sh.nEntries, kEntries);
+		for (uint32_t e = lane; e < n; e += 32)
 		{
-			const uint32_t p = sh.par[e];
-			if (p != kNone)
+			if (sh.lnk[e] == kLinkTodo) // (the others were settled when the entry was made)
 			{
-				const uint32_t pe = p % kCacheSize;
-				link = sh.tag[pe] == p ? pe : kLinkMiss;
+				const uint32_t pe = cacheFind(sh, sh.par[e]);
+				sh.lnk[e] = (uint16_t)(pe != kEntryNone ? pe : kLinkMiss);
 			}
 		}
-		sh.lnk[e] = (uint16_t)link;
 	}
 	__syncwarp();
 
@@ -327,9 +659,8 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 	for (uint32_t r = 0; r < kWarpItems; r++)
 	{
 		const uint32_t owner = sh.perm[r * 32 + lane];
-		const uint32_t wslot = tileBase + owner;
-		const uint32_t wts = sh.ownTs[owner];
-		const bool work = wts != kNone;
+		const uint32_t wslot = sh.slotOf[owner];
+		const bool work = wslot != kNone;
 		uint32_t mask = 0;
 
 		// ---- phase 2: world matrix, leaf-first chain product (transform.hpp:199-211) ----
@@ -341,19 +672,19 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		if (work)
 		{
 			const uint32_t steps = sh.ownSteps[owner];
-			uint32_t e = wts % kCacheSize;
+			uint32_t e = owner;
 			uint32_t slowFrom = kNone; // transform slot the slow path continues from
 			bool slow = false;
-			if (sh.tag[e] == wts && steps != kDepthUnknown)
+			if (steps != kDepthUnknown)
 			{
-				Mat43P Mp; // column pairs straight out of the row-major cache entry
+				Mat43P Mp; // column pairs straight out of the row-major entry
 				#pragma unroll
 				for (int l = 0; l < 3; l++)
 				{
 					const float4 a = sh.L[e][l];
 					Mp.p[l][0] = pack2(a.x, a.y); Mp.p[l][1] = pack2(a.z, a.w);
 				}
-				uint32_t link = sh.lnk[e];
+				uint32_t link = steps ? (uint32_t)sh.lnk[e] : kLinkEnd;
 				#pragma unroll 2
 				for (uint32_t s = 0; s < steps && link < kLinkMiss; s++)
 				{
@@ -363,17 +694,16 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 					link = sh.lnk[e];
 				}
 				M = unpairMat(Mp);
-				// the hint and the links agree unless the parent is not cached (or the hint is stale): finish generically
-				if (link != kLinkEnd && steps != 0)
+				// the hint and the links agree unless an ancestor has no entry (or the hint is stale): finish generically
+				if (link != kLinkEnd)
 				{
 					slow = true; slowFrom = sh.par[e];
 				}
 			}
 			else
 			{
-				uint32_t p;
-				M = fetchLocal(sh, A, wts, p);
-				slow = steps != 0; slowFrom = p;
+				M = cachedLocal(sh, e);
+				slow = true; slowFrom = sh.par[e];
 			}
 			if (slow)
 				walkChainSlow(sh, A, slowFrom, M);
@@ -431,13 +761,7 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 			if (v < P.viewCount) // warp-uniform
 			{
 				const ViewConst& V = P.views[v];
-				// planes (2j, 2j+1) share one packed FMA chain; slots past planeCount are neutral (+inf)
-				f32x2 d[3];
-				#pragma unroll
-				for (int j = 0; j < 3; j++)
-					d[j] = fma2(pack2(V.ux[j].x, V.ux[j].y), pack2(cw[0], cw[0]), fma2(pack2(V.uy[j].x, V.uy[j].y), pack2(cw[1], cw[1]),
-						fma2(pack2(V.uz[j].x, V.uz[j].y), pack2(cw[2], cw[2]), pack2(V.ud[j].x, V.ud[j].y))));
-				const float dmin = fminf(fminf(fminf(lo2(d[0]), hi2(d[0])), fminf(lo2(d[1]), hi2(d[1]))), fminf(lo2(d[2]), hi2(d[2])));
+				const float dmin = minPlaneDistance(V, cw[0], cw[1], cw[2]);
 				const float t = reach + V.slack;
 				const bool front = dmin > t, behind = dmin < -t;
 				if (V.enabled)
@@ -486,7 +810,7 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 		}
 		if (mask) // bakedModel = (float4x3)model (mesh.cpp:171,249)
 		{
-			float4* w = A.world + (size_t)wslot * kWorldStride;
+			float4* w = A.world + (size_t)(tileBase + owner) * kWorldStride;
 			w[0] = make_float4(M.c[0][0], M.c[0][1], M.c[0][2], M.c[1][0]);
 			w[1] = make_float4(M.c[1][1], M.c[1][2], M.c[2][0], M.c[2][1]);
 			w[2] = make_float4(M.c[2][2], M.c[3][0], M.c[3][1], M.c[3][2]);
@@ -501,19 +825,17 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 	}
 	__syncwarp();
 
-	// ---- back to slot order: isVisible, one ballot word per 32 slots and view, the tile's visible count per view ----
+	// ---- back to survivor order: isVisible, one ballot word per 32 survivors and view, the tile's visible count per view ----
 	// (no inter-tile dependency in this kernel: list positions are assigned by kScanChunks + kScatter below)
-	const uint32_t words = A.tiles * (kCullTile / 32);
-	uint32_t visibleCount = 0; // lane v: visible slots of the tile in view v
+	uint32_t visibleCount = 0; // lane v: visible survivors of the tile in view v
 	#pragma unroll
 	for (uint32_t r = 0; r < kWarpItems; r++)
 	{
 		const uint32_t own = lane + r * 32;
-		const uint32_t slot = tileBase + own;
 		const uint32_t mask = sh.maskOf[own];
-		// isVisible of the (last) main view, written for every slot like mesh.cpp:144-146,152-153,161-167
-		if (A.visibleView != kNone && slot < P.occupancy)
-			A.visible[slot] = (uint8_t)((mask >> A.visibleView) & 1u);
+		// isVisible of the (last) main view: the prepass stored 0 for every slot, the visible survivors get their 1 here
+		if (A.visibleView != kNone && ((mask >> A.visibleView) & 1u))
+			A.visible[sh.slotOf[own]] = 1;
 		uint32_t mine = 0; // lane v keeps the ballot word of view v
 		#pragma unroll
 		for (uint32_t v = 0; v < kViews; v++)
@@ -531,10 +853,11 @@ __global__ void __launch_bounds__(kCullThreads, 8) kCull(const __grid_constant__
 	{
 		// visible slots per chunk of kChunkTiles tiles: the only cross-tile quantity the compaction needs
 		if (visibleCount)
-			atomicAdd(&A.chunkCount[(size_t)lane * A.chunks + tileBase / (kChunkTiles * kCullTile)], visibleCount);
+			atomicAdd(&A.chunkCount[(size_t)lane * A.chunks + tileBase / kChunkItems], visibleCount);
 		if (P.hasReady && sh.inst[lane])
 			atomicAdd(&A.counters[ctrPoolInst(P.poolIndex, lane)], sh.inst[lane]);
 	}
+	} // tile loop
 }
 
 // Exclusive scan of the per-chunk visible counts of one view (one block per view) -> list offset of every chunk.
@@ -549,13 +872,14 @@ __global__ void __launch_bounds__(kScanThreads) kScanChunks(const __grid_constan
 	__shared__ uint32_t sCarry;
 	uint32_t* counts = A.chunkCount + (size_t)v * A.chunks;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t chunks = (A.counters[kCtrSurvivors + P.poolIndex] + kChunkItems - 1) / kChunkItems; // chunks that hold survivors
 	if (threadIdx.x == 0)
 		sCarry = A.baseCounter[v] != kNone ? A.counters[A.baseCounter[v]] : 0;
 	__syncthreads();
-	for (uint32_t base = 0; base < A.chunks; base += kScanThreads)
+	for (uint32_t base = 0; base < chunks; base += kScanThreads)
 	{
 		const uint32_t i = base + threadIdx.x;
-		const uint32_t c = i < A.chunks ? counts[i] : 0;
+		const uint32_t c = i < chunks ? counts[i] : 0;
 		uint32_t inc = c;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
@@ -580,7 +904,7 @@ __global__ void __launch_bounds__(kScanThreads) kScanChunks(const __grid_constan
 		__syncthreads();
 		const uint32_t carry = sCarry;
 		const uint32_t exclusive = carry + sWarp[warp] + inc - c;
-		if (i < A.chunks)
+		if (i < chunks)
 			counts[i] = exclusive;
 		__syncthreads();
 		if (threadIdx.x == kScanThreads - 1)
@@ -611,18 +935,21 @@ __global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constan
 		sHistDyn[i] = 0;
 	__syncthreads();
 	const uint32_t words = A.tiles * (kCullTile / 32);
-	const uint32_t units = A.chunks * P.viewCount;
+	const uint32_t survivors = A.counters[kCtrSurvivors + P.poolIndex];
+	const uint32_t liveWords = ((survivors + kWarpTile - 1) / kWarpTile) * kWarpItems; // ballot words kCull wrote
+	const uint32_t chunks = (survivors + kChunkItems - 1) / kChunkItems;
+	const uint32_t units = chunks * P.viewCount;
 	for (uint32_t u = blockIdx.x * kScatterWarps + warp; u < units; u += gridDim.x * kScatterWarps)
 	{
-		// chunks are walked from the END of the pool: the world matrices kCull wrote last are still in L2 when this kernel
+		// chunks are walked from the END of the list: the world matrices kCull wrote last are still in L2 when this kernel
 		// starts, the ones it wrote first were evicted long ago either way (list positions come from the scan, not the order)
-		const uint32_t v = u % P.viewCount, chunk = A.chunks - 1 - u / P.viewCount;
+		const uint32_t v = u % P.viewCount, chunk = chunks - 1 - u / P.viewCount;
 		const ViewConst& V = P.views[v];
 		if (!V.enabled) // warp-uniform
 			continue;
 		const uint32_t firstWord = chunk * kChunkWords + lane * kWordsPerLane;
 		uint2 w = make_uint2(0u, 0u);
-		if (firstWord + kWordsPerLane <= words) // (words is a multiple of 8: kCullTile / 32 words per tile)
+		if (firstWord + kWordsPerLane <= liveWords) // (kCull writes kWarpItems == kWordsPerLane words per warp tile)
 			w = *reinterpret_cast<const uint2*>(A.visBits + (size_t)v * words + firstWord);
 		const uint32_t sum = __popc(w.x) + __popc(w.y);
 		uint32_t inc = sum;
@@ -668,7 +995,7 @@ __global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constan
 			for (uint32_t b = 0; b < kGatherBatch; b++)
 			{
 				const uint32_t j = j0 + 32 * b;
-				slot[b] = chunk * (kChunkWords * 32) + (j < total ? sList[warp][j] : sList[warp][j0]);
+				slot[b] = chunk * kChunkItems + (j < total ? sList[warp][j] : sList[warp][j0]); // (a survivor index)
 				w2[b] = A.world[(size_t)slot[b] * kWorldStride + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
 			}
 			#pragma unroll
@@ -750,7 +1077,22 @@ static void prepareClassifier(ViewConst& V)
 	V.slack = forceExact ? inf : maxAbsD * kBandD * 1.0001f;
 }
 
-uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter)
+// Prepass spheres of every transform: once per change of transforms, pools or active flags (after launchLink: needs rho)
+uint32_t launchChainBounds(Context& c)
+{
+	auto& t = c.tf;
+	if (t.occupancy == 0)
+		return 0;
+	ChainArgs A;
+	A.bound = t.bound; A.parent = t.parent; A.flags = t.flags; A.posSx = t.posSx; A.rho = t.rho;
+	A.chainRoot = t.chainRoot; A.rootW = t.rootW; A.record = t.record; A.count = t.occupancy;
+	cudaMemsetAsync(t.rootW, 0, (size_t)t.occupancy * sizeof(uint32_t), c.stream);
+	kChainBounds<<<(t.occupancy + 255) / 256, 256, 0, c.stream>>>(A);
+	kChainRecords<<<(t.occupancy + 255) / 256, 256, 0, c.stream>>>(A);
+	return 2;
+}
+
+uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEvent_t afterCull, cudaEvent_t afterScatter)
 {
 	auto& p = c.pools[pool];
 	c.poolLaunched[pool] = false;
@@ -796,15 +1138,19 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	P.hasReady = p.hasReady ? 1 : 0;
 
 	A.tRot = c.tf.rot; A.tPosSx = c.tf.posSx; A.tSYZ = c.tf.sYZ; A.tParent = c.tf.parent; A.tFlags = c.tf.flags;
+	A.tRecord = c.tf.record;
 	A.aabbA = p.aabbA; A.aabbB = p.aabbB; A.tslot = p.tslot; A.mflags = p.flags; A.ready = p.ready;
-	A.world = p.world; A.visible = p.visible;
+	A.surList = p.surList; A.surTs = p.surTs; A.world = p.world; A.visible = p.visible;
 	A.visBits = p.visBits; A.chunkCount = p.cullStatus; A.counters = c.dCounters;
 	A.keys = c.keys[0]; A.payloads = c.payloads[0]; A.sortHist = c.sortHist;
+	A.surBits = p.surBits; A.blockCount = p.blockCount; A.bucketCount = p.bucketCount;
 	A.tiles = (p.occupancy + kCullTile - 1) / kCullTile;
 	A.chunks = (A.tiles + kChunkTiles - 1) / kChunkTiles;
+	static const bool prepassOff = []{ const char* e = getenv("GSP_PREPASS"); return e && !strcmp(e, "0"); }();
+	A.prepassCull = prepassOff ? 0u : 1u;
 	p.visibleValid = A.visibleView != kNone;
 
-	// 8 resident blocks x 27 KB of shared memory need the large carve-out (function attributes are per device, and one
+	// 7 resident blocks x 31 KB of shared memory need the large carve-out (function attributes are per device, and one
 	// context = one device, so the flag lives in the context)
 	if (!c.cullAttrsSet)
 	{
@@ -819,15 +1165,25 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 		c.cullAttrsSet = true;
 	}
 	cudaMemsetAsync(p.cullStatus, 0, (size_t)A.chunks * kMaxViews * sizeof(uint32_t), c.stream);
-	// the view loop is unrolled at compile time (plane constants become direct constant-bank operands)
-	if (P.viewCount <= 1) kCull<1><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
-	else if (P.viewCount <= 2) kCull<2><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
-	else if (P.viewCount <= 3) kCull<3><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
-	else if (P.viewCount <= 4) kCull<4><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
-	else if (P.viewCount <= 5) kCull<5><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A); // camera + 4 cascades
-	else if (P.viewCount <= 6) kCull<6><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
-	else if (P.viewCount <= 8) kCull<8><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
-	else kCull<16><<<A.tiles, kCullThreads, 0, c.stream>>>(P, A);
+	// the view loops are unrolled at compile time (plane constants become direct constant-bank operands)
+	const uint32_t preBlocks = (p.occupancy + kPreTile - 1) / kPreTile;
+	cudaMemsetAsync(p.bucketCount, 0, ((size_t)preBlocks / kPreBucket + 1) * sizeof(uint32_t), c.stream);
+	// kCull is persistent: its warps stride over the survivor tiles (the survivor count only exists on the device)
+	const uint32_t cullBlocks = std::max(1u, std::min(A.tiles, c.smCount * kCullBlocksPerSM));
+	#define GSP_LAUNCH_CULL(V) do { \
+		kPrepass<V><<<preBlocks, kPreThreads, 0, c.stream>>>(P, A); \
+		kCompactSurvivors<<<(preBlocks + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, c.stream>>>(P, A, preBlocks); \
+		if (afterPrepass) cudaEventRecord(afterPrepass, c.stream); \
+		kCull<V><<<cullBlocks, kCullThreads, 0, c.stream>>>(P, A); } while (0)
+	if (P.viewCount <= 1) GSP_LAUNCH_CULL(1);
+	else if (P.viewCount <= 2) GSP_LAUNCH_CULL(2);
+	else if (P.viewCount <= 3) GSP_LAUNCH_CULL(3);
+	else if (P.viewCount <= 4) GSP_LAUNCH_CULL(4);
+	else if (P.viewCount <= 5) GSP_LAUNCH_CULL(5); // camera + 4 cascades
+	else if (P.viewCount <= 6) GSP_LAUNCH_CULL(6);
+	else if (P.viewCount <= 8) GSP_LAUNCH_CULL(8);
+	else GSP_LAUNCH_CULL(16);
+	#undef GSP_LAUNCH_CULL
 	if (afterCull) cudaEventRecord(afterCull, c.stream);
 	kScanChunks<<<P.viewCount, kScanThreads, 0, c.stream>>>(P, A);
 	{
@@ -844,7 +1200,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_
 	}
 	if (afterScatter) cudaEventRecord(afterScatter, c.stream);
 	c.poolLaunched[pool] = true;
-	return 3;
+	return 5;
 }
 
 } // namespace gsp

@@ -16,9 +16,10 @@ struct EmitArgs
 	const SegmentDev* __restrict__ segments;
 	const uint32_t* __restrict__ counters;
 	const uint32_t* __restrict__ keys;
-	const uint32_t* __restrict__ payloads;
+	uint32_t* __restrict__ payloads;      // in: pool << 28 | survivor index; out: pool << 28 | slot (what the exchange exports)
 	gsp_record* __restrict__ records;
-	const float4* world[kMaxPools];
+	const float4* world[kMaxPools];       // per survivor (compact)
+	const uint32_t* surList[kMaxPools];   // survivor index -> slot
 	uint32_t stride[kMaxPools];
 	uint32_t bufferIndex[kMaxViews][kMaxPools];
 	uint32_t segView[kMaxViews * kMaxPools];
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(kEmitThreads) kEmit(const __grid_constant__ Em
 		const uint32_t count = A.counters[seg.countIndex];
 		const uint32_t view = A.segView[segIndex];
 		const uint32_t* __restrict__ keys = A.keys + seg.offset;
-		const uint32_t* __restrict__ payloads = A.payloads + seg.offset;
+		uint32_t* __restrict__ payloads = A.payloads + seg.offset;
 		float4* __restrict__ out = reinterpret_cast<float4*>(A.records + seg.offset);
 		const uint32_t base = (g - (segIndex ? sGroupEnd[segIndex - 1] : 0u)) * kGroup;
 		// kEmitUnroll independent records per lane group: all list reads, then all gathers, then all stores, so that
@@ -76,20 +77,28 @@ __global__ void __launch_bounds__(kEmitThreads) kEmit(const __grid_constant__ Em
 			}
 		}
 		float4 w[kEmitUnroll];
+		uint32_t slotOf[kEmitUnroll]; // lane 3 of the group resolves the survivor index to the pool slot
 		#pragma unroll
 		for (uint32_t r = 0; r < kEmitUnroll; r++)
 		{
 			const uint32_t j = base + r * kEmitRecordsPerIter + (threadIdx.x >> 2);
-			const uint32_t pool = payload[r] >> 28, slot = payload[r] & 0x0FFFFFFFu;
+			const uint32_t pool = payload[r] >> 28, index = payload[r] & 0x0FFFFFFFu;
 			w[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (j < count && q < 3)
-				w[r] = A.world[pool][(size_t)slot * kWorldStride + q];
+			slotOf[r] = 0;
+			if (j < count)
+			{
+				if (q < 3)
+					w[r] = A.world[pool][(size_t)index * kWorldStride + q];
+				else
+					slotOf[r] = A.surList[pool][index];
+			}
 		}
 		#pragma unroll
 		for (uint32_t r = 0; r < kEmitUnroll; r++)
 		{
 			const uint32_t j = base + r * kEmitRecordsPerIter + (threadIdx.x >> 2);
-			const uint32_t pool = payload[r] >> 28, slot = payload[r] & 0x0FFFFFFFu;
+			const uint32_t pool = payload[r] >> 28;
+			const uint32_t slot = __shfl_sync(0xffffffffu, slotOf[r], (threadIdx.x & 28u) | 3u);
 			const float pz = __shfl_up_sync(0xffffffffu, w[r].z, 1);
 			const float pw = __shfl_up_sync(0xffffffffu, w[r].w, 1);
 			float4 o;
@@ -104,7 +113,11 @@ __global__ void __launch_bounds__(kEmitThreads) kEmit(const __grid_constant__ Em
 			else
 				o = make_float4(pz, pw, orderedToFloat(seg.descending ? ~k[r] : k[r]), __uint_as_float(A.bufferIndex[view][pool]));
 			if (j < count)
+			{
 				out[(size_t)j * 4 + q] = o;
+				if (q == 3)
+					payloads[j] = (pool << 28) | slot; // the run now names slots (gsp_export_runs*, gsp_get_sorted_run_device)
+			}
 		}
 	}
 }
@@ -123,6 +136,7 @@ uint32_t launchEmit(Context& c)
 	for (uint32_t p = 0; p < c.poolCount; p++)
 	{
 		A.world[p] = c.pools[p].world;
+		A.surList[p] = c.pools[p].surList;
 		A.stride[p] = c.pools[p].stride;
 	}
 	for (uint32_t v = 0; v < (uint32_t)c.views.size(); v++)

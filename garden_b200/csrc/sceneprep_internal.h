@@ -48,6 +48,17 @@ struct TransformsDev
 	uint32_t* entity = nullptr; // owner entity id (0 = free slot)
 	uint32_t* parentEntity = nullptr;
 	uint16_t* flags = nullptr;
+	// conservative bound inputs of the prepass (cull.cu): x = largest |scale| component, y = |position|, both rounded up by
+	// 2^-10; x = +inf for transforms whose local matrix needs the guarded code (the prepass then never culls below them)
+	float2* bound = nullptr;
+	// Prepass sphere of every mesh on this transform (kChainBounds + kChainRecords, refreshed whenever transforms, pools or
+	// active flags changed): xyz = centre (the chain root's position), w = radius W >= 0 — ONE sphere per hierarchy (the
+	// largest bound of any mesh below the root), so a hierarchy survives or is dropped as a whole; w < 0: the transform is
+	// dead or inactive (never a candidate); w = +inf / NaN: never culled by the prepass.
+	float4* record = nullptr;
+	uint32_t* rho = nullptr;       // bits of the largest box radius of any mesh on the transform (kLinkPool)
+	uint32_t* chainRoot = nullptr; // root slot of the transform's parent chain
+	uint32_t* rootW = nullptr;     // per ROOT slot: bits of max over its hierarchy of D + S * rho
 	uint32_t* entityToSlot = nullptr; // entity id -> slot + 1
 	uint32_t entityCap = 0;
 };
@@ -63,10 +74,18 @@ struct PoolDev
 	uint32_t* tslot = nullptr; // transform slot or kNone (resolved by the link kernel)
 	uint8_t* flags = nullptr;
 	uint8_t* ready = nullptr;
-	float4* world = nullptr;   // kWorldStride x float4 per slot: float4x3 world matrix (c0..c3 lanes xyz) in the first three, written for visible slots
+	float* radius = nullptr;   // per slot: distance of the farthest AABB corner from the local origin, rounded up (prepass)
+	// ---- per frame. The prepass compacts the slots that survive the filter and its conservative bound into a list in slot
+	// order; everything downstream (world matrices, ballots, chunks, payloads) is indexed by SURVIVOR INDEX ----
+	uint32_t* surList = nullptr;  // survivor index -> slot
+	uint32_t* surTs = nullptr;    // survivor index -> transform slot
+	float4* world = nullptr;   // kWorldStride x float4 per SURVIVOR: float4x3 world matrix (c0..c3 lanes xyz), written when visible anywhere
 	uint8_t* visible = nullptr; // isVisible of the last main view, per slot
-	uint32_t* cullStatus = nullptr; // [kMaxViews][tiles] visible count per tile and view, scanned in place to list offsets
-	uint32_t* visBits = nullptr;    // [kMaxViews][tiles * 8] visibility ballot words
+	uint32_t* cullStatus = nullptr; // [kMaxViews][chunks] visible count per chunk of survivors and view, scanned in place to list offsets
+	uint32_t* visBits = nullptr;    // [kMaxViews][tiles * 8] visibility ballot words over survivor indices
+	uint32_t* surBits = nullptr;     // [prepass blocks][32] survivor bit per slot
+	uint32_t* blockCount = nullptr;  // [prepass blocks]
+	uint32_t* bucketCount = nullptr; // [prepass blocks / 64 + 1]
 	uint32_t cullTiles = 0, cullTilesCap = 0;
 	bool visibleValid = false;
 };
@@ -134,6 +153,7 @@ struct Context
 	std::vector<gsp_view> views;
 	float cameraPos[3] = {0, 0, 0};
 	bool viewsSet = false, linkDirty = true, layoutDirty = true, resultsValid = false;
+	bool chainDirty = true; // the transform pool changed since kChainBounds last ran
 	bool cullAttrsSet = false, scatterAttrSet = false; // kernel function attributes applied on this context's device
 	bool frameEnqueued = false; // a frame has been enqueued since the last structural change (its results may still be in flight)
 
@@ -172,7 +192,7 @@ struct Context
 	uint32_t launchCount = 0;
 	bool profiling = false;
 	cudaEvent_t phaseEvents[8] = {};
-	cudaEvent_t poolEvents[kMaxPools][2] = {};
+	cudaEvent_t poolEvents[kMaxPools][3] = {}; // after the prepass, after kCull, after the scatter
 	bool poolLaunched[kMaxPools] = {};
 	bool phaseEventsCreated = false, phaseTimesValid = false;
 	uint32_t* dError = nullptr;
@@ -181,14 +201,16 @@ struct Context
 // counters layout helpers
 __host__ __device__ inline uint32_t ctrPoolEnd(uint32_t pool, uint32_t view) { return pool * kMaxViews + view; }
 __host__ __device__ inline uint32_t ctrPoolInst(uint32_t pool, uint32_t view) { return kMaxPools * kMaxViews + pool * kMaxViews + view; }
-constexpr uint32_t kCtrCullTicket = 2 * kMaxPools * kMaxViews; // + pool
-constexpr uint32_t kCtrError = kCtrCullTicket + kMaxPools;
+constexpr uint32_t kCtrCullTicket = 2 * kMaxPools * kMaxViews; // + pool (unused)
+constexpr uint32_t kCtrSurvivors = kCtrCullTicket + kMaxPools;  // + pool: survivors of the prepass
+constexpr uint32_t kCtrError = kCtrSurvivors + kMaxPools;
 constexpr uint32_t kCtrCount = kCtrError + 8;
 
 // float4 per slot in PoolDev::world: the 48-byte matrix, unpadded. (Padding it to one 64-byte DRAM line was measured and is
 // slower: neighbouring slots are usually visible together and then share lines; 0.980 -> 1.012 ms per frame on C4.)
 constexpr uint32_t kWorldStride = 3;
-constexpr uint32_t kCullTile = 256;       // slots per cull tile (= threads per block)
+constexpr uint32_t kCullTile = 256;       // survivors per cull block (4 warp tiles of 64)
+constexpr uint32_t kPreTile = 1024;       // slots per prepass block
 constexpr uint32_t kSortItems = 16;       // keys per thread in the radix sort
 constexpr uint32_t kSortThreads = 256;
 constexpr uint32_t kSortTile = kSortItems * kSortThreads;
@@ -203,7 +225,8 @@ uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, ui
 uint32_t launchBuildHierarchy(Context& c);
 uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy);
 uint32_t launchLink(Context& c);
-uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterCull, cudaEvent_t afterScatter);
+uint32_t launchChainBounds(Context& c);
+uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEvent_t afterCull, cudaEvent_t afterScatter);
 uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);
 uint32_t launchInstances(Context& c, int seg, const float* viewProj, void* dDst, uint32_t stride, uint32_t offset, uint32_t capacity);

@@ -68,7 +68,7 @@ __device__ __forceinline__ void loadTile(uint8_t* sTile, const uint8_t* __restri
 // entity id); the entity -> slot map is built from the SoA copy afterwards (kBuildEntityMap), once its size is known.
 __global__ void __launch_bounds__(kStageThreads) kStageTransforms(const uint8_t* __restrict__ aos, uint32_t stride,
 	uint32_t first, uint32_t count, int full, uint32_t tileSlots, float4* __restrict__ rot, float4* __restrict__ posSx,
-	float2* __restrict__ sYZ, uint16_t* __restrict__ flags, uint32_t* __restrict__ entity,
+	float2* __restrict__ sYZ, uint16_t* __restrict__ flags, float2* __restrict__ bound, uint32_t* __restrict__ entity,
 	uint32_t* __restrict__ parentEntity, uint32_t* __restrict__ maxEntity, const uint32_t* __restrict__ slotMap)
 {
 	extern __shared__ __align__(16) uint8_t sTile[];
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kStageThreads) kStageTransforms(const uint8_t*
 		Mat43 unused;
 		if (!localModel43Fast<true>(ps.x, ps.y, ps.z, q.x, q.y, q.z, q.w, ps.w, syz.x, syz.y, unused))
 			f |= kTfExactLocal; // the per-frame kernel must use the guarded 4-lane code for this transform
+		bound[slot] = transformBound(ps.x, ps.y, ps.z, ps.w, syz.x, syz.y, q.x, q.y, q.z, q.w);
 		if (e) f |= kTfLive;
 		if (w & 0xffu) f |= kTfSelfBit;
 		if (w & 0xff00u) f |= kTfAncBit;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) kComputeDepth(uint32_t count, const uint3
 // isVisible byte the host currently holds (for the changed-slots-only write-back).
 __global__ void __launch_bounds__(kStageThreads) kStagePool(const uint8_t* __restrict__ aos, uint32_t stride, uint32_t count,
 	uint32_t tileSlots, float4* __restrict__ aabbA, float2* __restrict__ aabbB, uint32_t* __restrict__ entity,
-	uint8_t* __restrict__ flags)
+	uint8_t* __restrict__ flags, float* __restrict__ radius)
 {
 	extern __shared__ __align__(16) uint8_t sTile[];
 	const uint32_t tileFirst = blockIdx.x * tileSlots;
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(kStageThreads) kStagePool(const uint8_t* __res
 		float mxx = ldF32(m + kMcAabbMax), mxy = ldF32(m + kMcAabbMax + 4), mxz = ldF32(m + kMcAabbMax + 8);
 		aabbA[i] = make_float4(mnx, mny, mnz, mxx);
 		aabbB[i] = make_float2(mxy, mxz);
+		radius[i] = aabbRadiusBound(mnx, mny, mnz, mxx, mxy, mxz);
 		entity[i] = e;
 		// aabb.getSize() = max - min, fixW(), areAllTrue(size <= 0)  (mesh.cpp:140-142, aabb.hpp:142)
 		bool degenerate = (__fsub_rn(mxx, mnx) <= 0.0f) && (__fsub_rn(mxy, mny) <= 0.0f) && (__fsub_rn(mxz, mnz) <= 0.0f);
@@ -194,8 +196,12 @@ __global__ void __launch_bounds__(kStageThreads) kStagePool(const uint8_t* __res
 	}
 }
 
+// Also folds the slot's box radius into its transform's `rho` (largest radius of any mesh on the transform, over all pools):
+// radii are >= +0 or NaN, whose bit patterns order like unsigned integers with NaN on top, so atomicMax on the bits works and
+// a NaN box keeps its transform from ever being culled by the prepass.
 __global__ void __launch_bounds__(256) kLinkPool(uint32_t count, const uint32_t* __restrict__ entity,
-	const uint32_t* __restrict__ entityToSlot, uint32_t entityCap, uint32_t* __restrict__ tslot)
+	const uint32_t* __restrict__ entityToSlot, uint32_t entityCap, uint32_t* __restrict__ tslot,
+	const float* __restrict__ radius, uint32_t* __restrict__ tRho)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
@@ -203,6 +209,8 @@ __global__ void __launch_bounds__(256) kLinkPool(uint32_t count, const uint32_t*
 	uint32_t e = entity[i];
 	uint32_t s = (e && e < entityCap) ? entityToSlot[e] : 0;
 	tslot[i] = s ? s - 1 : kNone;
+	if (s)
+		atomicMax(&tRho[s - 1], __float_as_uint(radius[i]));
 }
 
 // Slots per tile: a multiple of 4 (tile bytes stay a multiple of 16) that fits the shared-memory budget.
@@ -225,7 +233,7 @@ uint32_t launchStageTransforms(Context& c, const void* dAos, uint32_t stride, ui
 	const uint32_t tileSlots = tileSlotsFor(stride, smem);
 	cudaFuncSetAttribute(kStageTransforms, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	kStageTransforms<<<blocksFor(count, tileSlots), kStageThreads, smem, c.stream>>>((const uint8_t*)dAos, stride, first, count,
-		full ? 1 : 0, tileSlots, t.rot, t.posSx, t.sYZ, t.flags, t.entity, t.parentEntity, dMaxEntity, dSlotMap);
+		full ? 1 : 0, tileSlots, t.rot, t.posSx, t.sYZ, t.flags, t.bound, t.entity, t.parentEntity, dMaxEntity, dSlotMap);
 	return 1;
 }
 
@@ -252,20 +260,22 @@ uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t s
 	const uint32_t tileSlots = tileSlotsFor(stride, smem);
 	cudaFuncSetAttribute(kStagePool, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	kStagePool<<<blocksFor(occupancy, tileSlots), kStageThreads, smem, c.stream>>>((const uint8_t*)dAos, stride, occupancy,
-		tileSlots, p.aabbA, p.aabbB, p.entity, p.flags);
+		tileSlots, p.aabbA, p.aabbB, p.entity, p.flags, p.radius);
 	return 1;
 }
 
 uint32_t launchLink(Context& c)
 {
 	uint32_t n = 0;
+	if (c.tf.occupancy)
+		cudaMemsetAsync(c.tf.rho, 0, (size_t)c.tf.occupancy * sizeof(uint32_t), c.stream);
 	for (uint32_t i = 0; i < c.poolCount; i++)
 	{
 		auto& p = c.pools[i];
 		if (!p.set || p.occupancy == 0)
 			continue;
 		kLinkPool<<<blocksFor(p.occupancy, 256), 256, 0, c.stream>>>(p.occupancy, p.entity, c.tf.entityToSlot,
-			c.tf.entityCap, p.tslot);
+			c.tf.entityCap, p.tslot, p.radius, c.tf.rho);
 		n++;
 	}
 	return n;

@@ -14,9 +14,16 @@ import subprocess
 import sys
 
 rep, cubin, sym, top = sys.argv[1:5]
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+import os
+kfilter = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []  # reports with several kernels
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", *kfilter], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hdr = next(r for r in rows if r and r[0] == "Address")
+# a report with several kernels prints one table per kernel: NCU_SECTION=n picks the n-th (default: all rows)
+section = os.environ.get("NCU_SECTION", "0" if kfilter else None)
+if section is not None:
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Address"] + [len(rows)]
+    rows = rows[starts[int(section)]:starts[int(section) + 1]]
 dyn = [dict(zip(hdr, r)) for r in rows if len(r) == len(hdr) and r[0].startswith("0x")]
 dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 inside, notes, static = False, [], []

@@ -27,6 +27,10 @@ sp.set_pool_count(len(pools))
 for k, m in enumerate(pools):
     sp.set_mesh_pool(k, scene.pools[k].render_type, m, m.dtype.itemsize, m.size)
 sp.set_views(views, scene.camera_pos)
+sp.set_profiling(True)
+phase = np.zeros(6)
 for _ in range(args.frames):
     sp.run()
+    phase = sp.phase_times()
 print("visible", sp.last_visible_total(), "launches", sp.last_launch_count())
+print("phase ms (last frame): link %.4f | kCull %.4f | scan+scatter %.4f | prepass %.4f | sort %.4f | emit %.4f | sum %.4f" % (*phase, phase.sum()))
