@@ -135,11 +135,12 @@ void gsp_destroy(gsp_context* ctx)
 	for (auto& p : c.pools)
 	{
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
-		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus); cudaFree(p.visBits);
-		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount); cudaFree(p.bucketCount);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.visBits);
+		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount);
 	}
+	cudaFree(c.frameZero);
 	cudaFree(c.dSegments); cudaFree(c.keys[0]); cudaFree(c.keys[1]); cudaFree(c.payloads[0]); cudaFree(c.payloads[1]);
-	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortHist); cudaFree(c.sortStatus); cudaFree(c.sortTickets);
+	cudaFree(c.records); cudaFree(c.dCounters); cudaFree(c.sortStatus);
 	cudaFree(c.segTileOffset); cudaFree(c.dAosScratch);
 	cudaFreeHost(c.hCounters); cudaFreeHost(c.hGather); cudaFreeHost(c.hRecords); cudaFreeHost(c.hVisible); cudaFree(c.dVisScratch);
 	if (c.phaseEventsCreated)
@@ -392,8 +393,8 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		if (cap == 0) cap = 1;
 		GSP_CUDA(cudaStreamSynchronize(c.stream));
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
-		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.cullStatus); cudaFree(p.visBits);
-		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount); cudaFree(p.bucketCount);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.visBits);
+		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount);
 		p.visBits = nullptr; p.radius = nullptr; p.surList = nullptr; p.surTs = nullptr; p.surBits = nullptr; p.blockCount = nullptr; p.bucketCount = nullptr;
 		p.aabbA = nullptr; p.aabbB = nullptr; p.entity = nullptr; p.tslot = nullptr; p.flags = nullptr; p.ready = nullptr;
 		p.world = nullptr; p.visible = nullptr; p.cullStatus = nullptr; p.capacity = 0;
@@ -412,12 +413,11 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 			const size_t preBlocks = ((size_t)cap + kPreTile - 1) / kPreTile;
 			GSP_CUDA(cudaMalloc((void**)&p.surBits, preBlocks * (kPreTile / 32) * sizeof(uint32_t)));
 			GSP_CUDA(cudaMalloc((void**)&p.blockCount, preBlocks * sizeof(uint32_t)));
-			GSP_CUDA(cudaMalloc((void**)&p.bucketCount, (preBlocks / 64 + 1) * sizeof(uint32_t)));
 		}
 		p.cullTilesCap = (cap + kCullTile - 1) / kCullTile;
-		GSP_CUDA(cudaMalloc((void**)&p.cullStatus, (size_t)p.cullTilesCap * kMaxViews * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&p.visBits, (size_t)p.cullTilesCap * kMaxViews * (kCullTile / 32) * sizeof(uint32_t)));
 		p.capacity = cap;
+		c.layoutDirty = true; // (the per-frame scratch of the pool is carved out of the context's zeroed block)
 	}
 	if (p.occupancy != occupancy || p.renderType != renderType || p.stride != stride || !p.set ||
 		(p.count == 0) != (count == 0) || p.drawReady != drawReady)
@@ -577,12 +577,10 @@ static int rebuildLayout(Context& c)
 	const size_t nseg = c.segments.size();
 	if (nseg > c.dSegmentsCap || !c.dSegments)
 	{
-		cudaFree(c.dSegments); cudaFree(c.sortHist); cudaFree(c.sortTickets); cudaFree(c.segTileOffset);
-		c.dSegments = nullptr; c.sortHist = nullptr; c.sortTickets = nullptr; c.segTileOffset = nullptr;
+		cudaFree(c.dSegments); cudaFree(c.segTileOffset);
+		c.dSegments = nullptr; c.segTileOffset = nullptr;
 		size_t cap = std::max<size_t>(nseg, 8);
 		GSP_CUDA(cudaMalloc((void**)&c.dSegments, cap * sizeof(SegmentDev)));
-		GSP_CUDA(cudaMalloc((void**)&c.sortHist, cap * 4 * 256 * sizeof(uint32_t)));
-		GSP_CUDA(cudaMalloc((void**)&c.sortTickets, cap * 4 * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&c.segTileOffset, (cap + 1) * sizeof(uint32_t)));
 		c.dSegmentsCap = (uint32_t)cap;
 	}
@@ -590,6 +588,34 @@ static int rebuildLayout(Context& c)
 	{
 		GSP_CUDA(cudaMemcpy(c.dSegments, dev.data(), nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice));
 		GSP_CUDA(cudaMemcpy(c.segTileOffset, tileOffsets.data(), (nseg + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
+	{
+		// Everything that must be zero at the start of a frame lives in ONE block cleared by ONE memset per frame:
+		// sort histograms and tickets of every segment, per pool the chunk counts and the survivor bucket counts.
+		size_t words = nseg * 4 * 256 + nseg * 4;
+		for (uint32_t p = 0; p < (uint32_t)kMaxPools; p++)
+		{
+			auto& pool = c.pools[p];
+			const size_t chunksCap = ((size_t)pool.cullTilesCap + 7) / 8, preBlocks = ((size_t)pool.capacity + kPreTile - 1) / kPreTile;
+			words += chunksCap * kMaxViews + preBlocks / 64 + 1;
+		}
+		if (words > c.frameZeroCap || !c.frameZero)
+		{
+			cudaFree(c.frameZero); c.frameZero = nullptr;
+			GSP_CUDA(cudaMalloc((void**)&c.frameZero, words * sizeof(uint32_t)));
+			c.frameZeroCap = words;
+		}
+		c.frameZeroWords = words;
+		uint32_t* at = c.frameZero;
+		c.sortHist = at; at += nseg * 4 * 256;
+		c.sortTickets = at; at += nseg * 4;
+		for (uint32_t p = 0; p < (uint32_t)kMaxPools; p++)
+		{
+			auto& pool = c.pools[p];
+			const size_t chunksCap = ((size_t)pool.cullTilesCap + 7) / 8, preBlocks = ((size_t)pool.capacity + kPreTile - 1) / kPreTile;
+			pool.cullStatus = at; at += chunksCap * kMaxViews;
+			pool.bucketCount = at; at += preBlocks / 64 + 1;
+		}
 	}
 	if (c.arenaElems > c.arenaCap || !c.keys[0])
 	{
@@ -664,11 +690,7 @@ int gsp_run_async(gsp_context* ctx)
 	}
 	if (prof) cudaEventRecord(c.phaseEvents[1], c.stream);
 	GSP_CUDA(cudaMemsetAsync(c.dCounters, 0, kCtrCount * sizeof(uint32_t), c.stream));
-	if (!c.segments.empty())
-	{
-		GSP_CUDA(cudaMemsetAsync(c.sortHist, 0, c.segments.size() * 4 * 256 * sizeof(uint32_t), c.stream));
-		GSP_CUDA(cudaMemsetAsync(c.sortTickets, 0, c.segments.size() * 4 * sizeof(uint32_t), c.stream));
-	}
+	GSP_CUDA(cudaMemsetAsync(c.frameZero, 0, c.frameZeroWords * sizeof(uint32_t), c.stream));
 	for (uint32_t p = 0; p < c.poolCount; p++)
 		launches += launchCull(c, p, prof ? c.poolEvents[p][0] : nullptr, prof ? c.poolEvents[p][1] : nullptr, prof ? c.poolEvents[p][2] : nullptr);
 	launches += launchSort(c, prof ? c.phaseEvents[2] : nullptr);

@@ -90,6 +90,24 @@ __device__ __forceinline__ float minPlaneDistance(const ViewConst& V, float cx, 
 	return fminf(fminf(fminf(lo2(d[0]), hi2(d[0])), fminf(lo2(d[1]), hi2(d[1]))), fminf(lo2(d[2]), hi2(d[2])));
 }
 
+// One test for all box-shaped views of the frame (CullParams::boxMask; they share their orientation, e.g. the cascades of
+// one light): with a_j the common unit face normals and [lo_j, hi_j] the union of the boxes' extents along a_j, a sphere
+// (c, r) with a_j . c > hi_j + r (or < lo_j - r) for some j is behind the (j, +) (or (j, -)) face plane of EVERY box.
+// `reach` = r + the classifier's band, as in the per-plane test (the band also covers the <= 1e-6 by which the boxes'
+// normals may differ from the common ones, prepareBoxGroup). False for NaN / Inf.
+__device__ __forceinline__ bool boxesCulled(const CullParams& P, float cx, float cy, float cz, float reach)
+{
+	const float r = reach + P.boxSlack;
+	bool outside = false;
+	#pragma unroll
+	for (int j = 0; j < 3; j++)
+	{
+		const float t = fmaf(P.boxAxis[j][0], cx, fmaf(P.boxAxis[j][1], cy, P.boxAxis[j][2] * cz));
+		outside = outside || t > P.boxHi[j] + r || t < P.boxLo[j] - r;
+	}
+	return outside;
+}
+
 // ---- prepass: filter + hierarchical conservative culling + ordered compaction of the survivors ---------------------------
 // In a large scene most entities are outside every view, and the expensive part of the path — the leaf-first product of the
 // parent chain (transform.hpp:197-214) — is only needed for entities that might be visible. The prepass bounds the world box
@@ -115,6 +133,7 @@ __device__ __forceinline__ float minPlaneDistance(const ViewConst& V, float cx, 
 constexpr uint32_t kPreThreads = 256, kPreItems = kPreTile / kPreThreads, kPreWarps = kPreThreads / 32;
 constexpr uint32_t kPreWords = kPreTile / 32;      // survivor-bit words per prepass block
 constexpr uint32_t kPreBucket = 64;                // prepass blocks per bucket of the two-level survivor count
+static_assert(kPreBucket == 64, "kCompactSurvivors reads the blocks of a bucket as two per lane");
 constexpr uint32_t kPreMaxWalk = 255;
 static_assert(kPreWords == 32, "kCompactSurvivors handles one prepass block per warp, one word per lane");
 
@@ -218,22 +237,26 @@ __global__ void __launch_bounds__(kPreThreads) kPrepass(const __grid_constant__ 
 	for (uint32_t k = 0; k < kPreItems; k++)
 	{
 		bool survive = cand[k];
-		if (cand[k] && A.prepassCull)
+		const bool test = cand[k] && A.prepassCull != 0;
+		const float u = rec[k].w;
+		const float cx = rec[k].x - P.cam[0], cy = rec[k].y - P.cam[1], cz = rec[k].z - P.cam[2];
+		const float magnitude = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + u);
+		const float reach = fmaf(magnitude, kBandR, u * 1.0001f);
+		// box views (cascades) are skipped by the whole warp when every lane is certainly outside all of them
+		const bool outsideBoxes = P.boxMask != 0 && boxesCulled(P, cx, cy, cz, reach);
+		const uint32_t skipViews = __all_sync(0xffffffffu, outsideBoxes || !test) ? P.boxMask : 0u;
+		if (test)
 		{
-			const float u = rec[k].w;
-			const float cx = rec[k].x - P.cam[0], cy = rec[k].y - P.cam[1], cz = rec[k].z - P.cam[2];
-			const float magnitude = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + u);
-			const float reach = fmaf(magnitude, kBandR, u * 1.0001f);
 			bool maybe = false;
 			#pragma unroll
 			for (uint32_t v = 0; v < kViews; v++)
 			{
-				if (v < P.viewCount) // warp-uniform
+				if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
 				{
 					const ViewConst& V = P.views[v];
 					const float dmin = minPlaneDistance(V, cx, cy, cz);
 					const bool behind = dmin < -(reach + V.slack); // false for NaN / infinite bounds
-					if (V.enabled && !behind)
+					if (V.enabled && !behind && !(outsideBoxes && ((P.boxMask >> v) & 1u)))
 						maybe = true;
 				}
 			}
@@ -275,10 +298,21 @@ __global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __
 		return; // (whole warps; nothing below synchronises across warps)
 	uint32_t before = 0;
 	const uint32_t bucket = b / kPreBucket;
-	for (uint32_t j = lane; j < bucket; j += 32)
-		before += A.bucketCount[j];
-	for (uint32_t i = bucket * kPreBucket + lane; i < b; i += 32)
-		before += A.blockCount[i];
+	for (uint32_t j0 = lane; j0 < bucket; j0 += 32 * 8) // 8 independent loads in flight per lane
+	{
+		uint32_t v[8];
+		#pragma unroll
+		for (uint32_t q = 0; q < 8; q++)
+			v[q] = j0 + 32 * q < bucket ? A.bucketCount[j0 + 32 * q] : 0u;
+		#pragma unroll
+		for (uint32_t q = 0; q < 8; q++)
+			before += v[q];
+	}
+	{
+		const uint32_t i0 = bucket * kPreBucket + lane, i1 = i0 + 32; // (kPreBucket == 64: two blocks per lane)
+		const uint32_t v0 = i0 < b ? A.blockCount[i0] : 0u, v1 = i1 < b ? A.blockCount[i1] : 0u;
+		before += v0 + v1;
+	}
 	before = __reduce_add_sync(0xffffffffu, before);
 	const uint32_t bits = A.surBits[(size_t)b * kPreWords + lane];
 	const uint32_t c = __popc(bits);
@@ -322,7 +356,7 @@ __global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __
 // of a warp — which walk neighbouring chains — read neighbouring entries (no bank conflicts on the 128-bit loads).
 // Warps never synchronise with each other (only __syncwarp): while one warp waits for its loads, the others compute.
 constexpr uint32_t kWarpTile = 64, kWarpItems = kWarpTile / 32;       // survivors per warp tile, survivors per lane
-constexpr uint32_t kEntries = 88;                                     // kWarpTile own transforms + closure
+constexpr uint32_t kEntries = 96;                                     // kWarpTile own transforms + closure
 constexpr uint32_t kHalo = 16;                                        // survivors before the tile that may get an entry speculatively
 constexpr uint32_t kHashBits = 7, kHashSize = 1u << kHashBits, kHashProbes = 16;
 constexpr uint32_t kEntryNone = 0xFFu;
@@ -338,8 +372,6 @@ struct CullShared // one per warp
 	uint32_t hkey[kHashSize];   // hash table: transform slot (kNone = empty) ...
 	uint32_t par[kEntries];     // per entry: parent transform slot
 	uint32_t closure[kEntries - kWarpTile]; // transform slot of each closure entry (until its matrix has been computed)
-	float4 aabbA[kWarpTile];    // per owner: min xyz, max x
-	float2 aabbB[kWarpTile];    //            max y, z
 	uint32_t slotOf[kWarpTile]; // per owner: pool slot (kNone = past the end of the survivor list)
 	uint32_t hist[kDepthBins];
 	uint32_t inst[kMaxViews];
@@ -447,7 +479,7 @@ static __device__ __forceinline__ void walkChainSlow(const CullShared& sh, const
 // One block = kCullWarps independent warps; every warp walks the survivor list in tiles of kWarpTile with a grid stride.
 // Inside a tile the work items are ordered by chain length (deepest first); lane i takes item i of the deep half and item i
 // of the shallow half, so the warp walks chains of similar length together and every lane carries about the same total.
-constexpr uint32_t kCullThreads = 128, kCullWarps = kCullThreads / 32, kCullBlocksPerSM = 7;
+constexpr uint32_t kCullThreads = 128, kCullWarps = kCullThreads / 32, kCullBlocksPerSM = 8;
 static_assert(kCullWarps * kWarpTile == kCullTile, "a block covers one kCullTile per round");
 
 template<uint32_t kViews>
@@ -496,11 +528,6 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 			const uint32_t slot = valid[r] ? A.surList[tileBase + own] : kNone;
 			ts[r] = valid[r] ? A.surTs[tileBase + own] : kNone;
 			sh.slotOf[own] = slot;
-			if (valid[r])
-			{
-				sh.aabbA[own] = A.aabbA[slot];
-				sh.aabbB[own] = A.aabbB[slot];
-			}
 		}
 		uint16_t tf[kWarpItems];
 		float4 tq[kWarpItems], tp[kWarpItems];
@@ -662,6 +689,14 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 		const uint32_t wslot = sh.slotOf[owner];
 		const bool work = wslot != kNone;
 		uint32_t mask = 0;
+		// the box is only needed after the chain product: its loads fly meanwhile
+		float4 boxA = make_float4(0.f, 0.f, 0.f, 0.f);
+		float2 boxB = make_float2(0.f, 0.f);
+		if (work)
+		{
+			boxA = A.aabbA[wslot];
+			boxB = A.aabbB[wslot];
+		}
 
 		// ---- phase 2: world matrix, leaf-first chain product (transform.hpp:199-211) ----
 		Mat43 M;
@@ -715,8 +750,8 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 
 		float mn[3], mx[3];
 		{
-			const float4 ba = sh.aabbA[owner];
-			const float2 bb = sh.aabbB[owner];
+			const float4 ba = boxA;
+			const float2 bb = boxB;
 			mn[0] = ba.x; mn[1] = ba.y; mn[2] = ba.z; mx[0] = ba.w; mx[1] = bb.x; mx[2] = bb.y;
 		}
 
@@ -755,10 +790,13 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 
 		// ---- phase 3b: per view, the smallest unit-plane distance of the centre decides (see above) ----
 		uint32_t exactViews = 0; // views that need the exact test
+		// box views (cascades) are skipped by the whole warp when every lane's box is certainly outside all of them
+		const bool outsideBoxes = P.boxMask != 0 && finite && boxesCulled(P, cw[0], cw[1], cw[2], reach);
+		const uint32_t skipViews = __all_sync(kFull, outsideBoxes || !work) ? P.boxMask : 0u;
 		#pragma unroll
 		for (uint32_t v = 0; v < kViews; v++)
 		{
-			if (v < P.viewCount) // warp-uniform
+			if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
 			{
 				const ViewConst& V = P.views[v];
 				const float dmin = minPlaneDistance(V, cw[0], cw[1], cw[2]);
@@ -1077,6 +1115,85 @@ static void prepareClassifier(ViewConst& V)
 	V.slack = forceExact ? inf : maxAbsD * kBandD * 1.0001f;
 }
 
+// Is the view a box (three pairs of opposite planes with orthonormal normals, e.g. an orthographic cascade)? Then its face
+// normals and its extent [lo, hi] along each, in the camera-relative space the planes live in. Planes are expected in
+// Frustum(viewProj) order (frustum.hpp:53-60: the pairs are (0,1), (2,3), (4,5)); anything else simply is not recognised
+// (no shortcut, same result).
+static bool viewBox(const ViewConst& V, double n[3][3], double lo[3], double hi[3])
+{
+	if (V.planeCount != 6 || !(V.slack < INFINITY))
+		return false;
+	for (int j = 0; j < 3; j++)
+	{
+		const double a[3] = { V.ux[j].x, V.uy[j].x, V.uz[j].x }, b[3] = { V.ux[j].y, V.uy[j].y, V.uz[j].y };
+		const double da = V.ud[j].x, db = V.ud[j].y;
+		double len2 = 0.0;
+		for (int k = 0; k < 3; k++)
+		{
+			if (std::fabs(a[k] + b[k]) > 1e-6)
+				return false;
+			n[j][k] = a[k]; len2 += a[k] * a[k];
+		}
+		if (std::fabs(len2 - 1.0) > 1e-5 || !std::isfinite(da) || !std::isfinite(db))
+			return false;
+		lo[j] = -da; hi[j] = db; // inside: -da <= n . x <= db
+		if (!(hi[j] >= lo[j]))
+			return false;
+	}
+	for (int i = 0; i < 3; i++)
+		for (int j = i + 1; j < 3; j++)
+			if (std::fabs(n[i][0] * n[j][0] + n[i][1] * n[j][1] + n[i][2] * n[j][2]) > 1e-5)
+				return false;
+	return true;
+}
+
+// One bounding description for all box views of the frame that share the first one's orientation (see boxesCulled).
+static void prepareBoxGroup(CullParams& P)
+{
+	P.boxMask = 0; P.boxSlack = 0.0f;
+	double axis[3][3] = {}, glo[3] = {}, ghi[3] = {}, slack = 0.0;
+	for (uint32_t v = 0; v < P.viewCount; v++)
+	{
+		double n[3][3], lo[3], hi[3];
+		if (!P.views[v].enabled || !viewBox(P.views[v], n, lo, hi))
+			continue;
+		if (P.boxMask == 0)
+		{
+			memcpy(axis, n, sizeof(axis)); memcpy(glo, lo, sizeof(glo)); memcpy(ghi, hi, sizeof(ghi));
+		}
+		else
+		{
+			double dev = 0.0;
+			for (int j = 0; j < 3; j++)
+				for (int k = 0; k < 3; k++)
+					dev = std::max(dev, std::fabs(n[j][k] - axis[j][k]));
+			if (dev > 1e-6)
+				continue; // another orientation: tested per plane as usual
+			for (int j = 0; j < 3; j++)
+			{
+				glo[j] = std::min(glo[j], lo[j]); ghi[j] = std::max(ghi[j], hi[j]);
+			}
+		}
+		P.boxMask |= 1u << v;
+		slack = std::max(slack, (double)P.views[v].slack);
+	}
+	if (!P.boxMask)
+		return;
+	for (int j = 0; j < 3; j++)
+	{
+		for (int k = 0; k < 3; k++) P.boxAxis[j][k] = (float)axis[j][k];
+		// rounded outwards (the float conversion and the kBandD-style slack of the extents themselves)
+		P.boxLo[j] = (float)(glo[j] - std::fabs(glo[j]) * 1e-5 - 1e-30);
+		P.boxHi[j] = (float)(ghi[j] + std::fabs(ghi[j]) * 1e-5 + 1e-30);
+		if (!std::isfinite(P.boxLo[j]) || !std::isfinite(P.boxHi[j]))
+		{
+			P.boxMask = 0;
+			return;
+		}
+	}
+	P.boxSlack = (float)(slack * 1.0001);
+}
+
 // Prepass spheres of every transform: once per change of transforms, pools or active flags (after launchLink: needs rho)
 uint32_t launchChainBounds(Context& c)
 {
@@ -1136,6 +1253,9 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEve
 	P.key2D = isUI ? 1 : 0;
 	P.descending = sortedList ? 1 : 0;
 	P.hasReady = p.hasReady ? 1 : 0;
+	static const bool boxesOff = []{ const char* e = getenv("GSP_BOXGROUP"); return e && !strcmp(e, "0"); }();
+	if (!boxesOff)
+		prepareBoxGroup(P);
 
 	A.tRot = c.tf.rot; A.tPosSx = c.tf.posSx; A.tSYZ = c.tf.sYZ; A.tParent = c.tf.parent; A.tFlags = c.tf.flags;
 	A.tRecord = c.tf.record;
@@ -1164,10 +1284,8 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEve
 		cudaFuncSetAttribute(kCull<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		c.cullAttrsSet = true;
 	}
-	cudaMemsetAsync(p.cullStatus, 0, (size_t)A.chunks * kMaxViews * sizeof(uint32_t), c.stream);
 	// the view loops are unrolled at compile time (plane constants become direct constant-bank operands)
 	const uint32_t preBlocks = (p.occupancy + kPreTile - 1) / kPreTile;
-	cudaMemsetAsync(p.bucketCount, 0, ((size_t)preBlocks / kPreBucket + 1) * sizeof(uint32_t), c.stream);
 	// kCull is persistent: its warps stride over the survivor tiles (the survivor count only exists on the device)
 	const uint32_t cullBlocks = std::max(1u, std::min(A.tiles, c.smCount * kCullBlocksPerSM));
 	#define GSP_LAUNCH_CULL(V) do { \

@@ -113,8 +113,14 @@ struct CullParams
 	uint32_t key2D;        // UI: key = model.c3.z + 1.0f (mesh.cpp:250)
 	uint32_t descending;   // translucent / UI lists sort descending (mesh.hpp:204)
 	uint32_t hasReady;
-	uint32_t anyWriteVisible;
-	uint32_t pad;
+	// Views whose six planes form a box (orthographic frusta: the CSM cascades) with the SAME orientation. boxAxis are the
+	// three common face normals, [boxLo, boxHi] the union of the views' extents along each: a sphere that lies beyond that
+	// interval on some axis is behind a face plane of EVERY such view, so one test of three dot products stands for all of
+	// them (cull.cu: boxesCulled); boxMask == 0: no such view in this frame.
+	uint32_t boxMask;
+	float boxAxis[3][3];
+	float boxLo[3], boxHi[3];
+	float boxSlack;
 };
 
 // A segment = one output list of one view: (view, canonical pool). Unsorted buffers own a segment each;
@@ -174,7 +180,8 @@ struct Context
 	uint32_t* dCounters = nullptr;
 	uint32_t* hCounters = nullptr; // pinned
 	// sort scratch
-	uint32_t* sortHist = nullptr;   // [segments][4][256]
+	uint32_t* frameZero = nullptr; size_t frameZeroWords = 0, frameZeroCap = 0; // per-frame scratch that starts at zero (one memset)
+	uint32_t* sortHist = nullptr;   // [segments][4][256] (inside frameZero)
 	unsigned long long* sortStatus = nullptr; // [tiles][256] look-back words tagged with the launch epoch (never cleared)
 	uint32_t sortEpoch = 0;
 	uint32_t* sortTickets = nullptr; // [segments][4]
