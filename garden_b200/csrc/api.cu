@@ -107,7 +107,7 @@ int gsp_create(int device, gsp_context** out)
 		cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaEventCreateWithFlags(&c.copyEvent, cudaEventDisableTiming) != cudaSuccess ||
 		cudaMalloc((void**)&c.dCounters, kCtrCount * sizeof(uint32_t)) != cudaSuccess ||
-		cudaMallocHost((void**)&c.hCounters, (kCtrCount + 8) * sizeof(uint32_t)) != cudaSuccess)
+		cudaMallocHost((void**)&c.hCounters, (kCtrCount + 16) * sizeof(uint32_t)) != cudaSuccess)
 	{
 		gCreateError = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
 		delete ctx;
@@ -131,7 +131,8 @@ void gsp_destroy(gsp_context* ctx)
 	if (c.copyStream) cudaStreamSynchronize(c.copyStream);
 	auto& t = c.tf;
 	cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);
-	cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.bound); cudaFree(t.record); cudaFree(t.rho); cudaFree(t.chainRoot); cudaFree(t.rootW); cudaFree(t.entityToSlot);
+	cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.bound); cudaFree(t.record); cudaFree(t.rho); cudaFree(t.chainRoot); cudaFree(t.rootW); cudaFree(t.poolMask); cudaFree(t.entityToSlot);
+	cudaFree(t.tBits); cudaFree(t.tBlockCount); cudaFree(t.tList); cudaFree(t.tIndex); cudaFree(t.tWorld);
 	for (auto& p : c.pools)
 	{
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
@@ -150,6 +151,8 @@ void gsp_destroy(gsp_context* ctx)
 		for (auto& pe : c.poolEvents)
 			for (auto& e : pe)
 				cudaEventDestroy(e);
+		for (auto& e : c.splitEvents)
+			cudaEventDestroy(e);
 	}
 	cudaStreamSynchronize(c.copyStream);
 	cudaStreamDestroy(c.copyStream);
@@ -249,8 +252,11 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 		if (cap == 0) cap = 1;
 		GSP_CUDA(cudaStreamSynchronize(c.stream));
 		cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);
-		cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.bound); cudaFree(t.record); cudaFree(t.rho); cudaFree(t.chainRoot); cudaFree(t.rootW);
-		t.bound = nullptr; t.record = nullptr; t.rho = nullptr; t.chainRoot = nullptr; t.rootW = nullptr;
+		cudaFree(t.parentEntity); cudaFree(t.flags); cudaFree(t.bound); cudaFree(t.record); cudaFree(t.rho); cudaFree(t.chainRoot); cudaFree(t.rootW); cudaFree(t.poolMask);
+		cudaFree(t.tBits); cudaFree(t.tBlockCount); cudaFree(t.tList); cudaFree(t.tIndex); cudaFree(t.tWorld);
+		t.tBits = nullptr; t.tBlockCount = nullptr; t.tList = nullptr; t.tIndex = nullptr; t.tWorld = nullptr; t.splitCap = 0;
+		t.bound = nullptr; t.record = nullptr; t.rho = nullptr; t.chainRoot = nullptr; t.rootW = nullptr; t.poolMask = nullptr;
+		c.layoutDirty = true; // (tBucketCount is carved out of the per-frame zero block)
 		t.rot = nullptr; t.posSx = nullptr; t.sYZ = nullptr; t.parent = nullptr; t.entity = nullptr;
 		t.parentEntity = nullptr; t.flags = nullptr; t.capacity = 0;
 		GSP_CUDA(cudaMalloc((void**)&t.rot, (size_t)cap * sizeof(float4)));
@@ -264,6 +270,7 @@ int gsp_set_transforms(gsp_context* ctx, const void* aos, uint32_t stride, uint3
 		GSP_CUDA(cudaMalloc((void**)&t.rho, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.chainRoot, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.rootW, (size_t)cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.poolMask, (size_t)cap * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&t.flags, (((size_t)cap + 1) & ~(size_t)1) * sizeof(uint16_t))); // whole 32-bit words: gsp_set_active updates a flag entry through the word that holds it
 		t.capacity = cap;
 	}
@@ -592,7 +599,8 @@ static int rebuildLayout(Context& c)
 	{
 		// Everything that must be zero at the start of a frame lives in ONE block cleared by ONE memset per frame:
 		// sort histograms and tickets of every segment, per pool the chunk counts and the survivor bucket counts.
-		size_t words = nseg * 4 * 256 + nseg * 4;
+		const size_t tBuckets = (((size_t)c.tf.capacity + kPreTile - 1) / kPreTile) / 64 + 1;
+		size_t words = nseg * 4 * 256 + nseg * 4 + tBuckets;
 		for (uint32_t p = 0; p < (uint32_t)kMaxPools; p++)
 		{
 			auto& pool = c.pools[p];
@@ -609,6 +617,7 @@ static int rebuildLayout(Context& c)
 		uint32_t* at = c.frameZero;
 		c.sortHist = at; at += nseg * 4 * 256;
 		c.sortTickets = at; at += nseg * 4;
+		c.tf.tBucketCount = at; at += tBuckets;
 		for (uint32_t p = 0; p < (uint32_t)kMaxPools; p++)
 		{
 			auto& pool = c.pools[p];
@@ -648,6 +657,44 @@ static int rebuildLayout(Context& c)
 	return GSP_OK;
 }
 
+// After linking: which pools take the split path (cull.cu)? A pool whose chains mostly find their ancestors among the pool's
+// own components (every node of a hierarchy carries a mesh of that pool) is handled by the fused kernel; when more than 2 %
+// of its slots have a parent without a mesh in the pool — hierarchies spread over several mesh systems, or inner nodes
+// without meshes — world matrices are computed once per surviving transform instead. GSP_SPLIT=0 / 1 forces the choice.
+static int decideSplit(Context& c)
+{
+	uint32_t* hCross = c.hCounters + kCtrCount + 2;
+	GSP_CUDA(cudaMemcpyAsync(hCross, c.dCounters + kCtrCross, kMaxPools * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	static const int forced = []{ const char* e = getenv("GSP_SPLIT"); return !e ? -1 : (!strcmp(e, "0") ? 0 : 1); }();
+	c.anySplit = false;
+	for (uint32_t p = 0; p < c.poolCount; p++)
+	{
+		auto& pool = c.pools[p];
+		const bool eligible = pool.set && pool.occupancy > 0 && pool.renderType != GSP_RT_UI;
+		bool split = eligible && (uint64_t)hCross[p] * 50u > pool.occupancy;
+		if (forced >= 0)
+			split = eligible && forced == 1;
+		pool.split = split;
+		c.anySplit = c.anySplit || split;
+	}
+	auto& t = c.tf;
+	if (c.anySplit && t.splitCap < t.capacity)
+	{
+		cudaFree(t.tBits); cudaFree(t.tBlockCount); cudaFree(t.tList); cudaFree(t.tIndex); cudaFree(t.tWorld);
+		t.tBits = nullptr; t.tBlockCount = nullptr; t.tList = nullptr; t.tIndex = nullptr; t.tWorld = nullptr; t.splitCap = 0;
+		const size_t cap = t.capacity, preBlocks = (cap + kPreTile - 1) / kPreTile;
+		GSP_CUDA(cudaMalloc((void**)&t.tBits, preBlocks * (kPreTile / 32) * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.tBlockCount, preBlocks * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.tList, cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.tIndex, cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMemset(t.tIndex, 0xFF, cap * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&t.tWorld, cap * kWorldStride * sizeof(float4)));
+		t.splitCap = (uint32_t)cap;
+	}
+	return GSP_OK;
+}
+
 int gsp_run_async(gsp_context* ctx)
 {
 	if (!ctx)
@@ -675,12 +722,16 @@ int gsp_run_async(gsp_context* ctx)
 		for (auto& pe : c.poolEvents)
 			for (auto& e : pe)
 				GSP_CUDA(cudaEventCreate(&e));
+		for (auto& e : c.splitEvents)
+			GSP_CUDA(cudaEventCreate(&e));
 		c.phaseEventsCreated = true;
 	}
 	if (prof) cudaEventRecord(c.phaseEvents[0], c.stream);
 	if (c.linkDirty)
 	{
 		launches += launchLink(c);
+		int rc = decideSplit(c); // (one host synchronisation per structural change)
+		if (rc) return rc;
 		c.linkDirty = false;
 	}
 	if (c.chainDirty)
@@ -691,6 +742,11 @@ int gsp_run_async(gsp_context* ctx)
 	if (prof) cudaEventRecord(c.phaseEvents[1], c.stream);
 	GSP_CUDA(cudaMemsetAsync(c.dCounters, 0, kCtrCount * sizeof(uint32_t), c.stream));
 	GSP_CUDA(cudaMemsetAsync(c.frameZero, 0, c.frameZeroWords * sizeof(uint32_t), c.stream));
+	{
+		const uint32_t n = launchSplitWorld(c, prof ? c.splitEvents[0] : nullptr, prof ? c.splitEvents[1] : nullptr);
+		c.splitRan = n != 0;
+		launches += n;
+	}
 	for (uint32_t p = 0; p < c.poolCount; p++)
 		launches += launchCull(c, p, prof ? c.poolEvents[p][0] : nullptr, prof ? c.poolEvents[p][1] : nullptr, prof ? c.poolEvents[p][2] : nullptr);
 	launches += launchSort(c, prof ? c.phaseEvents[2] : nullptr);
@@ -1342,6 +1398,15 @@ int gsp_get_phase_times(gsp_context* ctx, float* ms)
 	// link | per pool: prepass, cull, then scan + scatter | sort passes | emission
 	GSP_CUDA(cudaEventElapsedTime(&ms[0], c.phaseEvents[0], c.phaseEvents[1]));
 	cudaEvent_t prev = c.phaseEvents[1];
+	if (c.anySplit && c.splitRan)
+	{
+		// split path: transform-level prepass + compaction + world matrices, booked under phase 1 (world matrices)
+		float pre = 0.0f, w = 0.0f;
+		GSP_CUDA(cudaEventElapsedTime(&pre, prev, c.splitEvents[0]));
+		GSP_CUDA(cudaEventElapsedTime(&w, c.splitEvents[0], c.splitEvents[1]));
+		ms[3] += pre; ms[1] += w;
+		prev = c.splitEvents[1];
+	}
 	for (uint32_t p = 0; p < c.poolCount; p++)
 	{
 		if (!c.poolLaunched[p])

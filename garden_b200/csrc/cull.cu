@@ -52,6 +52,12 @@ struct CullArgs
 	uint32_t tiles;                  // capacity in 256-survivor tiles (stride of visBits)
 	uint32_t chunks;                 // capacity in chunks (stride of chunkCount)
 	uint32_t prepassCull;            // 0: the prepass only applies the filter (GSP_PREPASS=0, for A/B measurements)
+	uint32_t surCounter;             // counter index holding the length of surList (pool survivors, or surviving transforms)
+	// ---- split path (pools whose hierarchies do not live in the pool itself): world matrices per surviving TRANSFORM ----
+	const uint32_t* __restrict__ tList;   // surviving transforms in slot order (kPrepassT + kCompactSurvivors<true>)
+	const uint32_t* __restrict__ tIndex;  // transform slot -> index in tList (only meaningful where tList[index] == slot)
+	float4* __restrict__ tWorld;          // [surviving transform][kWorldStride] chain product, camera NOT subtracted
+	uint32_t tCounter;                    // counter index holding the length of tList
 };
 
 constexpr uint32_t kChunkTiles = 8;                                // 256-survivor tiles per compaction chunk
@@ -179,22 +185,32 @@ __global__ void __launch_bounds__(256) kChainRecords(const __grid_constant__ Cha
 	if (t >= A.count)
 		return;
 	const uint16_t f = A.flags[t];
-	float4 rec = make_float4(0.f, 0.f, 0.f, -1.0f); // dead or inactive: never a candidate (mesh.cpp:149-155)
-	if ((f & kTfLive) && (f & kTfActive))
+	float4 rec = make_float4(0.f, 0.f, 0.f, -__int_as_float(0x7f800000)); // dead slot
+	if (f & kTfLive)
 	{
+		float w;
 		if (f & kTfAncestors)
 		{
 			const uint32_t root = A.chainRoot[t];
 			const float4 c = A.posSx[root];
-			rec = make_float4(c.x, c.y, c.z, __uint_as_float(A.rootW[root]));
+			rec = make_float4(c.x, c.y, c.z, 0.f);
+			w = __uint_as_float(A.rootW[root]);
 		}
 		else
 		{
 			// modelWithAncestors == false: the model is the local matrix alone (transform.hpp:200)
 			const float4 c = A.posSx[t];
 			const float rho = __uint_as_float(A.rho[t]);
-			rec = make_float4(c.x, c.y, c.z, rho == 0.0f ? 0.0f : A.bound[t].x * rho);
+			rec = make_float4(c.x, c.y, c.z, 0.f);
+			w = rho == 0.0f ? 0.0f : A.bound[t].x * rho;
 		}
+		if (w != w)
+			w = __int_as_float(0x7f800000); // NaN bound: never culled (and the sign below stays meaningful)
+		// the sign carries isActive() (mesh.cpp:149-155): a mesh on an inactive transform is never a candidate, but the
+		// transform may still be an ancestor of active ones, so the sphere itself is kept
+		rec.w = (f & kTfActive) ? w : -w;
+		if (!(f & kTfActive) && w == 0.0f)
+			rec.w = -0.0f;
 	}
 	A.record[t] = rec;
 }
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(kPreThreads) kPrepass(const __grid_constant__ 
 		rec[k] = make_float4(0.f, 0.f, 0.f, -1.0f);
 		if (cand[k])
 			rec[k] = A.tRecord[ts[k]];
-		cand[k] = cand[k] && !(rec[k].w < 0.0f); // live and active transform (NaN radius: candidate, never culled here)
+		cand[k] = cand[k] && !signbit(rec[k].w); // live and active transform (kChainRecords stores -W otherwise)
 	}
 	uint32_t total = 0;
 	#pragma unroll
@@ -283,15 +299,87 @@ __global__ void __launch_bounds__(kPreThreads) kPrepass(const __grid_constant__ 
 	}
 }
 
+// Split path: the same test per TRANSFORM, for the views any split pool takes part in (P.views[].enabled). The records are
+// per hierarchy, so whole hierarchies survive and a surviving mesh always finds its transform — and its ancestors — here.
+template<uint32_t kViews>
+__global__ void __launch_bounds__(kPreThreads) kPrepassT(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+{
+	__shared__ uint32_t sCount[kPreWarps];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t blockBase = blockIdx.x * kPreTile;
+	uint32_t total = 0;
+	#pragma unroll
+	for (uint32_t k = 0; k < kPreItems; k++)
+	{
+		const uint32_t t = blockBase + k * kPreThreads + threadIdx.x;
+		const bool live = t < P.occupancy && (A.tFlags[t] & kTfLive);
+		const float4 rec = live ? A.tRecord[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+		const float u = fabsf(rec.w); // (the sign only says "inactive": an inactive transform may still be somebody's ancestor)
+		const float cx = rec.x - P.cam[0], cy = rec.y - P.cam[1], cz = rec.z - P.cam[2];
+		const float magnitude = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + u);
+		const float reach = fmaf(magnitude, kBandR, u * 1.0001f);
+		const bool test = live && A.prepassCull != 0;
+		const bool outsideBoxes = P.boxMask != 0 && boxesCulled(P, cx, cy, cz, reach);
+		const uint32_t skipViews = __all_sync(0xffffffffu, outsideBoxes || !test) ? P.boxMask : 0u;
+		bool survive = live;
+		if (test)
+		{
+			bool maybe = false;
+			#pragma unroll
+			for (uint32_t v = 0; v < kViews; v++)
+			{
+				if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
+				{
+					const ViewConst& V = P.views[v];
+					const float dmin = minPlaneDistance(V, cx, cy, cz);
+					const bool behind = dmin < -(reach + V.slack);
+					if (V.enabled && !behind && !(outsideBoxes && ((P.boxMask >> v) & 1u)))
+						maybe = true;
+				}
+			}
+			survive = maybe;
+		}
+		const uint32_t votes = __ballot_sync(0xffffffffu, survive);
+		if (lane == 0)
+			A.surBits[(size_t)blockIdx.x * kPreWords + k * kPreWarps + warp] = votes;
+		total += __popc(votes);
+	}
+	if (lane == 0)
+		sCount[warp] = total;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t sum = 0;
+		#pragma unroll
+		for (uint32_t w = 0; w < kPreWarps; w++)
+			sum += sCount[w];
+		A.blockCount[blockIdx.x] = sum;
+		if (sum)
+			atomicAdd(&A.bucketCount[blockIdx.x / kPreBucket], sum);
+	}
+}
+
 // Survivor bits -> surList (+ the survivors' transform slots) in slot order. One WARP per prepass block (lane = one word of
 // 32 slots). The block's position in the list = survivors of all earlier blocks = (sum of the earlier buckets) + (sum of
 // the earlier blocks of its own bucket): a few hundred L2-resident words read by the 32 lanes in parallel, so no block ever
 // waits for another one. The set bits are expanded into shared memory first, so that the list is written (and the
 // transform links are gathered) by whole warps.
 constexpr uint32_t kCompactWarps = 8;
-__global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A,
-	uint32_t preBlocks)
+struct CompactArgs
 {
+	const uint32_t* __restrict__ bits;        // [blocks][32]
+	const uint32_t* __restrict__ blockCount;  // [blocks]
+	const uint32_t* __restrict__ bucketCount; // [blocks / kPreBucket + 1]
+	uint32_t* __restrict__ list;              // out: survivor index -> slot
+	uint32_t* __restrict__ aux;               // out: kTransforms ? slot -> survivor index : survivor index -> tslot[slot]
+	const uint32_t* __restrict__ tslot;
+	uint32_t* __restrict__ counters;
+	uint32_t counterIndex, blocks;
+};
+template<bool kTransforms>
+__global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __grid_constant__ CompactArgs A)
+{
+	const uint32_t preBlocks = A.blocks;
 	__shared__ uint16_t sOffsets[kCompactWarps][kPreTile];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * kCompactWarps + warp;
 	if (b >= preBlocks)
@@ -314,7 +402,7 @@ __global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __
 		before += v0 + v1;
 	}
 	before = __reduce_add_sync(0xffffffffu, before);
-	const uint32_t bits = A.surBits[(size_t)b * kPreWords + lane];
+	const uint32_t bits = A.bits[(size_t)b * kPreWords + lane];
 	const uint32_t c = __popc(bits);
 	uint32_t inc = c;
 	#pragma unroll
@@ -336,11 +424,14 @@ __global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __
 	for (uint32_t j = lane; j < total; j += 32)
 	{
 		const uint32_t slot = b * kPreTile + sOffsets[warp][j];
-		A.surList[before + j] = slot;
-		A.surTs[before + j] = A.tslot[slot];
+		A.list[before + j] = slot;
+		if (kTransforms)
+			A.aux[slot] = before + j;
+		else
+			A.aux[before + j] = A.tslot[slot];
 	}
 	if (b == preBlocks - 1 && lane == 0)
-		A.counters[kCtrSurvivors + P.poolIndex] = before + total;
+		A.counters[A.counterIndex] = before + total;
 }
 
 // ---- shared-memory cache of local matrices ----------------------------------------------------------------------------------
@@ -476,20 +567,126 @@ static __device__ __forceinline__ void walkChainSlow(const CullShared& sh, const
 	}
 }
 
+// ---- phase 3: the world box against every view -------------------------------------------------------------------------------
+// M = the model matrix (camera position already subtracted, transform.hpp:211), box = the component's AABB. Returns the bit
+// mask of views in which the reference's isBehindFrustum (aabb.hpp:438-464) does NOT cull the box. Called by all lanes of a
+// warp (it votes); lanes with work == false return 0.
+template<uint32_t kViews>
+__device__ __forceinline__ uint32_t classifyBox(const CullParams& P, const Mat43& M, const float4 boxA, const float2 boxB, const bool work)
+{
+	constexpr uint32_t kFull = 0xffffffffu;
+	uint32_t mask = 0;
+	float mn[3], mx[3];
+	{
+		const float4 ba = boxA;
+		const float2 bb = boxB;
+		mn[0] = ba.x; mn[1] = ba.y; mn[2] = ba.z; mx[0] = ba.w; mx[1] = bb.x; mx[2] = bb.y;
+	}
+
+	// ---- phase 3a: bounding sphere of the transformed box + error band (any rounding is fine here, the band absorbs it) ----
+	float cw[3]; // world-space centre
+	float reach; // sphere radius + band
+	bool finite;
+	{
+		float ctr[3], ext[3], amax[3];
+		#pragma unroll
+		for (int k = 0; k < 3; k++)
+		{
+			ctr[k] = 0.5f * (mn[k] + mx[k]);
+			ext[k] = 0.5f * fabsf(mx[k] - mn[k]);
+			amax[k] = fmaxf(fabsf(mn[k]), fabsf(mx[k]));
+		}
+		#pragma unroll
+		for (int l = 0; l < 3; l++)
+			cw[l] = fmaf(M.c[0][l], ctr[0], fmaf(M.c[1][l], ctr[1], fmaf(M.c[2][l], ctr[2], M.c[3][l])));
+		// sum_i |c_i| * e_i <= sqrt(3 * sum_i |c_i|^2 e_i^2): with e = ext it bounds the corner distance from the centre,
+		// with e = amax (plus |c3|) it bounds every |corner lane| and every partial sum of the corner transform
+		float rr = 0.0f, ra = 0.0f;
+		#pragma unroll
+		for (int i = 0; i < 3; i++)
+		{
+			const float len2 = fmaf(M.c[i][0], M.c[i][0], fmaf(M.c[i][1], M.c[i][1], M.c[i][2] * M.c[i][2]));
+			rr = fmaf(len2, ext[i] * ext[i], rr);
+			ra = fmaf(len2, amax[i] * amax[i], ra);
+		}
+		const float c3max = fmaxf(fmaxf(fabsf(M.c[3][0]), fabsf(M.c[3][1])), fabsf(M.c[3][2]));
+		const float magnitude = fmaf(sqrtApprox(3.0f * ra), 1.0001f, c3max);
+		reach = fmaf(magnitude, kBandR, sqrtApprox(3.0f * rr) * 1.0001f);
+		// NaN / Inf anywhere in the matrix poisons this sum: such entities always take the exact test
+		finite = fabsf(((cw[0] + cw[1]) + (cw[2] + rr)) + ra) < __int_as_float(0x7f800000);
+	}
+
+	// ---- phase 3b: per view, the smallest unit-plane distance of the centre decides (see above) ----
+	uint32_t exactViews = 0; // views that need the exact test
+	// box views (cascades) are skipped by the whole warp when every lane's box is certainly outside all of them
+	const bool outsideBoxes = P.boxMask != 0 && finite && boxesCulled(P, cw[0], cw[1], cw[2], reach);
+	const uint32_t skipViews = __all_sync(kFull, outsideBoxes || !work) ? P.boxMask : 0u;
+	#pragma unroll
+	for (uint32_t v = 0; v < kViews; v++)
+	{
+		if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
+		{
+			const ViewConst& V = P.views[v];
+			const float dmin = minPlaneDistance(V, cw[0], cw[1], cw[2]);
+			const float t = reach + V.slack;
+			const bool front = dmin > t, behind = dmin < -t;
+			if (V.enabled)
+			{
+				if (front && finite)
+					mask |= 1u << v;
+				else if (!(behind && finite))
+					exactViews |= 1u << v;
+			}
+		}
+	}
+	if (!work)
+	{
+		mask = 0; exactViews = 0;
+	}
+	if (exactViews) // rare: the box straddles a plane
+	{
+		float vx[8], vy[8], vz[8];
+		#pragma unroll
+		for (int k = 0; k < 8; k++)
+			transformCorner43(M, (k & 4) ? mx[0] : mn[0], (k & 2) ? mx[1] : mn[1], (k & 1) ? mx[2] : mn[2], vx[k], vy[k], vz[k]);
+		while (exactViews)
+		{
+			const uint32_t v = __ffs(exactViews) - 1;
+			exactViews &= exactViews - 1;
+			const ViewConst& V = P.views[v];
+			bool culled = false;
+			for (uint32_t i = 0; i < V.planeCount && !culled; i++)
+			{
+				const float nx = V.planes[i][0], ny = V.planes[i][1], nz = V.planes[i][2], nd = V.planes[i][3];
+				bool allBehind = true;
+				#pragma unroll
+				for (int k = 0; k < 8; k++)
+					allBehind = allBehind && (planeDistance(nx, ny, nz, nd, vx[k], vy[k], vz[k]) < 0.0f);
+				culled = allBehind;
+			}
+			if (!culled)
+				mask |= 1u << v;
+		}
+	}
+	return mask;
+}
+
 // One block = kCullWarps independent warps; every warp walks the survivor list in tiles of kWarpTile with a grid stride.
 // Inside a tile the work items are ordered by chain length (deepest first); lane i takes item i of the deep half and item i
 // of the shallow half, so the warp walks chains of similar length together and every lane carries about the same total.
 constexpr uint32_t kCullThreads = 128, kCullWarps = kCullThreads / 32, kCullBlocksPerSM = 8;
 static_assert(kCullWarps * kWarpTile == kCullTile, "a block covers one kCullTile per round");
 
-template<uint32_t kViews>
+// kWorldOnly: the split path's first half — the items are surviving TRANSFORMS (A.surList = tList, A.surTs = tList), the
+// chain product goes to A.tWorld without the camera translation, nothing is classified.
+template<uint32_t kViews, bool kWorldOnly>
 __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
 {
 	__shared__ CullShared shAll[kCullWarps];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	CullShared& sh = shAll[warp];
 	constexpr uint32_t kFull = 0xffffffffu;
-	const uint32_t survivors = A.counters[kCtrSurvivors + P.poolIndex];
+	const uint32_t survivors = A.counters[A.surCounter];
 	const uint32_t tileCount = (survivors + kWarpTile - 1) / kWarpTile;
 	const uint32_t words = A.tiles * (kCullTile / 32);
 
@@ -692,7 +889,7 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 		// the box is only needed after the chain product: its loads fly meanwhile
 		float4 boxA = make_float4(0.f, 0.f, 0.f, 0.f);
 		float2 boxB = make_float2(0.f, 0.f);
-		if (work)
+		if (work && !kWorldOnly)
 		{
 			boxA = A.aabbA[wslot];
 			boxB = A.aabbB[wslot];
@@ -743,103 +940,23 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 			if (slow)
 				walkChainSlow(sh, A, slowFrom, M);
 		}
+		if (kWorldOnly)
+		{
+			if (work)
+			{
+				float4* w = A.tWorld + (size_t)(tileBase + owner) * kWorldStride;
+				w[0] = make_float4(M.c[0][0], M.c[0][1], M.c[0][2], M.c[1][0]);
+				w[1] = make_float4(M.c[1][1], M.c[1][2], M.c[2][0], M.c[2][1]);
+				w[2] = make_float4(M.c[2][2], M.c[3][0], M.c[3][1], M.c[3][2]);
+			}
+			continue;
+		}
 		// translate(-cameraPosition, model): c3.xyz += -cam, w kept (matrix/transform.hpp:71-74)
 		M.c[3][0] = __fadd_rn(M.c[3][0], -P.cam[0]);
 		M.c[3][1] = __fadd_rn(M.c[3][1], -P.cam[1]);
 		M.c[3][2] = __fadd_rn(M.c[3][2], -P.cam[2]);
 
-		float mn[3], mx[3];
-		{
-			const float4 ba = boxA;
-			const float2 bb = boxB;
-			mn[0] = ba.x; mn[1] = ba.y; mn[2] = ba.z; mx[0] = ba.w; mx[1] = bb.x; mx[2] = bb.y;
-		}
-
-		// ---- phase 3a: bounding sphere of the transformed box + error band (any rounding is fine here, the band absorbs it) ----
-		float cw[3]; // world-space centre
-		float reach; // sphere radius + band
-		bool finite;
-		{
-			float ctr[3], ext[3], amax[3];
-			#pragma unroll
-			for (int k = 0; k < 3; k++)
-			{
-				ctr[k] = 0.5f * (mn[k] + mx[k]);
-				ext[k] = 0.5f * fabsf(mx[k] - mn[k]);
-				amax[k] = fmaxf(fabsf(mn[k]), fabsf(mx[k]));
-			}
-			#pragma unroll
-			for (int l = 0; l < 3; l++)
-				cw[l] = fmaf(M.c[0][l], ctr[0], fmaf(M.c[1][l], ctr[1], fmaf(M.c[2][l], ctr[2], M.c[3][l])));
-			// sum_i |c_i| * e_i <= sqrt(3 * sum_i |c_i|^2 e_i^2): with e = ext it bounds the corner distance from the centre,
-			// with e = amax (plus |c3|) it bounds every |corner lane| and every partial sum of the corner transform
-			float rr = 0.0f, ra = 0.0f;
-			#pragma unroll
-			for (int i = 0; i < 3; i++)
-			{
-				const float len2 = fmaf(M.c[i][0], M.c[i][0], fmaf(M.c[i][1], M.c[i][1], M.c[i][2] * M.c[i][2]));
-				rr = fmaf(len2, ext[i] * ext[i], rr);
-				ra = fmaf(len2, amax[i] * amax[i], ra);
-			}
-			const float c3max = fmaxf(fmaxf(fabsf(M.c[3][0]), fabsf(M.c[3][1])), fabsf(M.c[3][2]));
-			const float magnitude = fmaf(sqrtApprox(3.0f * ra), 1.0001f, c3max);
-			reach = fmaf(magnitude, kBandR, sqrtApprox(3.0f * rr) * 1.0001f);
-			// NaN / Inf anywhere in the matrix poisons this sum: such entities always take the exact test
-			finite = fabsf(((cw[0] + cw[1]) + (cw[2] + rr)) + ra) < __int_as_float(0x7f800000);
-		}
-
-		// ---- phase 3b: per view, the smallest unit-plane distance of the centre decides (see above) ----
-		uint32_t exactViews = 0; // views that need the exact test
-		// box views (cascades) are skipped by the whole warp when every lane's box is certainly outside all of them
-		const bool outsideBoxes = P.boxMask != 0 && finite && boxesCulled(P, cw[0], cw[1], cw[2], reach);
-		const uint32_t skipViews = __all_sync(kFull, outsideBoxes || !work) ? P.boxMask : 0u;
-		#pragma unroll
-		for (uint32_t v = 0; v < kViews; v++)
-		{
-			if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
-			{
-				const ViewConst& V = P.views[v];
-				const float dmin = minPlaneDistance(V, cw[0], cw[1], cw[2]);
-				const float t = reach + V.slack;
-				const bool front = dmin > t, behind = dmin < -t;
-				if (V.enabled)
-				{
-					if (front && finite)
-						mask |= 1u << v;
-					else if (!(behind && finite))
-						exactViews |= 1u << v;
-				}
-			}
-		}
-		if (!work)
-		{
-			mask = 0; exactViews = 0;
-		}
-		if (exactViews) // rare: the box straddles a plane
-		{
-			float vx[8], vy[8], vz[8];
-			#pragma unroll
-			for (int k = 0; k < 8; k++)
-				transformCorner43(M, (k & 4) ? mx[0] : mn[0], (k & 2) ? mx[1] : mn[1], (k & 1) ? mx[2] : mn[2], vx[k], vy[k], vz[k]);
-			while (exactViews)
-			{
-				const uint32_t v = __ffs(exactViews) - 1;
-				exactViews &= exactViews - 1;
-				const ViewConst& V = P.views[v];
-				bool culled = false;
-				for (uint32_t i = 0; i < V.planeCount && !culled; i++)
-				{
-					const float nx = V.planes[i][0], ny = V.planes[i][1], nz = V.planes[i][2], nd = V.planes[i][3];
-					bool allBehind = true;
-					#pragma unroll
-					for (int k = 0; k < 8; k++)
-						allBehind = allBehind && (planeDistance(nx, ny, nz, nd, vx[k], vy[k], vz[k]) < 0.0f);
-					culled = allBehind;
-				}
-				if (!culled)
-					mask |= 1u << v;
-			}
-		}
+		mask = classifyBox<kViews>(P, M, boxA, boxB, work);
 		uint32_t readyCount = 1;
 		if (P.hasReady && mask) // a getReadyMeshesAsync override's extra predicate (e.g. sprite.cpp:90-97)
 		{
@@ -862,6 +979,8 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 		sh.maskOf[owner] = (uint16_t)mask;
 	}
 	__syncwarp();
+	if (kWorldOnly)
+		continue;
 
 	// ---- back to survivor order: isVisible, one ballot word per 32 survivors and view, the tile's visible count per view ----
 	// (no inter-tile dependency in this kernel: list positions are assigned by kScanChunks + kScatter below)
@@ -898,6 +1017,115 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 	} // tile loop
 }
 
+// ---- split path, second half: the pool's survivors pick up their transform's world matrix and are classified ----------------
+// One survivor per lane, one ballot word per warp step. The matrix comes from tWorld (kCull<.., true> over the surviving
+// transforms); a survivor whose transform is not there (cannot happen while the two prepasses see the same spheres; kept as
+// a guard) multiplies its chain from the SoA streams right here. Everything after the matrix is the fused kernel's phase 3.
+constexpr uint32_t kClassifyThreads = 256;
+static __device__ __noinline__ Mat43 chainFromStreams(const CullArgs& a, uint32_t ts)
+{
+	Mat43 M = loadLocal43(a, ts);
+	if (!(a.tFlags[ts] & kTfAncestors))
+		return M;
+	uint32_t p = a.tParent[ts], depth = 0;
+	while (p != kNone)
+	{
+		if (++depth > kMaxChainDepth)
+		{
+			atomicExch(&a.counters[kCtrError], (uint32_t)GSP_ERR_HIERARCHY);
+			break;
+		}
+		M = matMul43(loadLocal43(a, p), M);
+		p = a.tParent[p];
+	}
+	return M;
+}
+
+template<uint32_t kViews>
+__global__ void __launch_bounds__(kClassifyThreads) kClassify(const __grid_constant__ CullParams P, const __grid_constant__ CullArgs A)
+{
+	constexpr uint32_t kFull = 0xffffffffu;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t survivors = A.counters[A.surCounter], transforms = A.counters[A.tCounter];
+	const uint32_t liveWords = ((survivors + kWarpTile - 1) / kWarpTile) * kWarpItems; // kScatter reads the words in pairs
+	const uint32_t words = A.tiles * (kCullTile / 32);
+	const uint32_t warpsTotal = gridDim.x * (kClassifyThreads / 32);
+	for (uint32_t word = blockIdx.x * (kClassifyThreads / 32) + (threadIdx.x >> 5); word < liveWords; word += warpsTotal)
+	{
+		const uint32_t idx = word * 32 + lane;
+		const bool valid = idx < survivors;
+		uint32_t slot = kNone, ts = kNone, tidx = kNone;
+		if (valid)
+		{
+			slot = A.surList[idx]; ts = A.surTs[idx];
+		}
+		float4 boxA = make_float4(0.f, 0.f, 0.f, 0.f);
+		float2 boxB = make_float2(0.f, 0.f);
+		if (valid)
+		{
+			tidx = A.tIndex[ts];
+			boxA = A.aabbA[slot]; boxB = A.aabbB[slot];
+		}
+		Mat43 M;
+		#pragma unroll
+		for (int i = 0; i < 4; i++)
+			for (int l = 0; l < 3; l++)
+				M.c[i][l] = (i == l) ? 1.0f : 0.0f;
+		const bool found = valid && tidx < transforms && A.tList[tidx] == ts;
+		if (found)
+		{
+			const float4* w = A.tWorld + (size_t)tidx * kWorldStride;
+			const float4 w0 = w[0], w1 = w[1], w2 = w[2];
+			M.c[0][0] = w0.x; M.c[0][1] = w0.y; M.c[0][2] = w0.z; M.c[1][0] = w0.w;
+			M.c[1][1] = w1.x; M.c[1][2] = w1.y; M.c[2][0] = w1.z; M.c[2][1] = w1.w;
+			M.c[2][2] = w2.x; M.c[3][0] = w2.y; M.c[3][1] = w2.z; M.c[3][2] = w2.w;
+		}
+		else if (valid)
+			M = chainFromStreams(A, ts);
+		// translate(-cameraPosition, model): c3.xyz += -cam, w kept (matrix/transform.hpp:71-74)
+		M.c[3][0] = __fadd_rn(M.c[3][0], -P.cam[0]);
+		M.c[3][1] = __fadd_rn(M.c[3][1], -P.cam[1]);
+		M.c[3][2] = __fadd_rn(M.c[3][2], -P.cam[2]);
+		uint32_t mask = classifyBox<kViews>(P, M, boxA, boxB, valid);
+		uint32_t readyCount = 1;
+		if (P.hasReady && mask) // a getReadyMeshesAsync override's extra predicate (e.g. sprite.cpp:90-97)
+		{
+			readyCount = A.ready[slot];
+			if (readyCount == 0) mask = 0;
+		}
+		if (mask) // bakedModel = (float4x3)model (mesh.cpp:171,249)
+		{
+			float4* w = A.world + (size_t)idx * kWorldStride;
+			w[0] = make_float4(M.c[0][0], M.c[0][1], M.c[0][2], M.c[1][0]);
+			w[1] = make_float4(M.c[1][1], M.c[1][2], M.c[2][0], M.c[2][1]);
+			w[2] = make_float4(M.c[2][2], M.c[3][0], M.c[3][1], M.c[3][2]);
+			if (A.visibleView != kNone && ((mask >> A.visibleView) & 1u))
+				A.visible[slot] = 1; // (the prepass stored 0 for every slot)
+		}
+		uint32_t mine = 0, inst = 0; // lane v keeps the ballot word / instance count of view v
+		#pragma unroll
+		for (uint32_t v = 0; v < kViews; v++)
+		{
+			const bool bit = (mask >> v) & 1u;
+			const uint32_t b = __ballot_sync(kFull, bit);
+			if (lane == v) mine = b;
+			if (P.hasReady)
+			{
+				const uint32_t n = __reduce_add_sync(kFull, bit ? readyCount : 0u);
+				if (lane == v) inst = n;
+			}
+		}
+		if (lane < P.viewCount)
+		{
+			A.visBits[(size_t)lane * words + word] = mine;
+			if (mine)
+				atomicAdd(&A.chunkCount[(size_t)lane * A.chunks + idx / kChunkItems], (uint32_t)__popc(mine));
+			if (P.hasReady && inst)
+				atomicAdd(&A.counters[ctrPoolInst(P.poolIndex, lane)], inst);
+		}
+	}
+}
+
 // Exclusive scan of the per-chunk visible counts of one view (one block per view) -> list offset of every chunk.
 // Also publishes the list length after this pool (poolEnd), which is the draw count the host reads back.
 constexpr uint32_t kScanThreads = 1024;
@@ -910,7 +1138,7 @@ __global__ void __launch_bounds__(kScanThreads) kScanChunks(const __grid_constan
 	__shared__ uint32_t sCarry;
 	uint32_t* counts = A.chunkCount + (size_t)v * A.chunks;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t chunks = (A.counters[kCtrSurvivors + P.poolIndex] + kChunkItems - 1) / kChunkItems; // chunks that hold survivors
+	const uint32_t chunks = (A.counters[A.surCounter] + kChunkItems - 1) / kChunkItems; // chunks that hold survivors
 	if (threadIdx.x == 0)
 		sCarry = A.baseCounter[v] != kNone ? A.counters[A.baseCounter[v]] : 0;
 	__syncthreads();
@@ -973,7 +1201,7 @@ __global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constan
 		sHistDyn[i] = 0;
 	__syncthreads();
 	const uint32_t words = A.tiles * (kCullTile / 32);
-	const uint32_t survivors = A.counters[kCtrSurvivors + P.poolIndex];
+	const uint32_t survivors = A.counters[A.surCounter];
 	const uint32_t liveWords = ((survivors + kWarpTile - 1) / kWarpTile) * kWarpItems; // ballot words kCull wrote
 	const uint32_t chunks = (survivors + kChunkItems - 1) / kChunkItems;
 	const uint32_t units = chunks * P.viewCount;
@@ -1209,6 +1437,94 @@ uint32_t launchChainBounds(Context& c)
 	return 2;
 }
 
+static void setKernelAttributes(Context& c)
+{
+	// 8 resident blocks x 26 KB of shared memory need the large carve-out (function attributes are per device, and one
+	// context = one device, so the flag lives in the context)
+	if (c.cullAttrsSet)
+		return;
+	#define GSP_CARVEOUT(V) do { \
+		cudaFuncSetAttribute(kCull<V, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+		cudaFuncSetAttribute(kCull<V, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); } while (0)
+	GSP_CARVEOUT(1); GSP_CARVEOUT(2); GSP_CARVEOUT(3); GSP_CARVEOUT(4); GSP_CARVEOUT(5); GSP_CARVEOUT(6); GSP_CARVEOUT(8); GSP_CARVEOUT(16);
+	#undef GSP_CARVEOUT
+	c.cullAttrsSet = true;
+}
+
+static void commonArgs(Context& c, CullArgs& A)
+{
+	A.tRot = c.tf.rot; A.tPosSx = c.tf.posSx; A.tSYZ = c.tf.sYZ; A.tParent = c.tf.parent; A.tFlags = c.tf.flags;
+	A.tRecord = c.tf.record;
+	A.counters = c.dCounters;
+	A.tList = c.tf.tList; A.tIndex = c.tf.tIndex; A.tWorld = c.tf.tWorld; A.tCounter = kCtrSurvivorsT;
+	static const bool prepassOff = []{ const char* e = getenv("GSP_PREPASS"); return e && !strcmp(e, "0"); }();
+	A.prepassCull = prepassOff ? 0u : 1u;
+}
+
+// view count -> template instantiation (the view loops are unrolled at compile time: plane constants become direct
+// constant-bank operands)
+#define GSP_FOR_VIEW_COUNT(N, LAUNCH) do { \
+	if ((N) <= 1) { LAUNCH(1); } else if ((N) <= 2) { LAUNCH(2); } else if ((N) <= 3) { LAUNCH(3); } else if ((N) <= 4) { LAUNCH(4); } \
+	else if ((N) <= 5) { LAUNCH(5); } else if ((N) <= 6) { LAUNCH(6); } else if ((N) <= 8) { LAUNCH(8); } else { LAUNCH(16); } } while (0)
+
+// Split path, once per frame for all split pools: surviving transforms (for the views any split pool takes part in), their
+// list, and their world matrices.
+uint32_t launchSplitWorld(Context& c, cudaEvent_t before, cudaEvent_t after)
+{
+	auto& t = c.tf;
+	if (!c.anySplit || t.occupancy == 0)
+		return 0;
+	CullParams P = {};
+	CullArgs A = {};
+	bool any = false;
+	for (uint32_t v = 0; v < (uint32_t)c.views.size(); v++)
+	{
+		const gsp_view& gv = c.views[v];
+		ViewConst& V = P.views[v];
+		V.enabled = 0;
+		for (uint32_t p = 0; p < c.poolCount; p++)
+			if (c.pools[p].split && c.segOf[v][p] >= 0 && c.participates[v][p])
+				V.enabled = 1;
+		if (!V.enabled)
+			continue;
+		any = true;
+		memcpy(V.planes, gv.planes, sizeof(V.planes));
+		V.planeCount = gv.planeCount;
+		prepareClassifier(V);
+	}
+	if (!any)
+		return 0;
+	for (int i = 0; i < 3; i++)
+		P.cam[i] = c.cameraPos[i];
+	P.viewCount = (uint32_t)c.views.size();
+	P.occupancy = t.occupancy;
+	static const bool boxesOff = []{ const char* e = getenv("GSP_BOXGROUP"); return e && !strcmp(e, "0"); }();
+	if (!boxesOff)
+		prepareBoxGroup(P);
+	commonArgs(c, A);
+	A.surBits = t.tBits; A.blockCount = t.tBlockCount; A.bucketCount = t.tBucketCount;
+	A.surList = t.tList; A.surTs = t.tList; // the items of the world-only kCull ARE transform slots
+	A.surCounter = kCtrSurvivorsT;
+	A.visibleView = kNone;
+	A.tiles = (t.occupancy + kCullTile - 1) / kCullTile;
+	A.chunks = (A.tiles + kChunkTiles - 1) / kChunkTiles;
+	setKernelAttributes(c);
+	if (before) cudaEventRecord(before, c.stream);
+	const uint32_t preBlocks = (t.occupancy + kPreTile - 1) / kPreTile;
+	const uint32_t cullBlocks = std::max(1u, std::min(A.tiles, c.smCount * kCullBlocksPerSM));
+	CompactArgs K;
+	K.bits = t.tBits; K.blockCount = t.tBlockCount; K.bucketCount = t.tBucketCount; K.list = t.tList; K.aux = t.tIndex;
+	K.tslot = nullptr; K.counters = c.dCounters; K.counterIndex = kCtrSurvivorsT; K.blocks = preBlocks;
+	#define GSP_LAUNCH_WORLD(V) do { \
+		kPrepassT<V><<<preBlocks, kPreThreads, 0, c.stream>>>(P, A); \
+		kCompactSurvivors<true><<<(preBlocks + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, c.stream>>>(K); \
+		kCull<V, true><<<cullBlocks, kCullThreads, 0, c.stream>>>(P, A); } while (0)
+	GSP_FOR_VIEW_COUNT(P.viewCount, GSP_LAUNCH_WORLD);
+	#undef GSP_LAUNCH_WORLD
+	if (after) cudaEventRecord(after, c.stream);
+	return 3;
+}
+
 uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEvent_t afterCull, cudaEvent_t afterScatter)
 {
 	auto& p = c.pools[pool];
@@ -1257,50 +1573,33 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEve
 	if (!boxesOff)
 		prepareBoxGroup(P);
 
-	A.tRot = c.tf.rot; A.tPosSx = c.tf.posSx; A.tSYZ = c.tf.sYZ; A.tParent = c.tf.parent; A.tFlags = c.tf.flags;
-	A.tRecord = c.tf.record;
+	commonArgs(c, A);
 	A.aabbA = p.aabbA; A.aabbB = p.aabbB; A.tslot = p.tslot; A.mflags = p.flags; A.ready = p.ready;
 	A.surList = p.surList; A.surTs = p.surTs; A.world = p.world; A.visible = p.visible;
-	A.visBits = p.visBits; A.chunkCount = p.cullStatus; A.counters = c.dCounters;
+	A.visBits = p.visBits; A.chunkCount = p.cullStatus;
 	A.keys = c.keys[0]; A.payloads = c.payloads[0]; A.sortHist = c.sortHist;
 	A.surBits = p.surBits; A.blockCount = p.blockCount; A.bucketCount = p.bucketCount;
+	A.surCounter = kCtrSurvivors + pool;
 	A.tiles = (p.occupancy + kCullTile - 1) / kCullTile;
 	A.chunks = (A.tiles + kChunkTiles - 1) / kChunkTiles;
-	static const bool prepassOff = []{ const char* e = getenv("GSP_PREPASS"); return e && !strcmp(e, "0"); }();
-	A.prepassCull = prepassOff ? 0u : 1u;
 	p.visibleValid = A.visibleView != kNone;
+	setKernelAttributes(c);
 
-	// 7 resident blocks x 31 KB of shared memory need the large carve-out (function attributes are per device, and one
-	// context = one device, so the flag lives in the context)
-	if (!c.cullAttrsSet)
-	{
-		cudaFuncSetAttribute(kCull<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(kCull<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(kCull<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(kCull<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(kCull<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(kCull<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(kCull<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(kCull<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		c.cullAttrsSet = true;
-	}
-	// the view loops are unrolled at compile time (plane constants become direct constant-bank operands)
 	const uint32_t preBlocks = (p.occupancy + kPreTile - 1) / kPreTile;
-	// kCull is persistent: its warps stride over the survivor tiles (the survivor count only exists on the device)
+	// kCull / kClassify are persistent: their warps stride over the survivors (the count only exists on the device)
 	const uint32_t cullBlocks = std::max(1u, std::min(A.tiles, c.smCount * kCullBlocksPerSM));
+	const uint32_t classifyBlocks = std::max(1u, std::min((p.occupancy + kClassifyThreads - 1) / kClassifyThreads, c.smCount * 8u));
+	const bool split = p.split && !isUI && c.anySplit;
+	CompactArgs K;
+	K.bits = p.surBits; K.blockCount = p.blockCount; K.bucketCount = p.bucketCount; K.list = p.surList; K.aux = p.surTs;
+	K.tslot = p.tslot; K.counters = c.dCounters; K.counterIndex = kCtrSurvivors + pool; K.blocks = preBlocks;
 	#define GSP_LAUNCH_CULL(V) do { \
 		kPrepass<V><<<preBlocks, kPreThreads, 0, c.stream>>>(P, A); \
-		kCompactSurvivors<<<(preBlocks + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, c.stream>>>(P, A, preBlocks); \
+		kCompactSurvivors<false><<<(preBlocks + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, c.stream>>>(K); \
 		if (afterPrepass) cudaEventRecord(afterPrepass, c.stream); \
-		kCull<V><<<cullBlocks, kCullThreads, 0, c.stream>>>(P, A); } while (0)
-	if (P.viewCount <= 1) GSP_LAUNCH_CULL(1);
-	else if (P.viewCount <= 2) GSP_LAUNCH_CULL(2);
-	else if (P.viewCount <= 3) GSP_LAUNCH_CULL(3);
-	else if (P.viewCount <= 4) GSP_LAUNCH_CULL(4);
-	else if (P.viewCount <= 5) GSP_LAUNCH_CULL(5); // camera + 4 cascades
-	else if (P.viewCount <= 6) GSP_LAUNCH_CULL(6);
-	else if (P.viewCount <= 8) GSP_LAUNCH_CULL(8);
-	else GSP_LAUNCH_CULL(16);
+		if (split) kClassify<V><<<classifyBlocks, kClassifyThreads, 0, c.stream>>>(P, A); \
+		else kCull<V, false><<<cullBlocks, kCullThreads, 0, c.stream>>>(P, A); } while (0)
+	GSP_FOR_VIEW_COUNT(P.viewCount, GSP_LAUNCH_CULL);
 	#undef GSP_LAUNCH_CULL
 	if (afterCull) cudaEventRecord(afterCull, c.stream);
 	kScanChunks<<<P.viewCount, kScanThreads, 0, c.stream>>>(P, A);

@@ -59,6 +59,11 @@ struct TransformsDev
 	uint32_t* rho = nullptr;       // bits of the largest box radius of any mesh on the transform (kLinkPool)
 	uint32_t* chainRoot = nullptr; // root slot of the transform's parent chain
 	uint32_t* rootW = nullptr;     // per ROOT slot: bits of max over its hierarchy of D + S * rho
+	uint32_t* poolMask = nullptr;  // bit p: pool p holds a mesh on this transform (kLinkPool)
+	// split path (allocated when a pool needs it): surviving transforms and their world matrices
+	uint32_t* tBits = nullptr; uint32_t* tBlockCount = nullptr; uint32_t* tBucketCount = nullptr; // (tBucketCount inside frameZero)
+	uint32_t* tList = nullptr; uint32_t* tIndex = nullptr; float4* tWorld = nullptr;
+	uint32_t splitCap = 0;
 	uint32_t* entityToSlot = nullptr; // entity id -> slot + 1
 	uint32_t entityCap = 0;
 };
@@ -68,6 +73,7 @@ struct PoolDev
 	uint32_t occupancy = 0, capacity = 0, count = 0, stride = 0, renderType = 0, drawReady = 0;
 	uint32_t viewMask = 0xFFFFFFFFu; // bit v: isDrawReady(views[v].shadowPass) (gsp_set_pool_view_mask)
 	bool hasReady = false, set = false;
+	bool split = false; // the pool's hierarchies reach outside the pool: world matrices per transform, then kClassify (cull.cu)
 	float4* aabbA = nullptr;  // min xyz, max x
 	float2* aabbB = nullptr;  // max y, z
 	uint32_t* entity = nullptr;
@@ -160,6 +166,9 @@ struct Context
 	float cameraPos[3] = {0, 0, 0};
 	bool viewsSet = false, linkDirty = true, layoutDirty = true, resultsValid = false;
 	bool chainDirty = true; // the transform pool changed since kChainBounds last ran
+	bool anySplit = false;  // some pool takes the split path this frame
+	bool splitRan = false;
+	cudaEvent_t splitEvents[2] = {};
 	bool cullAttrsSet = false, scatterAttrSet = false; // kernel function attributes applied on this context's device
 	bool frameEnqueued = false; // a frame has been enqueued since the last structural change (its results may still be in flight)
 
@@ -210,8 +219,10 @@ __host__ __device__ inline uint32_t ctrPoolEnd(uint32_t pool, uint32_t view) { r
 __host__ __device__ inline uint32_t ctrPoolInst(uint32_t pool, uint32_t view) { return kMaxPools * kMaxViews + pool * kMaxViews + view; }
 constexpr uint32_t kCtrCullTicket = 2 * kMaxPools * kMaxViews; // + pool (unused)
 constexpr uint32_t kCtrSurvivors = kCtrCullTicket + kMaxPools;  // + pool: survivors of the prepass
-constexpr uint32_t kCtrError = kCtrSurvivors + kMaxPools;
-constexpr uint32_t kCtrCount = kCtrError + 8;
+constexpr uint32_t kCtrSurvivorsT = kCtrSurvivors + kMaxPools; // surviving transforms (split path)
+constexpr uint32_t kCtrCross = kCtrSurvivorsT + 1;            // + pool: slots whose parent transform has no mesh in the pool (link time)
+constexpr uint32_t kCtrError = kCtrCross + kMaxPools;
+constexpr uint32_t kCtrCount = kCtrError + 8;  // (the pinned host mirror has 16 more words: staging scalars, link-time statistics)
 
 // float4 per slot in PoolDev::world: the 48-byte matrix, unpadded. (Padding it to one 64-byte DRAM line was measured and is
 // slower: neighbouring slots are usually visible together and then share lines; 0.980 -> 1.012 ms per frame on C4.)
@@ -233,6 +244,7 @@ uint32_t launchBuildHierarchy(Context& c);
 uint32_t launchStagePool(Context& c, uint32_t pool, const void* dAos, uint32_t stride, uint32_t occupancy);
 uint32_t launchLink(Context& c);
 uint32_t launchChainBounds(Context& c);
+uint32_t launchSplitWorld(Context& c, cudaEvent_t before, cudaEvent_t after);
 uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEvent_t afterCull, cudaEvent_t afterScatter);
 uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kStageThreads) kStagePool(const uint8_t* __res
 // a NaN box keeps its transform from ever being culled by the prepass.
 __global__ void __launch_bounds__(256) kLinkPool(uint32_t count, const uint32_t* __restrict__ entity,
 	const uint32_t* __restrict__ entityToSlot, uint32_t entityCap, uint32_t* __restrict__ tslot,
-	const float* __restrict__ radius, uint32_t* __restrict__ tRho)
+	const float* __restrict__ radius, uint32_t* __restrict__ tRho, uint32_t* __restrict__ tPoolMask, uint32_t poolBit)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count)
@@ -210,7 +210,33 @@ __global__ void __launch_bounds__(256) kLinkPool(uint32_t count, const uint32_t*
 	uint32_t s = (e && e < entityCap) ? entityToSlot[e] : 0;
 	tslot[i] = s ? s - 1 : kNone;
 	if (s)
+	{
 		atomicMax(&tRho[s - 1], __float_as_uint(radius[i]));
+		atomicOr(&tPoolMask[s - 1], poolBit);
+	}
+}
+
+// How many slots of the pool walk a chain whose first ancestor carries no mesh of the SAME pool: such chains cannot be found
+// among the pool's own survivors, and when they are common the pool takes the split path (world matrices per transform).
+__global__ void __launch_bounds__(256) kPoolLocality(uint32_t count, const uint32_t* __restrict__ tslot,
+	const uint32_t* __restrict__ tParent, const uint16_t* __restrict__ tFlags, const uint32_t* __restrict__ tPoolMask,
+	uint32_t poolBit, uint32_t* __restrict__ cross)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool outside = false;
+	if (i < count)
+	{
+		const uint32_t ts = tslot[i];
+		if (ts != kNone)
+		{
+			const uint16_t f = tFlags[ts];
+			const uint32_t p = tParent[ts];
+			outside = (f & kTfLive) && (f & kTfAncestors) && p != kNone && !(tPoolMask[p] & poolBit);
+		}
+	}
+	const uint32_t n = __popc(__ballot_sync(0xffffffffu, outside));
+	if ((threadIdx.x & 31) == 0 && n)
+		atomicAdd(cross, n);
 }
 
 // Slots per tile: a multiple of 4 (tile bytes stay a multiple of 16) that fits the shared-memory budget.
@@ -268,14 +294,27 @@ uint32_t launchLink(Context& c)
 {
 	uint32_t n = 0;
 	if (c.tf.occupancy)
+	{
 		cudaMemsetAsync(c.tf.rho, 0, (size_t)c.tf.occupancy * sizeof(uint32_t), c.stream);
+		cudaMemsetAsync(c.tf.poolMask, 0, (size_t)c.tf.occupancy * sizeof(uint32_t), c.stream);
+	}
+	cudaMemsetAsync(c.dCounters + kCtrCross, 0, kMaxPools * sizeof(uint32_t), c.stream);
 	for (uint32_t i = 0; i < c.poolCount; i++)
 	{
 		auto& p = c.pools[i];
 		if (!p.set || p.occupancy == 0)
 			continue;
 		kLinkPool<<<blocksFor(p.occupancy, 256), 256, 0, c.stream>>>(p.occupancy, p.entity, c.tf.entityToSlot,
-			c.tf.entityCap, p.tslot, p.radius, c.tf.rho);
+			c.tf.entityCap, p.tslot, p.radius, c.tf.rho, c.tf.poolMask, 1u << i);
+		n++;
+	}
+	for (uint32_t i = 0; i < c.poolCount; i++)
+	{
+		auto& p = c.pools[i];
+		if (!p.set || p.occupancy == 0)
+			continue;
+		kPoolLocality<<<blocksFor(p.occupancy, 256), 256, 0, c.stream>>>(p.occupancy, p.tslot, c.tf.parent, c.tf.flags,
+			c.tf.poolMask, 1u << i, c.dCounters + kCtrCross + i);
 		n++;
 	}
 	return n;
