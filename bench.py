@@ -74,9 +74,15 @@ def load_traffic(workload: str, n: int, kernel_prefix: str):
             continue
         if doc.get("workload") != workload or int(doc.get("entities", 0)) != n:
             continue
-        for k in doc.get("kernels", []):
-            if kernel_prefix in k["kernel"]:
-                return {"bytes": int(k["traffic_bytes"]), "source": f"profiles/{path.name}"}
+        # kernel_prefix may name several kernels ("kPrepass+kCompactSurvivors+kCull"): one launch of each, summed
+        total, found = 0, 0
+        for want in kernel_prefix.split("+"):
+            for k in doc.get("kernels", []):
+                if want in k["kernel"]:
+                    total += int(k["traffic_bytes"]); found += 1
+                    break
+        if found == len(kernel_prefix.split("+")):
+            return {"bytes": total, "source": f"profiles/{path.name}"}
     return None
 
 
@@ -197,14 +203,17 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = reference_engine_run(args.workload, args.ref_sample, args.steps, args.warmup, args.seed)
+    sample = args.ref_sample or WORKLOADS[args.workload][1]
+    res = reference_engine_run(args.workload, sample, args.steps, args.warmup, args.seed)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][2]}", "entities_per_step": args.ref_sample,
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][2]}", "entities_per_gpu": sample,
+                   "entities_total": sample, "entities_per_step": sample,
                    "views": int(frame_views(args.workload).size), "visible_total": res["visible"],
-                   "note": "reference CPU thread-pool path on host cores; each step is a bounded sample of the workload"},
+                   "note": "the reference's own prepareMeshes (thread pool on all host cores) over the WHOLE workload, "
+                           "one call per view per step as mesh.cpp:795-847,893-903 does"},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,6 +221,156 @@ def run_reference_arm(args):
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def shard_scene(whole, a: int, b: int):
+    """Entities [a, b) of `whole` as a scene of their own (a and b at hierarchy boundaries: parents stay inside)."""
+    pools = []
+    for pd in whole.pools:
+        sel = (pd.entity_index >= a) & (pd.entity_index < b)
+        pools.append(scenes.PoolDesc(pd.render_type, (pd.entity_index[sel] - a).astype(np.uint32), pd.aabb[sel],
+                                     None if pd.enabled is None else pd.enabled[sel], None if pd.ready is None else pd.ready[sel],
+                                     pd.stride, pd.draw_ready))
+    return scenes.SceneDesc(whole.position[a:b], whole.rotation[a:b], whole.scale[a:b],
+                            np.where(whole.parent[a:b] >= 0, whole.parent[a:b] - a, -1).astype(np.int32), whole.tflags[a:b],
+                            pools, None, whole.camera_pos, whole.name)
+
+
+def stage_scene(sp, scene, views):
+    t, pools = scenes.build_aos(scene)
+    sp.set_transforms(t, t.dtype.itemsize, t.size)
+    sp.set_pool_count(len(pools))
+    for k, m in enumerate(pools):
+        sp.set_mesh_pool(k, scene.pools[k].render_type, m, m.dtype.itemsize, m.size)
+    sp.set_views(views, scene.camera_pos)
+    return [m.size for m in pools]
+
+
+def verify_exchange(workload: str, rank: int, world: int, local_rank: int, stream, per_rank: int = 180_000):
+    """Merged-order check over the REAL exchange (NCCL inside the library): a reduced scene of world x per_rank entities is
+    cut into contiguous ranges, every rank prepares its range and exchanges, rank 0 also sorts the WHOLE scene on its own GPU;
+    the concatenated slices of every list must equal that single-GPU sort — key bits and (global) slot order."""
+    import torch
+    import torch.distributed as dist
+    from garden_b200.binding import ScenePrep
+    from garden_b200.dist import PipelinedRunMerger
+    cfg = WORKLOADS[workload][0]
+    chain = scenes.CONFIGS[cfg]["depth"] + 1
+    per_rank = (per_rank // chain) * chain
+    whole = scenes.config_scene(cfg, n=per_rank * world, seed=4321)
+    whole.camera_pos = camera_pos()
+    views = frame_views(workload)
+    sp = ScenePrep(local_rank)
+    sp.set_stream(stream.cuda_stream)
+    stage_scene(sp, shard_scene(whole, rank * per_rank, (rank + 1) * per_rank), views)
+    pm = PipelinedRunMerger(sp)
+    for _ in range(2):
+        pm.frame()
+    pm.finish()
+    mine = pm.last_result()["slices"]
+    everyone = [None] * world
+    dist.all_gather_object(everyone, [(s[0], s[1], s[2], s[3]) for s in mine])
+    sp.close()
+    out = None
+    if rank == 0:
+        one = ScenePrep(local_rank)
+        one.set_stream(stream.cuda_stream)
+        pool_sizes = stage_scene(one, whole, views)
+        one.run()
+        counts = one.list_counts().astype(np.int64)
+        total = int(counts.sum())
+        k = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+        p = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+        one.export_runs(k.data_ptr(), p.data_ptr(), max(total, 1))
+        one.sync()
+        torch.cuda.synchronize()
+        kk, pp = k[:total].cpu().numpy().view(np.uint32), p[:total].cpu().numpy().view(np.uint32)
+        one.close()
+        # slot of a shard-local payload in the whole scene: pool slots are handed out in entity order, so rank r's slots of
+        # pool q start where the lower ranks' slots of that pool end
+        shard_pool_sizes = np.zeros((world, len(pool_sizes)), np.int64)
+        for r in range(world):
+            for q, pd in enumerate(whole.pools):
+                shard_pool_sizes[r, q] = int(((pd.entity_index >= r * per_rank) & (pd.entity_index < (r + 1) * per_rank)).sum())
+        first_slot = np.zeros_like(shard_pool_sizes)
+        first_slot[1:] = np.cumsum(shard_pool_sizes, axis=0)[:-1]
+        off, elements, ok = 0, 0, True
+        for l in range(counts.size):
+            want_k, want_p = kk[off:off + counts[l]], pp[off:off + counts[l]]
+            off += int(counts[l])
+            got_k, got_p = [], []
+            pos = 0
+            for r in range(world):
+                start, gk, gp, gr = everyone[r][l]
+                ok = ok and start == pos
+                pos += gk.size
+                pool = (gp >> 28).astype(np.int64)
+                slot = (gp & 0x0FFFFFFF).astype(np.int64) + first_slot[gr.astype(np.int64), pool]
+                got_k.append(gk); got_p.append(((pool << 28) | slot).astype(np.uint32))
+            got_k, got_p = np.concatenate(got_k), np.concatenate(got_p)
+            ok = ok and got_k.size == want_k.size and np.array_equal(got_k, want_k) and np.array_equal(got_p, want_p)
+            elements += int(want_k.size)
+        out = {"ok": bool(ok), "entities": int(per_rank * world), "lists": int(counts.size), "merged_elements": elements,
+               "protocol": "alltoall" if pm.all_to_all else "allgather",
+               "what": "slices of all ranks (real NCCL, exchange inside the library) concatenated == one single-GPU sort of the "
+                       "whole scene: key bits and slot order, every list"}
+        if not ok:
+            raise RuntimeError(f"multi-GPU merged order differs from the single-GPU sort: {out}")
+    dist.barrier()
+    return out
+
+
+def strong_scaling_point(args, rank: int, world: int, local_rank: int, stream):
+    """Device-resident frame time with the workload's N in TOTAL, split over the ranks (contiguous ranges of ONE scene)."""
+    import torch
+    import torch.distributed as dist
+    from garden_b200.binding import ScenePrep
+    from garden_b200.dist import PipelinedRunMerger
+    cfg, default_n, _ = WORKLOADS[args.workload]
+    total = args.entities or default_n
+    if args.workload == "C5":
+        total = (args.entities or default_n) * 8  # configs[4]: 64M in total
+    chain = scenes.CONFIGS[cfg]["depth"] + 1
+    per = (total // world // chain) * chain
+    scene = scenes.config_scene(cfg, n=per, seed=args.seed + 7919 * rank)  # (same generator and density as the weak shards)
+    scene.camera_pos = camera_pos()
+    views = frame_views(args.workload)
+    sp = ScenePrep(local_rank)
+    sp.set_stream(stream.cuda_stream)
+    stage_scene(sp, scene, views)
+    pm = PipelinedRunMerger(sp)
+    for _ in range(max(args.warmup, 3)):
+        pm.frame()
+    pm.finish()
+    sp.sync()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(5):
+        pm.frame()
+    p1.record(stream)
+    pm.finish(); sp.sync()
+    reps = max(1, int(np.ceil(args.min_seconds * 0.5e3 / (max(p0.elapsed_time(p1) / 5, 1e-3) * args.steps))))
+    r = torch.tensor([reps], dtype=torch.int64, device="cuda")
+    dist.all_reduce(r, op=dist.ReduceOp.MAX)
+    frames = args.steps * int(r.item())
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(frames):
+        pm.frame()
+    pm.finish()
+    e1.record(stream)
+    sp.sync()
+    dist.barrier(); torch.cuda.synchronize()
+    stats = torch.tensor([e0.elapsed_time(e1), float(sp.last_visible_total())], dtype=torch.float64, device="cuda")
+    mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    ms = float(mx[0]) / frames
+    sp.close()
+    return {"scaling": "strong", "entities_total": int(per * world), "entities_per_gpu": int(per), "ms_per_step": ms,
+            "value": per * world / (ms * 1e-3), "unit": UNIT, "visible_total": int(sm[1]), "frames_timed": frames,
+            "protocol": "alltoall" if pm.all_to_all else "allgather"}
 
 # ----------------------------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
@@ -230,6 +389,14 @@ def run_b200_arm(args):
 
     cfg, default_n, desc = WORKLOADS[args.workload]
     n = args.entities or default_n
+    merge_check, strong = None, None
+    if world > 1:
+        pre_stream = torch.cuda.Stream()
+        torch.cuda.set_stream(pre_stream)
+        if not args.no_verify:
+            merge_check = verify_exchange(args.workload, rank, world, local_rank, pre_stream)
+        if args.scaling in ("strong", "both"):
+            strong = strong_scaling_point(args, rank, world, local_rank, pre_stream)
     # weak scaling: every GPU owns an N-entity shard (contiguous entity range of a world-size * N scene)
     scene = scenes.config_scene(cfg, n=n, seed=args.seed + 7919 * rank)
     scene.camera_pos = camera_pos()
@@ -284,11 +451,28 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.start()
         sampler.wait_first_sample()
+    # a frame lasts well under a millisecond: every step is repeated `reps` times back to back so that the timed region lasts
+    # at least --min-seconds (clocks and power are then sampled under sustained load); ms_per_step stays per FRAME
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(5):
+        frame()
+    p1.record(stream)
+    if merger is not None:
+        merger.finish()
+    sp.sync()
+    probe_ms = max(p0.elapsed_time(p1) / 5, 1e-3)
+    reps = max(1, int(np.ceil(args.min_seconds * 1e3 / (probe_ms * args.steps))))
+    if world > 1:
+        r = torch.tensor([reps], dtype=torch.int64, device="cuda")
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        reps = int(r.item())
+    frames_timed = args.steps * reps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_begin = time.time()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(frames_timed):
         frame()
     if merger is not None:
         merger.finish()  # the compute stream waits for the last exchanges; every frame's flags are checked clean
@@ -316,7 +500,7 @@ def run_b200_arm(args):
         latency_ms = l0.elapsed_time(l1) / lat_steps
         exchange_parts = merger.timing_summary()
         merger.timing = None
-        exchange_bytes = int(merger.sets[0]["gathered"].numel() * 4)
+        exchange_bytes = merger.bytes_received()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches_per_step = sp.last_launch_count() + (merger.launches_per_frame if merger else 0)
     visible_total = sp.last_visible_total()
@@ -470,15 +654,23 @@ def run_b200_arm(args):
         latency_ms = float(mx[4])
     else:
         visible_sum = float(visible_total)
-    ms_per_step = elapsed_ms / args.steps
+    ms_per_step = elapsed_ms / frames_timed
     total_entities = n * world
     value = total_entities / (ms_per_step * 1e-3)
 
     if rank == 0:
         peak, peak_src = load_peaks()
         alg_bytes = BYTES_PER_ENTITY * n + BYTES_PER_VISIBLE * visible_total  # per GPU
-        names = ["link", "world matrices + culling (kCull)", "compaction + keys + sort histograms (kScanChunks + kScatter)",
-                 "(sort histogram: fused into kScatter)", "sort passes (kSortPass x4)", "record emission (kEmit)"]
+        # the cull stage = filter + conservative prepass (kPrepass) + survivor compaction (kCompactSurvivors) + world matrices
+        # and exact culling of the survivors (kCull, or kPrepassT/kCull<world>/kClassify on the split path): together they
+        # consume the 75 B/entity input stream of SURVEY.md 8d, so the stage is one roofline entry
+        phase = phase.copy()
+        cull_parts = {"prepass + survivor compaction (kPrepass, kCompactSurvivors)": round(float(phase[3]), 4),
+                      "world matrices + exact culling of the survivors (kCull)": round(float(phase[1]), 4)}
+        phase[1] += phase[3]; phase[3] = 0.0
+        names = ["link", "cull stage: filter + prepass + survivor compaction + world matrices + culling (kPrepass, kCompactSurvivors, kCull)",
+                 "compaction + keys + sort histograms (kScanChunks + kScatter)",
+                 "(unused)", "sort passes (kSortPass x4)", "record emission (kEmit)"]
         # algorithmic bytes attributed to each kernel group; they add up to 75*N + 132*SumVis:
         # inputs + isVisible | the 4 B/key histogram read of the formula (done on the fly here) | - |
         # 4 x (8 read + 8 write) | 64 B record write
@@ -490,6 +682,8 @@ def run_b200_arm(args):
             gbs = kernel_bytes[i] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             kernels.append({"name": names[i], "ms": round(ms, 4), "share": round(ms / frame_ms, 3) if frame_ms else 0,
                             "bytes": int(kernel_bytes[i]), "GBps": round(gbs, 1), "frac": round(gbs / peak, 3)})
+            if i == 1:
+                kernels[-1]["parts_ms"] = cull_parts
         dom = max(range(len(kernels)), key=lambda i: kernels[i]["ms"])
         frame_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
         roofline = {
@@ -500,21 +694,24 @@ def run_b200_arm(args):
                       "formula": "75*N + 132*SumVis (SURVEY.md 8d), per GPU, over the timed ms_per_step"},
             "kernels": kernels,
         }
-        kernel_symbol = {1: "kCull", 2: "kScatter", 4: "kSortPass", 5: "kEmit"}[(1, 2, 4, 5)[dom]]
+        kernel_symbol = {1: "kPrepass+kCompactSurvivors+kCull", 2: "kScatter", 4: "kSortPass", 5: "kEmit"}[(1, 2, 4, 5)[dom]]
         traffic = load_traffic(args.workload, n, kernel_symbol)
         if traffic:
             roofline["traffic"] = traffic["bytes"]
-            roofline["traffic_source"] = traffic["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+            roofline["traffic_source"] = traffic["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum, one launch of each kernel of the entry)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "entities_per_gpu": n, "entities_total": total_entities,
+                       "frames_timed": frames_timed,
+                       "timing": f"every one of the {args.steps} steps repeated {reps}x back to back (sustained load, "
+                                 f">= {args.min_seconds} s); ms_per_step is per frame",
                        "views": int(views.size), "visible_total": int(visible_sum),
                        "l2": "inputs larger than L2 (%.2f GB of SoA streams per frame vs 126 MB L2)" % (75 * n / 1e9),
-                       "sharding": ("contiguous entity ranges per GPU, all views per GPU; sorted runs all-gathered over NCCL "
-                                    "(one fixed-capacity block per rank, no host synchronisation) and k-way merged by key "
-                                    "range; frame k's exchange " + ("is serialised with" if args.no_overlap else "overlaps")
+                       "sharding": ("contiguous entity ranges per GPU, all views per GPU; sorted runs exchanged over NCCL by "
+                                    "key range (fixed-capacity blocks, no host synchronisation) and k-way merged; "
+                                    "frame k's exchange " + ("is serialised with" if args.no_overlap else "overlaps")
                                     + " frame k+1's cull") if world > 1 else "single GPU"},
             "roofline": roofline,
             "e2e": {"value": total_entities / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
@@ -527,16 +724,22 @@ def run_b200_arm(args):
                     "delta_writeback": {"value": total_entities / e2e_delta_s, "ms_per_step": e2e_delta_s * 1e3,
                                         "changed_slots_per_step": changed_total / e2e_steps},
                     "incremental": incremental},
-            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches": int(launches_per_step * frames_timed),
             "clocks": clocks,
         }
         if next_rows:
             line["next_rows"] = next_rows
         if world > 1:
-            line["exchange"] = {"frame_latency_ms_serialised": latency_ms, "allgather_bytes_per_rank": exchange_bytes,
-                                "collectives_per_frame": 1, "host_syncs_per_frame": 0, "parts_rank0": exchange_parts}
+            line["exchange"] = {"frame_latency_ms_serialised": latency_ms, "bytes_received_per_rank": exchange_bytes,
+                                "protocol": "alltoall" if merger.all_to_all else "allgather",
+                                "collectives_per_frame": 3 if merger.all_to_all else 1, "host_syncs_per_frame": 0,
+                                "where": "inside libgarden_sceneprep.so (gsp_exchange_async, NCCL loaded by the library)",
+                                "parts_rank0": exchange_parts}
+            line["config"]["merge_check"] = merge_check
+            if strong is not None:
+                line["config"]["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            res = reference_engine_run(args.workload, args.ref_sample, args.ref_steps, 1, args.seed)
+            res = reference_engine_run(args.workload, args.ref_sample or n, args.ref_steps, 1, args.seed)
             line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                                     "sample": res["sample"], "ms_per_step": res["ms_per_step"]}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
@@ -561,10 +764,16 @@ def main():
     ap.add_argument("--entities", type=int, default=0, help="override N per GPU (default: the workload's N)")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-sample", type=int, default=2_000_000, help="entities in the CPU reference sample")
-    ap.add_argument("--ref-steps", type=int, default=20)
+    ap.add_argument("--ref-sample", type=int, default=0, help="entities the CPU reference runs on (0 = the whole workload)")
+    ap.add_argument("--ref-steps", type=int, default=5, help="frames of the in-line cpu_baseline leg")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="the device-resident loop repeats every step until the timed region lasts at least this long")
+    ap.add_argument("--scaling", default="both", choices=["weak", "strong", "both"],
+                    help="N > 1: weak = the workload's N per GPU, strong = the workload's N in total; both = weak is the "
+                         "headline value and the strong-scaling numbers go under config.strong")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: run the exchange on the compute stream (no overlap)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: wait for every frame's exchange before the next frame")
+    ap.add_argument("--no-verify", action="store_true", help="N>1: skip the merged-order check against a single-GPU sort")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

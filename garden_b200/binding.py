@@ -53,6 +53,21 @@ SYMBOLS = {
     "gsp_merge_plan_words": (_u32, [_u32, _u32]),
     "gsp_export_runs_packed": (_i32, [_vp, _vp, _u32]),
     "gsp_merge_gathered_packed": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "gsp_comm_unique_id": (_i32, [_vp]),
+    "gsp_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
+    "gsp_comm_init_all": (_i32, [_vp, _u32]),
+    "gsp_comm_destroy": (_i32, [_vp]),
+    "gsp_comm_info": (_i32, [_vp, _pu32, _pu32, _pu32, _pu32]),
+    "gsp_exchange_configure": (_i32, [_vp, _u32]),
+    "gsp_exchange_autosize": (_i32, [_vp, _pu32]),
+    "gsp_exchange_async": (_i32, [_vp]),
+    "gsp_exchange_poll": (_i32, [_vp, _i32, _pu32, _pu32]),
+    "gsp_exchange_finish": (_i32, [_vp, _pu32, _pu32]),
+    "gsp_get_merged_device": (_i32, [_vp, _u32, _pp, _pp, _pp, _pu32, _pu32]),
+    "gsp_exchange_set_timing": (_i32, [_vp, _i32]),
+    "gsp_exchange_times": (_i32, [_vp, _vp]),
+    "gsp_exchange_bytes_received": (_u64, [_vp]),
+    "gsp_copy_to_host": (_i32, [_vp, _vp, _vp, C.c_size_t]),
     "gsp_emit_instances": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _u32, _u32, _u32]),
     "gsp_emit_instances_device": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _u32, _u32, _u32]),
     "gsp_frustum_planes": (None, [_vp, _vp]),

@@ -14,7 +14,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "libgarden_sceneprep.so"
-SOURCES = ["staging.cu", "cull.cu", "sort.cu", "emit.cu", "merge.cu", "visible.cu", "selftest.cu", "next.cu", "api.cu"]
+SOURCES = ["staging.cu", "cull.cu", "sort.cu", "emit.cu", "merge.cu", "exchange.cu", "visible.cu", "selftest.cu", "next.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # parity kernels spell every rounding explicitly (__fmul_rn/__fmaf_rn/...); -fmad=false is belt and braces
@@ -60,7 +60,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         if proc.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
     tmp = LIB.with_suffix(".so.tmp")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs]
+    # (NCCL is resolved with dlopen at run time — exchange.cu — so the library itself only needs libdl)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs, "-ldl"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")

@@ -11,11 +11,6 @@
 
 using namespace gsp;
 
-struct gsp_context
-{
-	Context c;
-};
-
 static std::string gCreateError;
 
 #define GSP_CUDA(call)                                                                             \
@@ -128,6 +123,7 @@ void gsp_destroy(gsp_context* ctx)
 	Context& c = ctx->c;
 	cudaSetDevice(c.device);
 	cudaStreamSynchronize(c.stream);
+	destroyExchange(c);
 	if (c.copyStream) cudaStreamSynchronize(c.copyStream);
 	auto& t = c.tf;
 	cudaFree(t.rot); cudaFree(t.posSx); cudaFree(t.sYZ); cudaFree(t.parent); cudaFree(t.entity);

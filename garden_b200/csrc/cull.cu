@@ -1602,6 +1602,11 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEve
 	GSP_FOR_VIEW_COUNT(P.viewCount, GSP_LAUNCH_CULL);
 	#undef GSP_LAUNCH_CULL
 	if (afterCull) cudaEventRecord(afterCull, c.stream);
+	if (c.arenaFreePending)
+	{
+		cudaStreamWaitEvent(c.stream, c.arenaFree, 0); // (exchange.cu: the last frame's runs have left the arenas)
+		c.arenaFreePending = false;
+	}
 	kScanChunks<<<P.viewCount, kScanThreads, 0, c.stream>>>(P, A);
 	{
 		// persistent grid: one wave of blocks, every warp strides over (chunk, view) units

@@ -26,6 +26,7 @@ struct MergeArgs
 	uint8_t* __restrict__ outRanks;
 	const uint32_t* __restrict__ outOffsets; // [lists]
 	uint32_t rankStride, ranks, lists, myRank;
+	uint32_t preSplit; // the runs were cut by common splitters before they travelled (all-to-all): every element is mine
 };
 
 // Warp-cooperative bound: all 32 lanes call it with the same arguments. Every round probes 32 evenly spaced positions of the
@@ -75,8 +76,12 @@ __global__ void __launch_bounds__(1024) kMergeBounds(const __grid_constant__ Mer
 		const uint32_t n = A.counts[run * A.lists + list];
 		const uint32_t* a = A.keys + (size_t)run * A.rankStride + A.offsets[run * A.lists + list];
 		// a key equal to a splitter belongs to the range that starts at the splitter
-		uint32_t lo = hasLo ? warpBound<false>(a, n, keyLo) : 0u;
-		uint32_t hi = hasHi ? warpBound<false>(a, n, keyHi) : n;
+		uint32_t lo = 0u, hi = n;
+		if (!A.preSplit)
+		{
+			lo = hasLo ? warpBound<false>(a, n, keyLo) : 0u;
+			hi = hasHi ? warpBound<false>(a, n, keyHi) : n;
+		}
 		if (hi < lo) hi = lo; // equal splitters
 		if (lane == 0)
 		{
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(1024) kMergeBounds(const __grid_constant__ Mer
 			start += A.bounds[(list * A.ranks + r) * 2 + 0];
 			length += A.bounds[(list * A.ranks + r) * 2 + 1] - A.bounds[(list * A.ranks + r) * 2 + 0];
 		}
-		A.sliceInfo[list * 2 + 0] = start;
+		A.sliceInfo[list * 2 + 0] = A.preSplit ? 0u : start; // (all-to-all: the global start comes from the length exchange)
 		A.sliceInfo[list * 2 + 1] = length;
 	}
 }
@@ -387,7 +392,7 @@ extern "C" int gsp_merge_gathered(void* cudaStream, uint32_t ranks, uint32_t myR
 	MergeArgs A;
 	A.keys = dKeys; A.payloads = dPayloads; A.offsets = dOffsets; A.counts = dCounts; A.bounds = dBounds;
 	A.sliceInfo = dSliceInfo; A.outKeys = dOutKeys; A.outPayloads = dOutPayloads; A.outRanks = dOutRanks;
-	A.outOffsets = dOutOffsets; A.rankStride = rankStride; A.ranks = ranks; A.lists = lists; A.myRank = myRank;
+	A.outOffsets = dOutOffsets; A.rankStride = rankStride; A.ranks = ranks; A.lists = lists; A.myRank = myRank; A.preSplit = 0;
 	launchMerge((cudaStream_t)cudaStream, A, maxRunLength);
 	return cudaGetLastError() == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
 }
@@ -402,6 +407,236 @@ extern "C" uint32_t gsp_merge_plan_words(uint32_t ranks, uint32_t lists)
 	return 2u * ranks * lists + lists + 2u * lists * ranks + 8u;
 }
 
+namespace gsp
+{
+// plan + bounds + merge of `ranks` packed blocks (block r at r * (kExHeaderWords + 2 * capacityElems) words)
+uint32_t launchMergePacked(cudaStream_t stream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
+	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPays, uint8_t* dOutRanks,
+	uint32_t outCapacity, bool preSplit)
+{
+	const uint32_t blockWords = kExHeaderWords + 2u * capacityElems;
+	kMergePlan<<<1, 32, 0, stream>>>(dGathered, blockWords, ranks, lists, outCapacity, dPlan);
+	MergeArgs A;
+	A.keys = dGathered + kExHeaderWords; A.payloads = dGathered + kExHeaderWords + capacityElems;
+	A.offsets = dPlan; A.counts = dPlan + ranks * lists;
+	A.outOffsets = dPlan + 2 * ranks * lists; A.bounds = dPlan + 2 * ranks * lists + lists;
+	A.sliceInfo = dSliceInfo; A.outKeys = dOutKeys; A.outPayloads = dOutPays; A.outRanks = dOutRanks;
+	A.rankStride = blockWords; A.ranks = ranks; A.lists = lists; A.myRank = myRank; A.preSplit = preSplit ? 1u : 0u;
+	// (pre-split runs are merged whole: size the grid for a full block per run)
+	return 1 + launchMerge(stream, A, preSplit ? (uint32_t)std::min<uint64_t>((uint64_t)capacityElems * ranks, 0xFFFFFFFFull) : capacityElems);
+}
+
+// ---- all-to-all protocol: common splitters from samples, one sub-block per destination --------------------------------------
+constexpr uint32_t kSamples = 64, kSampleWords = kSamples + 1; // (exchange.cu: kExSamples)
+
+// samples[list][k] = key at position (2k + 1) * count / (2 * kSamples) of my sorted run, samples[list][kSamples] = count
+__global__ void kSampleRuns(const SegmentDev* __restrict__ segments, const uint32_t* __restrict__ counters,
+	const uint32_t* __restrict__ keys, uint32_t lists, uint32_t* __restrict__ samples)
+{
+	const uint32_t l = blockIdx.x, k = threadIdx.x;
+	if (l >= lists || k > kSamples)
+		return;
+	const SegmentDev sg = segments[l];
+	const uint32_t c = sg.countIndex == kNone ? 0u : counters[sg.countIndex];
+	uint32_t v = c;
+	if (k < kSamples)
+		v = c ? keys[sg.offset + (uint32_t)(((uint64_t)(2 * k + 1) * c) / (2 * kSamples))] : 0xFFFFFFFFu;
+	samples[l * kSampleWords + k] = v;
+}
+
+// One block per list, one warp per splitter j = 1 .. ranks-1; lane r looks after rank r's samples.
+// Splitter j = the smallest key x whose weighted rank  W(x) = sum_r count_r * #(samples of r <= x)  reaches j/ranks of the
+// total weight (integer arithmetic, identical on every rank). Then the position of the splitter in MY run: bounds[list][j].
+struct SplitArgs
+{
+	const SegmentDev* __restrict__ segments;
+	const uint32_t* __restrict__ counters;
+	const uint32_t* __restrict__ keys;
+	const uint32_t* __restrict__ gathered; // [ranks][lists][kSampleWords]
+	const uint32_t* __restrict__ mine;     // [lists][kSampleWords]: my own samples (their last word = my run length)
+	uint32_t* __restrict__ splitters;      // [lists][ranks - 1], then bounds [lists][ranks + 1]
+	uint32_t lists, ranks;
+};
+__global__ void __launch_bounds__(1024) kSplitRuns(const __grid_constant__ SplitArgs A)
+{
+	const uint32_t l = blockIdx.x, j = (threadIdx.x >> 5) + 1, lane = threadIdx.x & 31;
+	uint32_t* bounds = A.splitters + A.lists * (A.ranks - 1) + l * (A.ranks + 1);
+	const SegmentDev sg = A.segments[l];
+	// (the frame counters may already belong to the NEXT frame when this runs on the exchange stream: the length travels
+	// with the samples)
+	const uint32_t myCount = A.mine[l * kSampleWords + kSamples];
+	if (threadIdx.x == 0)
+	{
+		bounds[0] = 0; bounds[A.ranks] = myCount;
+	}
+	if (j >= A.ranks)
+		return; // (whole warps)
+	const uint32_t* mine = lane < A.ranks ? A.gathered + ((size_t)lane * A.lists + l) * kSampleWords : nullptr;
+	const unsigned long long weight = mine ? mine[kSamples] : 0ull;
+	unsigned long long totalWeight = 0;
+	{
+		// exact 64-bit sum over the lanes
+		unsigned long long w = weight;
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			w += __shfl_xor_sync(0xffffffffu, w, o);
+		totalWeight = w * kSamples;
+	}
+	const unsigned long long target = (totalWeight * j + A.ranks - 1) / A.ranks;
+	// binary search on the key value: smallest x with W(x) >= target  (W is monotone in x, W(0xFFFFFFFF) = totalWeight)
+	uint32_t lo = 0, hi = 0xFFFFFFFFu;
+	while (lo < hi)
+	{
+		const uint32_t mid = lo + ((hi - lo) >> 1);
+		uint32_t cnt = 0;
+		if (mine && weight)
+		{
+			uint32_t a = 0, b = kSamples; // #samples <= mid
+			while (a < b)
+			{
+				const uint32_t m = (a + b) >> 1;
+				if (mine[m] <= mid) a = m + 1; else b = m;
+			}
+			cnt = a;
+		}
+		unsigned long long w = weight * cnt;
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			w += __shfl_xor_sync(0xffffffffu, w, o);
+		if (w >= target) hi = mid; else lo = mid + 1;
+	}
+	const uint32_t splitter = totalWeight ? lo : 0xFFFFFFFFu;
+	const uint32_t pos = warpBound<false>(A.keys + sg.offset, myCount, splitter); // keys equal to a splitter start the next range
+	if (lane == 0)
+	{
+		A.splitters[l * (A.ranks - 1) + (j - 1)] = splitter;
+		bounds[j] = pos;
+	}
+}
+
+// Packs my runs into `ranks` sub-blocks (block d = what rank d merges), each laid out like kExportPacked's block.
+struct PackArgs
+{
+	const SegmentDev* __restrict__ segments;
+	const uint32_t* __restrict__ keys;
+	const uint32_t* __restrict__ payloads;
+	const uint32_t* __restrict__ bounds; // [lists][ranks + 1]
+	uint32_t* __restrict__ blocks;       // [ranks][kExHeaderWords + 2 * capacity]
+	uint32_t lists, ranks, capacity;
+};
+constexpr uint32_t kPackMaxRanks = 32;
+__global__ void __launch_bounds__(256) kPackByDestination(const __grid_constant__ PackArgs A)
+{
+	__shared__ uint32_t sBound[kPackMaxRanks + 1];
+	__shared__ uint32_t sTotal[kPackMaxRanks], sBefore[kPackMaxRanks]; // per destination: all lists / the lists before this one
+	const size_t blockWords = kExHeaderWords + 2ull * A.capacity;
+	if (threadIdx.x < A.ranks)
+	{
+		uint32_t total = 0;
+		for (uint32_t l = 0; l < A.lists; l++)
+			total += A.bounds[l * (A.ranks + 1) + threadIdx.x + 1] - A.bounds[l * (A.ranks + 1) + threadIdx.x];
+		sTotal[threadIdx.x] = total;
+	}
+	__syncthreads();
+	if (blockIdx.x == 0)
+	{
+		// headers: { magic, lists, total, capacity, overflow, 0, 0, 0, count[lists] }
+		for (uint32_t d = 0; d < A.ranks; d++)
+		{
+			const bool overflow = sTotal[d] > A.capacity;
+			uint32_t* h = A.blocks + d * blockWords;
+			for (uint32_t i = threadIdx.x; i < kExHeaderWords; i += blockDim.x)
+			{
+				uint32_t w = 0;
+				if (i == 0) w = kExMagic;
+				else if (i == 1) w = A.lists;
+				else if (i == 2) w = sTotal[d];
+				else if (i == 3) w = A.capacity;
+				else if (i == 4) w = overflow ? 1u : 0u;
+				else if (i >= kExHeaderFixed && i < kExHeaderFixed + A.lists && !overflow)
+					w = A.bounds[(i - kExHeaderFixed) * (A.ranks + 1) + d + 1] - A.bounds[(i - kExHeaderFixed) * (A.ranks + 1) + d];
+				h[i] = w;
+			}
+		}
+	}
+	if (threadIdx.x < A.ranks)
+		sBefore[threadIdx.x] = 0;
+	for (uint32_t l = 0; l < A.lists; l++)
+	{
+		__syncthreads();
+		if (threadIdx.x <= A.ranks)
+			sBound[threadIdx.x] = A.bounds[l * (A.ranks + 1) + threadIdx.x];
+		__syncthreads();
+		const uint32_t n = sBound[A.ranks], from = A.segments[l].offset;
+		const uint32_t stride = gridDim.x * blockDim.x;
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		{
+			uint32_t d = 0;
+			while (d + 1 < A.ranks && i >= sBound[d + 1]) d++;
+			if (sTotal[d] > A.capacity)
+				continue; // that block overflowed: it carries no elements
+			uint32_t* dk = A.blocks + d * blockWords + kExHeaderWords;
+			const uint32_t at = sBefore[d] + (i - sBound[d]);
+			dk[at] = A.keys[from + i];
+			dk[A.capacity + at] = A.payloads[from + i];
+		}
+		__syncthreads();
+		if (threadIdx.x < A.ranks)
+			sBefore[threadIdx.x] += sBound[threadIdx.x + 1] - sBound[threadIdx.x];
+	}
+}
+
+__global__ void kSliceLengths(uint32_t lists, const uint32_t* __restrict__ sliceInfo, uint32_t* __restrict__ lengths)
+{
+	const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+	if (l < lists)
+		lengths[l] = sliceInfo[l * 2 + 1];
+}
+__global__ void kSliceStarts(uint32_t ranks, uint32_t myRank, uint32_t lists, const uint32_t* __restrict__ gathered,
+	uint32_t* __restrict__ sliceInfo)
+{
+	const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+	if (l >= lists)
+		return;
+	uint32_t start = 0;
+	for (uint32_t r = 0; r < myRank; r++)
+		start += gathered[r * lists + l];
+	sliceInfo[l * 2 + 0] = start;
+}
+
+uint32_t launchSampleRuns(Context& c, uint32_t* dSamples)
+{
+	const uint32_t lists = (uint32_t)c.segments.size();
+	kSampleRuns<<<lists, 96, 0, c.stream>>>(c.dSegments, c.dCounters, c.keys[0], lists, dSamples);
+	return 1;
+}
+uint32_t launchSplitAndPack(Context& c, cudaStream_t stream, uint32_t ranks, const uint32_t* dMySamples, const uint32_t* dGatheredSamples,
+	uint32_t* dSplitters, uint32_t* dSendBlocks, uint32_t capacityPerDest)
+{
+	const uint32_t lists = (uint32_t)c.segments.size();
+	SplitArgs S;
+	S.segments = c.dSegments; S.counters = c.dCounters; S.keys = c.keys[0]; S.gathered = dGatheredSamples; S.mine = dMySamples; S.splitters = dSplitters;
+	S.lists = lists; S.ranks = ranks;
+	kSplitRuns<<<lists, 32 * std::max(1u, ranks - 1), 0, stream>>>(S);
+	PackArgs P;
+	P.segments = c.dSegments; P.keys = c.keys[0]; P.payloads = c.payloads[0];
+	P.bounds = dSplitters + lists * (ranks - 1); P.blocks = dSendBlocks; P.lists = lists; P.ranks = ranks; P.capacity = capacityPerDest;
+	kPackByDestination<<<c.smCount * 4, 256, 0, stream>>>(P);
+	return 2;
+}
+uint32_t launchSliceLengths(cudaStream_t stream, uint32_t lists, const uint32_t* dSliceInfo, uint32_t* dLengths)
+{
+	kSliceLengths<<<(lists + 127) / 128, 128, 0, stream>>>(lists, dSliceInfo, dLengths);
+	return 1;
+}
+uint32_t launchSliceStarts(cudaStream_t stream, uint32_t ranks, uint32_t myRank, uint32_t lists, const uint32_t* dGatheredLengths,
+	uint32_t* dSliceInfo)
+{
+	kSliceStarts<<<(lists + 127) / 128, 128, 0, stream>>>(ranks, myRank, lists, dGatheredLengths, dSliceInfo);
+	return 1;
+}
+} // namespace gsp
+
 extern "C" int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
 	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
 	uint8_t* dOutRanks, uint32_t outCapacity)
@@ -409,15 +644,7 @@ extern "C" int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint3
 	if (ranks == 0 || ranks > 32 || myRank >= ranks || lists == 0 || lists > kExMaxLists || !dGathered || !dPlan || !dSliceInfo ||
 		!dOutKeys || !dOutPayloads || !dOutRanks)
 		return GSP_ERR_INVALID;
-	cudaStream_t stream = (cudaStream_t)cudaStream;
-	const uint32_t blockWords = kExHeaderWords + 2u * capacityElems;
-	kMergePlan<<<1, 32, 0, stream>>>(dGathered, blockWords, ranks, lists, outCapacity, dPlan);
-	MergeArgs A;
-	A.keys = dGathered + kExHeaderWords; A.payloads = dGathered + kExHeaderWords + capacityElems;
-	A.offsets = dPlan; A.counts = dPlan + ranks * lists;
-	A.outOffsets = dPlan + 2 * ranks * lists; A.bounds = dPlan + 2 * ranks * lists + lists;
-	A.sliceInfo = dSliceInfo; A.outKeys = dOutKeys; A.outPayloads = dOutPayloads; A.outRanks = dOutRanks;
-	A.rankStride = blockWords; A.ranks = ranks; A.lists = lists; A.myRank = myRank;
-	launchMerge(stream, A, capacityElems);
+	gsp::launchMergePacked((cudaStream_t)cudaStream, ranks, myRank, lists, capacityElems, dGathered, dPlan, dSliceInfo, dOutKeys,
+		dOutPayloads, dOutRanks, outCapacity, false);
 	return cudaGetLastError() == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
 }

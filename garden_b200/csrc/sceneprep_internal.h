@@ -149,9 +149,15 @@ struct SegmentDev // device-visible part
 	uint32_t descending, key2D, pad0, pad1;
 };
 
+struct Exchange; // multi-GPU exchange state (exchange.cu)
+
 struct Context
 {
 	int device = 0;
+	Exchange* exchange = nullptr;
+	// all-to-all exchange: the previous frame's runs are still being packed out of the key / payload arenas on the exchange
+	// stream; the next frame's first kScatter waits for this event (its prepass and kCull run meanwhile)
+	cudaEvent_t arenaFree = nullptr; bool arenaFreePending = false;
 	uint32_t smCount = 148; // cudaDevAttrMultiProcessorCount of `device` (grid sizes of the persistent kernels)
 	cudaStream_t ownStream = nullptr, stream = nullptr;
 	cudaStream_t copyStream = nullptr; cudaEvent_t copyEvent = nullptr; // list downloads overlap the caller / the write-back
@@ -251,7 +257,13 @@ uint32_t launchEmit(Context& c);
 uint32_t launchInstances(Context& c, int seg, const float* viewProj, void* dDst, uint32_t stride, uint32_t offset, uint32_t capacity);
 uint32_t launchSetActive(Context& c, const uint32_t* dIds, uint32_t count, int active);
 uint32_t launchExportPacked(Context& c, uint32_t* dBlock, uint32_t capacity);
+void destroyExchange(Context& c);
 uint32_t launchPackVisible(Context& c, uint32_t pool, uint32_t* dBits);
 uint32_t launchVisibleDelta(Context& c, uint32_t pool, uint32_t* list, uint32_t* dCount, uint32_t* hCountMapped);
 
 } // namespace gsp
+
+struct gsp_context
+{
+	gsp::Context c;
+};

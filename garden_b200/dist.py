@@ -188,166 +188,121 @@ class RunMerger:
 
 
 class PipelinedRunMerger:
-    """Gather + merge without any host synchronisation in the steady state, overlapped with the next frame.
+    """The exchange of libgarden_sceneprep.so (csrc/exchange.cu: NCCL inside the library, no Python in the data path), driven
+    one rank per process. This class only (a) carries the NCCL unique id from rank 0 to the others over torch.distributed
+    and (b) forwards to gsp_exchange_*:
 
-    Per frame, on the compute stream (the ScenePrep's stream, which must be torch's current stream):
-        gsp_run_async -> gsp_export_runs_packed (lengths read on the device) -> event
-    and on a second (exchange) stream:
-        wait(event) -> ONE NCCL all-gather of the fixed-capacity blocks -> gsp_merge_gathered_packed -> flags to pinned memory
-    so frame k's exchange runs while frame k+1 is being culled and sorted. Blocks, gathered buffers and merged slices are
-    double-buffered; a buffer set is reused only after the exchange that read it has finished (event wait, device side).
+        frame()   gsp_run_async + gsp_exchange_async   — no host synchronisation; frame k's exchange (the library's exchange
+                  stream) overlaps frame k+1's culling; buffer sets are double-buffered inside the library
+        poll()    gsp_exchange_poll: flags of finished frames; a frame whose runs overflowed the fixed-capacity blocks was
+                  not merged: grow() and repeat it
+        finish()  gsp_exchange_finish: the compute stream waits for the exchanges, the host for their flags
 
-    The block capacity is speculative (sized from a measured frame, with head room). The merge reports overflow through
-    the plan flags; `poll()` looks at the flags of finished frames and returns the frames that must be repeated after
-    `grow()` — a draw list is only valid once its frame's flags have been seen clean (`finish()` checks all of them)."""
+    Protocol: GSP_EXCHANGE=alltoall (default: sample-based common splitters, every rank receives only its key range) or
+    allgather (every rank receives every run)."""
 
     HEAD_ROOM = 1.25
-    launches_per_frame = 4  # kExportPacked + kMergePlan + kMergeBounds + kMergeSlice
 
     def __init__(self, sp, capacity: int | None = None, overlap: bool = True):
+        import ctypes as C
         import torch
         import torch.distributed as dist
-        self.torch, self.dist, self.sp = torch, dist, sp
+        self.torch, self.dist, self.sp, self.C = torch, dist, sp, C
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.compute = torch.cuda.current_stream()
-        self.exchange = torch.cuda.Stream() if overlap else self.compute
-        self.lists = sp.list_count()
-        self.capacity = 0
-        self.sets = []
-        self.frame_index = 0
-        self.pending = []  # (frame index, buffer set) whose flags have not been inspected yet
-        self.flags_seen = {}
-        self.timing = None  # set to a list to collect per-frame events (export | all-gather | merge)
+        self.overlap = overlap
+        lib = sp.lib
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            if lib.gsp_comm_unique_id(buf) != 0:
+                raise RuntimeError("gsp_comm_unique_id failed (is libnccl.so.2 loadable?)")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        backend = dist.get_backend()
+        if backend == "nccl":
+            ident = ident.cuda()
+        dist.broadcast(ident, src=0)
+        raw = bytes(ident.cpu().tolist())
+        sp._check(lib.gsp_comm_init(sp.h, raw, self.world, self.rank))
         if capacity is None:
-            capacity = self.measure_capacity()
-        self._allocate(int(capacity))
-
-    def measure_capacity(self) -> int:
-        """One synchronous frame: the largest per-rank total over all ranks, with head room (every rank gets the same value)."""
-        torch, dist = self.torch, self.dist
-        self.sp.run()
-        self.lists = self.sp.list_count()
-        mine = torch.tensor([int(self.sp.list_counts().astype(np.int64).sum())], dtype=torch.int64, device=self.dev)
-        dist.all_reduce(mine, op=dist.ReduceOp.MAX)
-        return int(int(mine.item()) * self.HEAD_ROOM) + 4096
-
-    def _allocate(self, capacity: int):
-        torch, lib = self.torch, self.sp.lib
-        self.capacity = capacity
-        words = lib.gsp_exchange_block_words(capacity)
-        plan_words = lib.gsp_merge_plan_words(self.world, max(self.lists, 1))
-        out_cap = capacity * self.world  # every rank's slice fits even if one rank's key range swallowed everything
-        self.sets = []
-        for _ in range(2):
-            self.sets.append({
-                "send": torch.empty(words, dtype=torch.int32, device=self.dev),
-                "gathered": torch.empty(words * self.world, dtype=torch.int32, device=self.dev),
-                "plan": torch.zeros(plan_words, dtype=torch.int32, device=self.dev),
-                "slice_info": torch.zeros(max(self.lists, 1) * 2, dtype=torch.int32, device=self.dev),
-                "out_keys": torch.empty(out_cap, dtype=torch.int32, device=self.dev),
-                "out_pays": torch.empty(out_cap, dtype=torch.int32, device=self.dev),
-                "out_ranks": torch.empty(out_cap, dtype=torch.uint8, device=self.dev),
-                "flags": torch.zeros(8, dtype=torch.int32).pin_memory(),
-                "exported": torch.cuda.Event(), "done": torch.cuda.Event(), "used": False, "out_cap": out_cap,
-            })
+            cap = C.c_uint32()
+            sp._check(lib.gsp_exchange_autosize(sp.h, C.byref(cap)))
+            self.capacity = cap.value
+        else:
+            sp.run()
+            sp._check(lib.gsp_exchange_configure(sp.h, int(capacity)))
+            self.capacity = int(capacity)
+        self.lists = sp.list_count()
+        info = [C.c_uint32() for _ in range(4)]
+        sp._check(lib.gsp_comm_info(sp.h, *[C.byref(i) for i in info]))
+        self.all_to_all = bool(info[3].value)
+        # kernels per frame on top of the single-GPU frame
+        self.launches_per_frame = 8 if self.all_to_all else 4
+        self.timing = None
+        self.frame_index = 0
 
     def grow(self, needed: int):
-        """Re-sizes the blocks for `needed` elements per rank (collective: every rank must call it with the same value)."""
+        """Re-sizes the blocks for `needed` elements (collective: every rank must call it with the same value)."""
         self.finish(check=False)
-        self._allocate(int(needed * self.HEAD_ROOM) + 4096)
+        self.capacity = int(needed * self.HEAD_ROOM) + 4096
+        self.sp._check(self.sp.lib.gsp_exchange_configure(self.sp.h, self.capacity))
 
     def frame(self):
-        """Enqueues one frame: scene preparation, export, all-gather, merge. Returns the buffer set that will hold the result."""
-        torch, dist, sp = self.torch, self.dist, self.sp
-        s = self.sets[self.frame_index & 1]
-        if s["used"]:
-            self.compute.wait_event(s["done"])  # the exchange that last read this set's block has finished
-        timing = self.timing
+        sp = self.sp
         sp.run_async()
-        if timing is not None:
-            t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            t[0].record(self.compute)
-        sp.export_runs_packed(s["send"].data_ptr(), self.capacity)
-        s["exported"].record(self.compute)
-        with torch.cuda.stream(self.exchange):
-            self.exchange.wait_event(s["exported"])
-            if timing is not None:
-                t[1].record(self.exchange)
-            dist.all_gather_into_tensor(s["gathered"], s["send"])
-            if timing is not None:
-                t[2].record(self.exchange)
-            rc = sp.lib.gsp_merge_gathered_packed(self.exchange.cuda_stream, self.world, self.rank, self.lists, self.capacity,
-                                                  s["gathered"].data_ptr(), s["plan"].data_ptr(), s["slice_info"].data_ptr(),
-                                                  s["out_keys"].data_ptr(), s["out_pays"].data_ptr(),
-                                                  s["out_ranks"].data_ptr(), s["out_cap"])
-            if rc != 0:
-                raise RuntimeError(f"gsp_merge_gathered_packed failed with {rc}")
-            if timing is not None:
-                t[3].record(self.exchange)
-                timing.append(t)
-            s["flags"].copy_(s["plan"][-8:], non_blocking=True)
-            s["done"].record(self.exchange)
-        s["used"] = True
-        s["frame"] = self.frame_index
-        self.pending.append((self.frame_index, s))
+        if self.timing is not None:
+            sp.lib.gsp_exchange_set_timing(sp.h, 1)
+        sp._check(sp.lib.gsp_exchange_async(sp.h))
+        if self.timing is not None:
+            ms = (self.C.c_float * 3)()
+            sp._check(sp.lib.gsp_exchange_times(sp.h, ms))  # (synchronises: only used by the serialised latency loop)
+            self.timing.append(tuple(ms))
         self.frame_index += 1
-        return s
+        if not self.overlap:
+            self.finish()
+
+    def _flags(self, wait: bool, finish: bool):
+        C, sp = self.C, self.sp
+        bits, needed = C.c_uint32(), C.c_uint32()
+        if finish:
+            sp._check(sp.lib.gsp_exchange_finish(sp.h, C.byref(bits), C.byref(needed)))
+        else:
+            sp._check(sp.lib.gsp_exchange_poll(sp.h, 1 if wait else 0, C.byref(bits), C.byref(needed)))
+        return [(self.frame_index - 1, bits.value, needed.value)] if bits.value else []
 
     def poll(self, wait: bool = False):
-        """Inspects the flags of frames whose exchange has finished. Returns [(frame, error bits, needed capacity)] of the
-        frames that failed (empty when everything seen so far is clean)."""
-        failed, still = [], []
-        for idx, s in self.pending:
-            if s.get("frame") != idx:  # its buffers were reused: the flags were already overwritten by a later frame
-                continue
-            if wait:
-                s["done"].synchronize()
-            if not s["done"].query():
-                still.append((idx, s))
-                continue
-            f = s["flags"].numpy().astype(np.int64) & 0xFFFFFFFF
-            self.flags_seen[idx] = f.copy()
-            if f[0]:
-                failed.append((idx, int(f[0]), int(f[2])))
-        self.pending = still
-        return failed
-
-    def timing_summary(self):
-        """Mean milliseconds of the export, all-gather and merge steps over the frames collected in `self.timing`."""
-        if not self.timing:
-            return None
-        self.torch.cuda.synchronize()
-        n = len(self.timing)
-        return {"export_ms": sum(t[0].elapsed_time(t[1]) for t in self.timing) / n,
-                "allgather_ms": sum(t[1].elapsed_time(t[2]) for t in self.timing) / n,
-                "merge_ms": sum(t[2].elapsed_time(t[3]) for t in self.timing) / n, "frames": n}
+        """[(frame, error bits, needed capacity)] of the finished frames that failed (empty: everything seen so far is clean)."""
+        return self._flags(wait, False)
 
     def finish(self, check: bool = True):
-        """Waits for every enqueued exchange (device side for the compute stream, host side for the flags)."""
-        for s in self.sets:
-            if s["used"]:
-                self.compute.wait_event(s["done"])
-        failed = self.poll(wait=True)
+        failed = self._flags(True, True)
         if check and failed:
             raise RuntimeError(f"exchange overflow in frames {failed}: call grow() and repeat them")
         return failed
 
+    def timing_summary(self):
+        if not self.timing:
+            return None
+        n = len(self.timing)
+        return {"export_or_sampling_ms": sum(t[0] for t in self.timing) / n, "collectives_ms": sum(t[1] for t in self.timing) / n,
+                "merge_ms": sum(t[2] for t in self.timing) / n, "frames": n,
+                "protocol": "alltoall" if self.all_to_all else "allgather"}
+
+    def bytes_received(self) -> int:
+        return int(self.sp.lib.gsp_exchange_bytes_received(self.sp.h))
+
     def last_result(self):
-        """Buffer set of the most recent frame plus its host-side description (for tests): synchronises."""
-        s = self.sets[(self.frame_index - 1) & 1]
-        s["done"].synchronize()
-        lists, world = self.lists, self.world
-        plan = s["plan"].cpu().numpy().view(np.uint32)
-        n_rl = world * lists
-        counts = plan[n_rl:2 * n_rl].reshape(world, lists).astype(np.int64)
-        out_offsets = plan[2 * n_rl:2 * n_rl + lists].astype(np.int64)
-        info = s["slice_info"].cpu().numpy().view(np.uint32).reshape(-1, 2)
+        """This rank's merged slices of the most recent frame on the host (for tests): synchronises."""
+        C, sp = self.C, self.sp
         slices = []
-        for l in range(lists):
-            o, start, length = int(out_offsets[l]), int(info[l, 0]), int(info[l, 1])
-            sl = slice(o, o + length)
-            slices.append((start, s["out_keys"][sl].cpu().numpy().view(np.uint32),
-                           s["out_pays"][sl].cpu().numpy().view(np.uint32), s["out_ranks"][sl].cpu().numpy()))
-        return {"counts": counts, "out_offsets": out_offsets, "flags": plan[-8:].copy(), "slices": slices,
-                "bytes_gathered": int(s["gathered"].numel() * 4)}
+        for l in range(self.lists):
+            k, p, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            start, count = C.c_uint32(), C.c_uint32()
+            sp._check(sp.lib.gsp_get_merged_device(sp.h, l, C.byref(k), C.byref(p), C.byref(r), C.byref(start), C.byref(count)))
+            n = count.value
+            keys, pays, ranks = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+            if n:
+                sp._check(sp.lib.gsp_copy_to_host(sp.h, k, keys.ctypes.data, n * 4))
+                sp._check(sp.lib.gsp_copy_to_host(sp.h, p, pays.ctypes.data, n * 4))
+                sp._check(sp.lib.gsp_copy_to_host(sp.h, r, ranks.ctypes.data, n))
+            slices.append((start.value, keys, pays, ranks))
+        return {"slices": slices, "bytes_received": self.bytes_received()}

@@ -184,6 +184,42 @@ int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint32_t myRank,
 	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
 	uint8_t* dOutRanks, uint32_t outCapacity);
 
+/* ---- the same exchange with NCCL inside the library: one context per GPU, any host language ------------------------------------
+ * ("one context may drive 1-8 GPUs" — here: n contexts, one per device, joined by one communicator.)
+ * Process-per-GPU: rank 0 calls gsp_comm_unique_id, the id travels out of band (MPI, a socket, torch.distributed), every rank
+ * calls gsp_comm_init. Single process: gsp_comm_init_all over its contexts; then drive every context from its own thread (NCCL's
+ * rule for several devices per process). libnccl.so.2 is loaded at run time on the first call; single-GPU users never need it.
+ * Per frame:  gsp_run_async(ctx); gsp_exchange_async(ctx);  — no host synchronisation, frame k's exchange (exchange stream)
+ * overlaps frame k+1. The blocks have a fixed capacity (gsp_exchange_autosize measures one frame; collective): a frame whose
+ * runs do not fit is flagged, nothing of it is merged, gsp_exchange_poll / _finish report it with the capacity that would
+ * have sufficed; the caller then calls gsp_exchange_configure (same value on every rank) and repeats the frame.
+ * GSP_EXCHANGE=allgather|alltoall selects the protocol (default alltoall: runs are cut by common, sample-based splitters
+ * before they travel, every rank receives only the key range it merges). */
+#define GSP_COMM_ID_BYTES 128
+int gsp_comm_unique_id(uint8_t id[GSP_COMM_ID_BYTES]);
+int gsp_comm_init(gsp_context* ctx, const uint8_t id[GSP_COMM_ID_BYTES], uint32_t ranks, uint32_t rank);
+int gsp_comm_init_all(gsp_context** contexts, uint32_t count);
+int gsp_comm_destroy(gsp_context* ctx);
+int gsp_comm_info(const gsp_context* ctx, uint32_t* ranks, uint32_t* rank, uint32_t* capacity, uint32_t* allToAll);
+int gsp_exchange_configure(gsp_context* ctx, uint32_t capacityElems);
+int gsp_exchange_autosize(gsp_context* ctx, uint32_t* capacityOut);
+int gsp_exchange_async(gsp_context* ctx);
+/* errorBits: 1 a block overflowed, 2 bad header, 4 merged lists exceed the output capacity. wait != 0: blocks until every
+ * enqueued exchange has finished. gsp_exchange_finish additionally makes the context's stream wait for them. */
+int gsp_exchange_poll(gsp_context* ctx, int wait, uint32_t* errorBits, uint32_t* neededCapacity);
+int gsp_exchange_finish(gsp_context* ctx, uint32_t* errorBits, uint32_t* neededCapacity);
+/* This rank's key-range slice of merged list `list` (gsp_list_count order) of the most recent exchange: device pointers,
+ * valid until two more exchanges have been enqueued. start = position of the slice in the merged list; ranks[i] = the GPU
+ * element i came from; payload = pool << 28 | slot ON THAT GPU. Ties resolve to (rank, payload) order. */
+int gsp_get_merged_device(gsp_context* ctx, uint32_t list, const uint32_t** keys, const uint32_t** payloads, const uint8_t** ranks,
+	uint32_t* start, uint32_t* count);
+int gsp_exchange_set_timing(gsp_context* ctx, int enabled);
+/* ms = { export / sampling, collective(s), merge } of the most recent exchange (needs gsp_exchange_set_timing) */
+int gsp_exchange_times(gsp_context* ctx, float ms[3]);
+uint64_t gsp_exchange_bytes_received(const gsp_context* ctx);
+/* Device -> host copy of memory this library handed out as a device pointer (merged slices, device-resident lists). */
+int gsp_copy_to_host(gsp_context* ctx, const void* devicePtr, void* host, size_t bytes);
+
 /* ---- the callers either side of the path ----------------------------------------------------------------- */
 /* Instance data of one draw list, in draw order: for record i, mvp = (float4x4)(viewProj * f32x4x4(bakedModel, (0,0,0,1)))
  * stored at instances + i * stride + mvpOffset (64 bytes, column-major) — what renderUnsorted / renderSorted pass to

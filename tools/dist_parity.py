@@ -87,29 +87,54 @@ def main():
         assert (start, gk.size) == (estart, ek.size), f"rank {rank} list {l}: slice bounds {start},{gk.size} vs {estart},{ek.size}"
         assert np.array_equal(gk, ek) and np.array_equal(gp, ep) and np.array_equal(gr, er), f"rank {rank} list {l}: content"
         checked += int(gk.size)
-    # ---- the pipelined, host-synchronisation-free exchange: same slices, three frames in flight, then the overflow path ----
+    # ---- the exchange INSIDE the library (csrc/exchange.cu: NCCL behind the C ABI, no host synchronisation, protocol chosen by
+    # GSP_EXCHANGE): three frames in flight, every slice against the numpy merge of ALL ranks' runs, then the overflow path ----
     from garden_b200.dist import PipelinedRunMerger
+    full = []
+    for l in range(lists):
+        runs_k = [everyone[r][1][offsets[r, l]: offsets[r, l] + all_counts[r, l]] for r in range(world)]
+        runs_p = [everyone[r][2][offsets[r, l]: offsets[r, l] + all_counts[r, l]] for r in range(world)]
+        full.append(merge_reference(runs_k, runs_p))
+
+    def check_slices(result, what):
+        for l in range(lists):
+            start, gk, gp, gr = result["slices"][l]
+            fk, fp, fr = full[l]
+            sl = slice(start, start + gk.size)
+            assert start + gk.size <= fk.size, f"rank {rank} list {l} ({what}): slice [{start}, {start + gk.size}) outside the list"
+            assert np.array_equal(gk, fk[sl]) and np.array_equal(gp, fp[sl]) and np.array_equal(gr, fr[sl]), \
+                f"rank {rank} list {l} ({what}): merged slice differs from the merge of all runs"
+        spans = [None] * world
+        dist.all_gather_object(spans, [(s[0], int(s[1].size)) for s in result["slices"]])
+        for l in range(lists):
+            pos = 0
+            for r in range(world):
+                assert spans[r][l][0] == pos, f"list {l} ({what}): rank {r} slice starts at {spans[r][l][0]}, expected {pos}"
+                pos += spans[r][l][1]
+            assert pos == int(totals[l]), f"list {l} ({what}): slices cover {pos} of {int(totals[l])}"
+        return spans
+
     pm = PipelinedRunMerger(sp)
     for _ in range(3):
         pm.frame()
         assert pm.poll() == []
     pm.finish()
-    res2 = pm.last_result()
-    assert np.array_equal(res2["counts"], all_counts) and int(res2["flags"][0]) == 0
-    for l in range(lists):
-        a0, b0 = slices[l], res2["slices"][l]
-        assert a0[0] == b0[0] and np.array_equal(a0[1], b0[1]) and np.array_equal(a0[2], b0[2]) and np.array_equal(a0[3], b0[3]), \
-            f"rank {rank} list {l}: pipelined exchange differs from the synchronous one"
-    tiny = PipelinedRunMerger(sp, capacity=max(int(all_counts.sum(axis=1).max()) // 3, 1))
-    tiny.frame()
-    failed = tiny.finish(check=False)
-    assert failed and failed[0][1] & 1 and failed[0][2] == int(all_counts.sum(axis=1).max()), failed
-    tiny.grow(failed[0][2])
-    tiny.frame()
-    assert tiny.finish(check=False) == []
-    res3 = tiny.last_result()
-    for l in range(lists):
-        assert np.array_equal(slices[l][1], res3["slices"][l][1]) and np.array_equal(slices[l][2], res3["slices"][l][2])
+    spans_lib = check_slices(pm.last_result(), "in-library exchange")
+    protocol = "alltoall" if pm.all_to_all else "allgather"
+    small = max(int(all_counts.sum(axis=1).max()) // (3 * (world if pm.all_to_all else 1)), 1)
+    pm.finish()
+    sp.run()
+    sp._check(sp.lib.gsp_exchange_configure(sp.h, small))
+    pm.capacity = small
+    pm.frame()
+    failed = pm.finish(check=False)
+    assert failed and failed[0][1] & 1 and failed[0][2] > small, failed
+    need = torch.tensor([failed[0][2]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(need, op=dist.ReduceOp.MAX)
+    pm.grow(int(need.item()))
+    pm.frame()
+    assert pm.finish(check=False) == []
+    check_slices(pm.last_result(), "after overflow -> grow -> repeat")
     spans = [None] * world
     dist.all_gather_object(spans, [(s[0], int(s[1].size)) for s in slices])
     if rank == 0:
@@ -122,7 +147,9 @@ def main():
         print(json.dumps({"dist_parity": "ok", "world": world, "entities": n, "lists": int(lists),
                           "merged_total": int(totals.sum()), "rank0_checked": checked,
                           "bytes_gathered": res["bytes_gathered"],
-                          "pipelined": "ok (3 frames in flight, overflow -> grow -> repeat)"}), flush=True)
+                          "in_library_exchange": f"ok ({protocol}; 3 frames in flight, overflow -> grow -> repeat)",
+                          "bytes_received_per_rank": pm.bytes_received(),
+                          "slice_lengths_list0": [s[0][1] for s in spans_lib]}), flush=True)
     sp.close()
     dist.barrier()
     dist.destroy_process_group()
