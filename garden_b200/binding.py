@@ -74,6 +74,8 @@ SYMBOLS = {
     "gsp_view_from_viewproj": (_i32, [_vp, _vp, _i32, _vp]),
     "gsp_set_active": (_i32, [_vp, _vp, _u32, _i32]),
     "gsp_writeback_active": (_i32, [_vp, _vp, _u32]),
+    "gsp_animate": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "gsp_writeback_trs": (_i32, [_vp, _vp, _u32]),
     "gsp_writeback_visible": (_i32, [_vp, _u32, _vp, _u32]),
     "gsp_writeback_visible_delta": (_i32, [_vp, _u32, _vp, _u32, _pu32]),
     "gsp_fetch_all": (_i32, [_vp]),
@@ -281,6 +283,18 @@ class ScenePrep:
     def set_active(self, entity_ids, active: bool):
         ids = np.ascontiguousarray(entity_ids, dtype=np.uint32)
         self._check(self.lib.gsp_set_active(self.h, ids.ctypes.data, ids.size, 1 if active else 0))
+
+    def animate(self, entity_ids, flags, frame_a, frame_b, t):
+        """TransformSystem::animateAsync on the device; frames are [n, 10] = position, scale, rotation."""
+        ids = np.ascontiguousarray(entity_ids, dtype=np.uint32)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8)
+        fa = np.ascontiguousarray(frame_a, dtype=np.float32); fb = np.ascontiguousarray(frame_b, dtype=np.float32)
+        tt = np.ascontiguousarray(t, dtype=np.float32)
+        assert fa.shape == (ids.size, 10) and fb.shape == (ids.size, 10) and fl.size == ids.size and tt.size == ids.size
+        self._check(self.lib.gsp_animate(self.h, ids.ctypes.data, fl.ctypes.data, fa.ctypes.data, fb.ctypes.data, tt.ctypes.data, ids.size))
+
+    def writeback_trs(self, aos, stride: int):
+        self._check(self.lib.gsp_writeback_trs(self.h, _ptr(aos), stride))
 
     def writeback_active(self, aos, stride: int):
         self._check(self.lib.gsp_writeback_active(self.h, _ptr(aos), stride))

@@ -1182,6 +1182,89 @@ int gsp_set_active(gsp_context* ctx, const uint32_t* entityIds, uint32_t count, 
 	return GSP_OK;
 }
 
+// f2: TransformSystem::animateAsync for `count` entities, entirely on the device (next.cu: kAnimate).
+int gsp_animate(gsp_context* ctx, const uint32_t* entityIds, const uint8_t* flags, const float* frameA, const float* frameB,
+	const float* t, uint32_t count)
+{
+	if (!ctx || ((!entityIds || !flags || !frameA || !frameB || !t) && count))
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	auto& tf = c.tf;
+	if (!tf.flags || !tf.entityToSlot)
+		return fail(c, GSP_ERR_STATE, "gsp_animate: gsp_set_transforms has not been called");
+	if (count == 0)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	// one upload: ids | t | frameA | frameB | flags
+	const size_t idBytes = (size_t)count * 4, frameBytes = (size_t)count * 40, flagBytes = ((size_t)count + 15) & ~(size_t)15;
+	const size_t bytes = 2 * idBytes + 2 * frameBytes + flagBytes;
+	if (c.hGatherCap < bytes)
+	{
+		GSP_CUDA(cudaStreamSynchronize(c.stream));
+		cudaFreeHost(c.hGather); c.hGather = nullptr; c.hGatherCap = 0;
+		GSP_CUDA(cudaMallocHost((void**)&c.hGather, bytes + bytes / 2));
+		c.hGatherCap = bytes + bytes / 2;
+	}
+	uint8_t* h = c.hGather;
+	memcpy(h, entityIds, idBytes); memcpy(h + idBytes, t, idBytes);
+	memcpy(h + 2 * idBytes, frameA, frameBytes); memcpy(h + 2 * idBytes + frameBytes, frameB, frameBytes);
+	memcpy(h + 2 * idBytes + 2 * frameBytes, flags, count);
+	size_t cap = c.dAosScratchCap;
+	uint8_t* d = (uint8_t*)c.dAosScratch;
+	GSP_CUDA(ensureDevice(d, cap, bytes, false, c.stream));
+	c.dAosScratch = d; c.dAosScratchCap = cap;
+	GSP_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c.stream));
+	GSP_CUDA(cudaMemsetAsync(c.dError, 0, sizeof(uint32_t), c.stream));
+	launchAnimate(c, (const uint32_t*)d, d + 2 * idBytes + 2 * frameBytes, (const float*)(d + 2 * idBytes),
+		(const float*)(d + 2 * idBytes + frameBytes), (const float*)(d + idBytes), count);
+	uint32_t* hScalars = c.hCounters + kCtrCount;
+	GSP_CUDA(cudaMemcpyAsync(&hScalars[1], c.dError, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream)); // the caller's arrays (and the pinned staging block) are free again
+	GSP_CUDA(cudaGetLastError());
+	c.chainDirty = true; c.resultsValid = false; c.frameEnqueued = false;
+	if (hScalars[1] == (uint32_t)GSP_ERR_HIERARCHY)
+		return fail(c, GSP_ERR_HIERARCHY, "gsp_animate: transform hierarchy is cyclic or deeper than 4096");
+	if (hScalars[1])
+		return fail(c, GSP_ERR_INVALID, "gsp_animate: an entity id has no TransformComponent (the other entities were animated)");
+	return GSP_OK;
+}
+
+// Stores position / scale / rotation of every live transform (bytes 16..27, 32..43, 48..63; lane W of position and scale —
+// childCount / childCapacity — is left alone) into the caller's pool: what the ECS needs back after gsp_animate.
+int gsp_writeback_trs(gsp_context* ctx, void* aos, uint32_t stride)
+{
+	if (!ctx)
+		return GSP_ERR_INVALID;
+	Context& c = ctx->c;
+	auto& t = c.tf;
+	if ((!aos && t.occupancy) || stride < kTfMinStride)
+		return fail(c, GSP_ERR_INVALID, "gsp_writeback_trs: bad pointer or stride");
+	if (!t.flags || t.occupancy == 0)
+		return GSP_OK;
+	GSP_CUDA(cudaSetDevice(c.device));
+	const uint32_t n = t.occupancy;
+	std::vector<float4> rot(n), ps(n);
+	std::vector<float2> syz(n);
+	std::vector<uint16_t> flags(n);
+	GSP_CUDA(cudaMemcpyAsync(rot.data(), t.rot, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaMemcpyAsync(ps.data(), t.posSx, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaMemcpyAsync(syz.data(), t.sYZ, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaMemcpyAsync(flags.data(), t.flags, (size_t)n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c.stream));
+	GSP_CUDA(cudaStreamSynchronize(c.stream));
+	uint8_t* base = (uint8_t*)aos;
+	parallelFor(n, [&](uint32_t first, uint32_t last) {
+		for (uint32_t i = first; i < last; i++)
+		{
+			if (!(flags[i] & kTfLive))
+				continue;
+			uint8_t* p = base + (size_t)i * stride;
+			const float pos[3] = { ps[i].x, ps[i].y, ps[i].z }, scl[3] = { ps[i].w, syz[i].x, syz[i].y };
+			memcpy(p + kTfPos, pos, 12); memcpy(p + kTfScale, scl, 12); memcpy(p + kTfRot, &rot[i], 16);
+		}
+	});
+	return GSP_OK;
+}
+
 int gsp_writeback_active(gsp_context* ctx, void* aos, uint32_t stride)
 {
 	if (!ctx)

@@ -357,7 +357,7 @@ int gsp_exchange_autosize(gsp_context* ctx, uint32_t* capacityOut)
 	uint32_t largest = 0;
 	GSP_CUDA(cudaMemcpyAsync(&largest, x.dScalar + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
-	uint64_t cap = x.allToAll ? (uint64_t)largest * 3 / (2 * x.ranks) + 8192 : (uint64_t)largest * 5 / 4 + 4096;
+	uint64_t cap = x.allToAll ? (uint64_t)largest * 4 / (3 * x.ranks) + 8192 : (uint64_t)largest * 5 / 4 + 4096;
 	if (capacityOut) *capacityOut = (uint32_t)cap;
 	return allocateSets(c, (uint32_t)cap);
 }

@@ -428,6 +428,7 @@ uint32_t launchMergePacked(cudaStream_t stream, uint32_t ranks, uint32_t myRank,
 
 // ---- all-to-all protocol: common splitters from samples, one sub-block per destination --------------------------------------
 constexpr uint32_t kSamples = 64, kSampleWords = kSamples + 1; // (exchange.cu: kExSamples)
+constexpr uint32_t kPackMaxRanks = 32;
 
 // samples[list][k] = key at position (2k + 1) * count / (2 * kSamples) of my sorted run, samples[list][kSamples] = count
 __global__ void kSampleRuns(const SegmentDev* __restrict__ segments, const uint32_t* __restrict__ counters,
@@ -469,9 +470,14 @@ __global__ void __launch_bounds__(1024) kSplitRuns(const __grid_constant__ Split
 	{
 		bounds[0] = 0; bounds[A.ranks] = myCount;
 	}
+	// every rank's samples of this list into shared memory (the value search below probes them ~200 times per lane)
+	__shared__ uint32_t sSamples[kPackMaxRanks][kSampleWords];
+	for (uint32_t i = threadIdx.x; i < A.ranks * kSampleWords; i += blockDim.x)
+		sSamples[i / kSampleWords][i % kSampleWords] = A.gathered[((size_t)(i / kSampleWords) * A.lists + l) * kSampleWords + i % kSampleWords];
+	__syncthreads();
 	if (j >= A.ranks)
 		return; // (whole warps)
-	const uint32_t* mine = lane < A.ranks ? A.gathered + ((size_t)lane * A.lists + l) * kSampleWords : nullptr;
+	const uint32_t* mine = lane < A.ranks ? sSamples[lane] : nullptr;
 	const unsigned long long weight = mine ? mine[kSamples] : 0ull;
 	unsigned long long totalWeight = 0;
 	{
@@ -524,7 +530,6 @@ struct PackArgs
 	uint32_t* __restrict__ blocks;       // [ranks][kExHeaderWords + 2 * capacity]
 	uint32_t lists, ranks, capacity;
 };
-constexpr uint32_t kPackMaxRanks = 32;
 __global__ void __launch_bounds__(256) kPackByDestination(const __grid_constant__ PackArgs A)
 {
 	__shared__ uint32_t sBound[kPackMaxRanks + 1];

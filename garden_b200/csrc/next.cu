@@ -116,6 +116,121 @@ __global__ void __launch_bounds__(256) kPropagateActive(uint32_t count, const ui
 	}
 }
 
+// ---- f2: TransformSystem::animateAsync (source/system/transform.cpp:609-623) on the staged transforms ----------------------------
+// lerp(f32x4 a, f32x4 b, float t) = a * (1 - t) + b * t (simd/vector/float.hpp:1469: two lane-wise products and a sum, no FMA):
+// position and scale are bit-exact. slerp (quaternion.hpp:175-193): dot4, shortest path, lerp when cosTheta > 1 - FLT_EPSILON,
+// else (a * sin((1 - t) * angle) + c * sin(t * angle)) / sin(angle) — the reference calls the HOST libm (acosf / sinf), the
+// device has its own (<= 2 ulp each), so the rotation carries a stated tolerance (tests/test_gpu_next.py). isActive goes through
+// the self bit + kPropagateActive like gsp_set_active. The per-transform data derived from TRS (exact-local flag, prepass
+// bound) is refreshed here; the chain records are marked stale by the caller.
+struct AnimateArgs
+{
+	const uint32_t* __restrict__ ids;
+	const uint8_t* __restrict__ flags;
+	const float* __restrict__ frameA;
+	const float* __restrict__ frameB;
+	const float* __restrict__ t;
+	const uint32_t* __restrict__ entityToSlot;
+	float4* __restrict__ rot;
+	float4* __restrict__ posSx;
+	float2* __restrict__ sYZ;
+	uint16_t* __restrict__ tflags;
+	float2* __restrict__ bound;
+	uint32_t* __restrict__ error;
+	uint32_t count, entityCap;
+};
+__global__ void __launch_bounds__(256) kAnimate(const __grid_constant__ AnimateArgs A)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= A.count)
+		return;
+	const uint32_t e = A.ids[i];
+	const uint32_t s1 = (e && e < A.entityCap) ? A.entityToSlot[e] : 0;
+	if (!s1)
+	{
+		atomicExch(A.error, (uint32_t)GSP_ERR_INVALID); // Manager::get<TransformComponent> would throw (ecsm.hpp:863-873)
+		return;
+	}
+	const uint32_t s = s1 - 1;
+	const uint32_t f = A.flags[i];
+	const float* a = A.frameA + (size_t)i * 10;
+	const float* b = A.frameB + (size_t)i * 10;
+	const float t = A.t[i], u = __fsub_rn(1.0f, t);
+	float4 ps = A.posSx[s];
+	float2 syz = A.sYZ[s];
+	float4 q = A.rot[s];
+	if (f & 1u) // animatePosition
+	{
+		ps.x = __fadd_rn(__fmul_rn(a[0], u), __fmul_rn(b[0], t));
+		ps.y = __fadd_rn(__fmul_rn(a[1], u), __fmul_rn(b[1], t));
+		ps.z = __fadd_rn(__fmul_rn(a[2], u), __fmul_rn(b[2], t));
+	}
+	if (f & 2u) // animateScale
+	{
+		ps.w = __fadd_rn(__fmul_rn(a[3], u), __fmul_rn(b[3], t));
+		syz.x = __fadd_rn(__fmul_rn(a[4], u), __fmul_rn(b[4], t));
+		syz.y = __fadd_rn(__fmul_rn(a[5], u), __fmul_rn(b[5], t));
+	}
+	if (f & 4u) // animateRotation
+	{
+		const float* qa = a + 6;
+		float c[4] = { b[6], b[7], b[8], b[9] };
+		float cosTheta = __fadd_rn(__fadd_rn(__fmul_rn(qa[0], c[0]), __fmul_rn(qa[1], c[1])), __fadd_rn(__fmul_rn(qa[2], c[2]), __fmul_rn(qa[3], c[3])));
+		if (cosTheta < 0.0f)
+		{
+			#pragma unroll
+			for (int l = 0; l < 4; l++) c[l] = -c[l];
+			cosTheta = -cosTheta;
+		}
+		float v[4];
+		if (cosTheta > 1.0f - 1.1920928955078125e-07f)
+		{
+			#pragma unroll
+			for (int l = 0; l < 4; l++) v[l] = __fadd_rn(__fmul_rn(qa[l], u), __fmul_rn(c[l], t));
+		}
+		else
+		{
+			const float angle = acosf(cosTheta);
+			const float w0 = sinf(__fmul_rn(u, angle)), w1 = sinf(__fmul_rn(t, angle)), w2 = sinf(angle);
+			#pragma unroll
+			for (int l = 0; l < 4; l++) v[l] = __fdiv_rn(__fadd_rn(__fmul_rn(qa[l], w0), __fmul_rn(c[l], w1)), w2);
+		}
+		q = make_float4(v[0], v[1], v[2], v[3]);
+	}
+	if (f & 7u)
+	{
+		A.posSx[s] = ps; A.sYZ[s] = syz; A.rot[s] = q;
+		Mat43 unused;
+		const bool exact = !localModel43Fast<true>(ps.x, ps.y, ps.z, q.x, q.y, q.z, q.w, ps.w, syz.x, syz.y, unused);
+		A.bound[s] = transformBound(ps.x, ps.y, ps.z, ps.w, syz.x, syz.y, q.x, q.y, q.z, q.w);
+		uint32_t* word = reinterpret_cast<uint32_t*>(A.tflags) + (s >> 1);
+		const uint32_t bit = (uint32_t)kTfExactLocal << ((s & 1) * 16);
+		if (exact) atomicOr(word, bit); else atomicAnd(word, ~bit);
+	}
+	if (f & 8u) // animateIsActive: setActive(round(t) ? b.isActive : a.isActive), transform.cpp:620-621
+	{
+		const bool active = roundf(t) != 0.0f ? ((f >> 5) & 1u) : ((f >> 4) & 1u);
+		uint32_t* word = reinterpret_cast<uint32_t*>(A.tflags) + (s >> 1);
+		const uint32_t bit = (uint32_t)kTfSelfBit << ((s & 1) * 16);
+		if (active) atomicOr(word, bit); else atomicAnd(word, ~bit);
+	}
+}
+
+uint32_t launchAnimate(Context& c, const uint32_t* dIds, const uint8_t* dFlags, const float* dA, const float* dB, const float* dT,
+	uint32_t count)
+{
+	auto& t = c.tf;
+	if (!count)
+		return 0;
+	AnimateArgs A;
+	A.ids = dIds; A.flags = dFlags; A.frameA = dA; A.frameB = dB; A.t = dT; A.entityToSlot = t.entityToSlot;
+	A.rot = t.rot; A.posSx = t.posSx; A.sYZ = t.sYZ; A.tflags = t.flags; A.bound = t.bound; A.error = c.dError;
+	A.count = count; A.entityCap = t.entityCap;
+	kAnimate<<<(count + 255) / 256, 256, 0, c.stream>>>(A);
+	kPropagateActive<<<(t.occupancy + 255) / 256, 256, 0, c.stream>>>(t.occupancy, t.parent, t.flags, c.dError);
+	return 2;
+}
+
 uint32_t launchSetActive(Context& c, const uint32_t* dIds, uint32_t count, int active)
 {
 	auto& t = c.tf;

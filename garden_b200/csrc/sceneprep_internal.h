@@ -256,6 +256,8 @@ uint32_t launchSort(Context& c, cudaEvent_t afterHistogram);
 uint32_t launchEmit(Context& c);
 uint32_t launchInstances(Context& c, int seg, const float* viewProj, void* dDst, uint32_t stride, uint32_t offset, uint32_t capacity);
 uint32_t launchSetActive(Context& c, const uint32_t* dIds, uint32_t count, int active);
+uint32_t launchAnimate(Context& c, const uint32_t* dIds, const uint8_t* dFlags, const float* dA, const float* dB, const float* dT,
+	uint32_t count);
 uint32_t launchExportPacked(Context& c, uint32_t* dBlock, uint32_t capacity);
 void destroyExchange(Context& c);
 uint32_t launchPackVisible(Context& c, uint32_t pool, uint32_t* dBits);

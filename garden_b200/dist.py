@@ -79,6 +79,55 @@ def plan_from_blocks(gathered: np.ndarray, ranks: int, lists: int, capacity: int
     return offsets, counts, out_offsets, flags
 
 
+# ---- the all-to-all protocol (garden_b200/csrc/merge.cu: kSampleRuns / kSplitRuns / kPackByDestination), stated in numpy ------
+EX_SAMPLES = 64
+
+
+def sample_run(keys: np.ndarray) -> np.ndarray:
+    """What kSampleRuns writes for one sorted run: EX_SAMPLES keys at positions (2k + 1) * n / (2 * EX_SAMPLES), then n."""
+    n = len(keys)
+    out = np.full(EX_SAMPLES + 1, 0xFFFFFFFF, dtype=np.uint32)
+    if n:
+        pos = ((2 * np.arange(EX_SAMPLES, dtype=np.uint64) + 1) * np.uint64(n)) // np.uint64(2 * EX_SAMPLES)
+        out[:EX_SAMPLES] = np.asarray(keys, dtype=np.uint32)[pos.astype(np.int64)]
+    out[EX_SAMPLES] = n
+    return out
+
+
+def common_splitters(samples: np.ndarray) -> np.ndarray:
+    """samples: [ranks, EX_SAMPLES + 1] of ONE list (every rank holds the same array after the all-gather).
+    Splitter j (j = 1 .. ranks-1) = the smallest key x whose weighted rank W(x) = sum_r n_r * #(samples of r <= x) reaches
+    ceil(j / ranks * sum_r n_r * EX_SAMPLES) — integer arithmetic, identical on every rank (kSplitRuns)."""
+    samples = np.asarray(samples, dtype=np.uint64)
+    ranks = samples.shape[0]
+    weights = samples[:, EX_SAMPLES]
+    total = int(weights.sum()) * EX_SAMPLES
+    out = np.full(max(ranks - 1, 0), 0xFFFFFFFF, dtype=np.uint32)
+    if total == 0:
+        return out
+    for j in range(1, ranks):
+        target = (total * j + ranks - 1) // ranks
+        lo, hi = 0, 0xFFFFFFFF
+        while lo < hi:
+            mid = lo + ((hi - lo) >> 1)
+            w = sum(int(weights[r]) * int(np.searchsorted(samples[r, :EX_SAMPLES], mid, side="right")) for r in range(ranks)
+                    if weights[r])
+            if w >= target:
+                hi = mid
+            else:
+                lo = mid + 1
+        out[j - 1] = lo
+    return out
+
+
+def split_bounds(keys: np.ndarray, splitters: np.ndarray) -> np.ndarray:
+    """[ranks + 1] cut positions of one sorted run: destination d gets keys[b[d]:b[d+1]]; a key equal to a splitter starts
+    the next range."""
+    keys = np.asarray(keys, dtype=np.uint32)
+    inner = np.searchsorted(keys, np.asarray(splitters, dtype=np.uint32), side="left")
+    return np.concatenate([[0], np.maximum.accumulate(inner), [len(keys)]]).astype(np.int64)
+
+
 def merge_reference(runs_keys, runs_payloads, my_rank: int | None = None):
     """numpy statement of the merge for ONE list: runs_* are per-rank arrays (sorted by key, ties by payload).
     Returns (keys, payloads, ranks) of the full merged list, or of rank `my_rank`'s key-range slice plus its start."""

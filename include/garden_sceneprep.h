@@ -244,6 +244,19 @@ int gsp_view_from_viewproj(const float* viewProj, const float* cameraOffset, int
  * gsp_writeback_active stores the resulting selfActive / ancestorsActive bytes (offsets 72 / 73) into the caller's pool.
  * A later gsp_set_transforms / gsp_update_transforms re-reads these bytes from the caller's memory. */
 int gsp_set_active(gsp_context* ctx, const uint32_t* entityIds, uint32_t count, int active);
+/* TransformSystem::animateAsync (source/system/transform.cpp:609-623; AnimationSystem::update, animation.cpp:155-190) for
+ * `count` entities (1-based ECS ids, each listed once) on the staged transforms — the keyframe pair never becomes an upload of
+ * whole components. flags[i]: bit 0 animatePosition, 1 animateScale, 2 animateRotation, 3 animateIsActive, 4 frameA.isActive,
+ * 5 frameB.isActive; frameA / frameB: [count][10] floats = position xyz, scale xyz, rotation xyzw; t[count].
+ * position / scale = lerp, bit-exact (a * (1 - t) + b * t, simd/vector/float.hpp:1469); rotation = slerp (quaternion.hpp:175-193):
+ * same branches and operation order, but acosf / sinf are the device's (<= 2 ulp each) where the reference calls the host
+ * libm: components agree within 4e-6 for unit quaternions (tests/test_gpu_next.py states and checks it); isActive =
+ * setActive(round(t) ? b.isActive : a.isActive) with the semantics of gsp_set_active.
+ * gsp_writeback_trs stores position / scale / rotation of every live transform into the caller's pool (bytes 16-27, 32-43,
+ * 48-63), gsp_writeback_active the flags. */
+int gsp_animate(gsp_context* ctx, const uint32_t* entityIds, const uint8_t* flags, const float* frameA, const float* frameB,
+	const float* t, uint32_t count);
+int gsp_writeback_trs(gsp_context* ctx, void* aos, uint32_t stride);
 int gsp_writeback_active(gsp_context* ctx, void* aos, uint32_t stride);
 
 /* Stores MeshRenderComponent::isVisible (offset 15) for every slot of `pool` exactly as the reference's main-view pass

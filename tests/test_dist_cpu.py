@@ -157,3 +157,92 @@ def test_plan_from_blocks_flags():
     bad = g.copy(); bad[0] = 1
     assert plan_from_blocks(bad, 2, 2, cap, out_capacity=32)[3][0] == 2
     assert plan_from_blocks(g, 2, 3, cap, out_capacity=32)[3][0] == 2  # list count mismatch
+
+
+# ---- the all-to-all protocol: common splitters from samples, one sub-block per destination ---------------------------------
+def test_common_splitters_balance_and_agree():
+    from garden_b200.dist import EX_SAMPLES, common_splitters, sample_run, split_bounds
+    rng = np.random.default_rng(5)
+    for ranks in (1, 2, 3, 8):
+        for trial in range(6):
+            runs = [np.sort(rng.integers(0, 1 << (8 if trial % 2 else 30), int(rng.integers(0, 20000))).astype(np.uint32)) for _ in range(ranks)]
+            if trial == 5:
+                runs[0] = np.zeros(0, np.uint32)  # an empty run carries no weight
+            samples = np.stack([sample_run(k) for k in runs])
+            assert samples.shape == (ranks, EX_SAMPLES + 1) and [int(s[-1]) for s in samples] == [len(k) for k in runs]
+            sp = common_splitters(samples)
+            assert sp.size == ranks - 1 and np.all(np.diff(sp.astype(np.int64)) >= 0)
+            bounds = [split_bounds(k, sp) for k in runs]
+            for b, k in zip(bounds, runs):
+                assert b[0] == 0 and b[-1] == len(k) and np.all(np.diff(b) >= 0)
+            # every key lands in exactly one destination, destinations are key ranges, and (few ties) they are balanced
+            total = sum(len(k) for k in runs)
+            sizes = [sum(int(b[d + 1] - b[d]) for b in bounds) for d in range(ranks)]
+            assert sum(sizes) == total
+            for d in range(ranks - 1):
+                left = [k[b[d]:b[d + 1]] for k, b in zip(runs, bounds)]
+                right = [k[b[d + 1]:b[d + 2]] for k, b in zip(runs, bounds)]
+                lmax = max((int(x.max()) for x in left if x.size), default=-1)
+                rmin = min((int(x.min()) for x in right if x.size), default=1 << 40)
+                assert lmax < rmin
+            if trial % 2 == 0 and total > 4000:
+                assert max(sizes) <= total / ranks * 1.25 + 64, (ranks, sizes)
+
+
+def _gloo_alltoall_worker(rank, world, port, out_dir):
+    """The all-to-all exchange over gloo with the numpy statements: samples all-gathered, common splitters, every rank cuts
+    its runs and hands destination d its pieces, every rank merges what it received; the slices tile the full merge."""
+    import torch
+    import torch.distributed as dist
+    from garden_b200.dist import common_splitters, sample_run, split_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    keys, pays = _lists_for_rank(rank)
+    lists = len(keys)
+    mine = torch.from_numpy(np.stack([sample_run(k) for k in keys]).astype(np.int64))
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    samples = np.stack([g.numpy() for g in gathered]).astype(np.uint32)  # [ranks, lists, S + 1]
+    out = {}
+    pieces = [[None] * lists for _ in range(world)]
+    for l in range(lists):
+        sp = common_splitters(samples[:, l, :])
+        b = split_bounds(keys[l], sp)
+        for d in range(world):
+            pieces[d][l] = (keys[l][b[d]:b[d + 1]], pays[l][b[d]:b[d + 1]])
+    received = [None] * world
+    # (gloo has no all_to_all: the object channel stands in for ncclSend / ncclRecv)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, pieces)
+    for src in range(world):
+        received[src] = everyone[src][rank]
+    lengths = np.zeros(lists, np.int64)
+    for l in range(lists):
+        k, p, s = merge_reference([received[src][l][0] for src in range(world)], [received[src][l][1] for src in range(world)])
+        out[f"k{l}"], out[f"p{l}"], out[f"s{l}"] = k, p, s
+        lengths[l] = k.size
+    all_len = [None] * world
+    dist.all_gather_object(all_len, lengths)
+    out["start"] = np.sum(np.stack(all_len)[:rank], axis=0) if rank else np.zeros(lists, np.int64)
+    np.savez(os.path.join(out_dir, f"a{rank}.npz"), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_alltoall_exchange_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    world, lists = 2, 3
+    per_rank = [_lists_for_rank(r, lists) for r in range(world)]
+    mp.spawn(_gloo_alltoall_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"a{r}.npz") for r in range(world)]
+    for l in range(lists):
+        full_k, full_p, full_r = merge_reference([per_rank[r][0][l] for r in range(world)], [per_rank[r][1][l] for r in range(world)])
+        pos = 0
+        for r in range(world):
+            assert int(res[r]["start"][l]) == pos
+            n = res[r][f"k{l}"].size
+            assert np.array_equal(res[r][f"k{l}"], full_k[pos:pos + n]) and np.array_equal(res[r][f"p{l}"], full_p[pos:pos + n])
+            assert np.array_equal(res[r][f"s{l}"], full_r[pos:pos + n])
+            pos += n
+        assert pos == full_k.size
