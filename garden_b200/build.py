@@ -14,7 +14,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "libgarden_sceneprep.so"
-SOURCES = ["staging.cu", "cull.cu", "sort.cu", "emit.cu", "merge.cu", "exchange.cu", "visible.cu", "selftest.cu", "next.cu", "api.cu"]
+SOURCES = ["staging.cu", "cull.cu", "sort.cu", "emit.cu", "merge.cu", "exchange.cu", "viewsetup.cu", "visible.cu", "selftest.cu", "next.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # parity kernels spell every rounding explicitly (__fmul_rn/__fmaf_rn/...); -fmad=false is belt and braces

@@ -238,6 +238,23 @@ int gsp_emit_instances_device(gsp_context* ctx, uint32_t view, int listKind, uin
  * viewProj the way the callers of prepareMeshes build their arguments (mesh.cpp:815,869,902; no UI frustum). */
 void gsp_frustum_planes(const float* viewProj, float* planes);
 int gsp_view_from_viewproj(const float* viewProj, const float* cameraOffset, int32_t shadowPass, gsp_view* view);
+/* The matrices themselves, in the reference's float operation order (host code; csrc/viewsetup.cu), so that a caller that hands
+ * over camera parameters instead of planes gets the reference's planes bit for bit. All matrices: 16 floats, column-major.
+ *   gsp_camera_view_proj   GraphicsSystem::prepareCommonConstants for a perspective camera without a parent
+ *                          (source/system/graphics.cpp:168-172,192-203,241; camera.hpp:111-121): the camera-relative view
+ *                          (translation zeroed), calcPerspProjInfRevZ, viewProj = projection * view
+ *   gsp_light_view_proj    calcLightViewProj (source/system/render/csm.cpp:260-308): cascade viewProj + cameraOffset for the
+ *                          camera sub-frustum [nearPlane, farPlane]
+ *   gsp_cascade_views      CsmRenderSystem::prepareShadowRender for passes 0 .. cascadeCount-1 (csm.cpp:311-329): `splits`
+ *                          holds cascadeCount-1 fractions of shadowDistance (csm.hpp:89); fills views[i] (planes, offset,
+ *                          shadowPass = i) and, if not NULL, viewProjs[i][16] */
+int gsp_camera_view_proj(const float* position, const float* rotation, const float* scale, float fieldOfView, float aspectRatio,
+	float nearPlane, float* view, float* projection, float* viewProj);
+int gsp_light_view_proj(const float* view, const float* lightDir, float fieldOfView, float aspectRatio, float nearPlane, float farPlane,
+	float zCoeff, uint32_t shadowMapSize, float* viewProj, float* cameraOffset);
+int gsp_cascade_views(const float* view, const float* lightDir, float fieldOfView, float aspectRatio, float cameraNear,
+	float shadowDistance, const float* splits, uint32_t cascadeCount, float zCoeff, uint32_t shadowMapSize, gsp_view* views,
+	float* viewProjs);
 /* TransformComponent::setActive(active) (source/system/transform.cpp:75-127) for `count` entities (1-based ECS ids) on the
  * staged hierarchy: selfActive is set, ancestorsActive is re-derived for every transform (AND of its ancestors' selfActive,
  * the invariant every setActive call maintains), and the next gsp_run filters on the new isActive() values.
