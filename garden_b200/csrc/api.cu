@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 #include <new>
 
 using namespace gsp;
@@ -1307,28 +1310,104 @@ int gsp_export_runs_packed(gsp_context* ctx, uint32_t* dBlock, uint32_t capacity
 
 } // extern "C"
 
-// Runs fn(first, last) over [0, n) on a few host threads (the write-back scatter touches every cache line of the pool).
+// Runs fn(first, last) over [0, n) on the library's host workers (the write-back scatter touches every cache line of a pool).
+// The workers are PERSISTENT (created on first use, parked on a condition variable between calls) and their number is
+// hardware_concurrency divided by the number of GPU processes sharing the host (LOCAL_WORLD_SIZE, as torchrun / mpirun set it),
+// at most 16; GSP_HOST_THREADS overrides. Eight ranks on a 32-core host thus run 4 workers each instead of 8 x 16 fresh threads.
+namespace
+{
+class HostWorkers
+{
+public:
+	static HostWorkers& get()
+	{
+		static HostWorkers pool;
+		return pool;
+	}
+	uint32_t size() const { return (uint32_t)threads.size() + 1; } // the caller works too
+	template<class F> void run(uint32_t n, F fn)
+	{
+		const uint32_t parts = size();
+		const uint32_t per = ((n + parts - 1) / parts + 31u) & ~31u;
+		std::function<void(uint32_t)> job = [&](uint32_t part)
+		{
+			const uint32_t first = (uint32_t)std::min<uint64_t>((uint64_t)part * per, n);
+			const uint32_t last = (uint32_t)std::min<uint64_t>((uint64_t)first + per, n);
+			if (first < last)
+				fn(first, last);
+		};
+		{
+			std::lock_guard<std::mutex> serial(callers); // (contexts of several caller threads share the workers)
+			{
+				std::lock_guard<std::mutex> lock(m);
+				current = &job; pending = (uint32_t)threads.size(); generation++;
+			}
+			wake.notify_all();
+			job(parts - 1);
+			std::unique_lock<std::mutex> lock(m);
+			done.wait(lock, [&]{ return pending == 0; });
+			current = nullptr;
+		}
+	}
+private:
+	HostWorkers()
+	{
+		uint32_t n = std::max(1u, std::thread::hardware_concurrency());
+		if (const char* e = getenv("LOCAL_WORLD_SIZE"))
+			n = std::max(1u, n / (uint32_t)std::max(1, atoi(e)));
+		n = std::min(n, 16u);
+		if (const char* e = getenv("GSP_HOST_THREADS"))
+			n = (uint32_t)std::max(1, std::min(64, atoi(e)));
+		for (uint32_t i = 0; i + 1 < n; i++)
+			threads.emplace_back([this, i]{ loop(i); });
+	}
+	~HostWorkers()
+	{
+		{
+			std::lock_guard<std::mutex> lock(m);
+			quit = true;
+		}
+		wake.notify_all();
+		for (auto& t : threads) t.join();
+	}
+	void loop(uint32_t index)
+	{
+		uint64_t seen = 0;
+		while (true)
+		{
+			std::function<void(uint32_t)>* job;
+			{
+				std::unique_lock<std::mutex> lock(m);
+				wake.wait(lock, [&]{ return quit || generation != seen; });
+				if (quit) return;
+				seen = generation; job = current;
+			}
+			(*job)(index);
+			{
+				std::lock_guard<std::mutex> lock(m);
+				if (--pending == 0) done.notify_one();
+			}
+		}
+	}
+	std::vector<std::thread> threads;
+	std::mutex m, callers;
+	std::condition_variable wake, done;
+	std::function<void(uint32_t)>* current = nullptr;
+	uint32_t pending = 0;
+	uint64_t generation = 0;
+	bool quit = false;
+};
+} // namespace
+
 template<class F>
 static void parallelFor(uint32_t n, F fn)
 {
-	uint32_t threads = std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-	if (n < (1u << 18))
-		threads = 1;
-	if (threads == 1)
+	if (n < (1u << 18) || HostWorkers::get().size() == 1)
 	{
 		fn(0u, n);
 		return;
 	}
-	std::vector<std::thread> pool;
-	const uint32_t per = ((n + threads - 1) / threads + 31u) & ~31u;
-	for (uint32_t t = 0; t < threads; t++)
-	{
-		const uint32_t first = std::min<uint64_t>((uint64_t)t * per, n), last = std::min<uint64_t>((uint64_t)first + per, n);
-		if (first < last)
-			pool.emplace_back([=]{ fn(first, last); });
-	}
-	for (auto& th : pool)
-		th.join();
+	HostWorkers::get().run(n, fn);
 }
 
 // Mapped pinned host words the write-back kernels store into directly (+2 trailing words: device counter mirror).

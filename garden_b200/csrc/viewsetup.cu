@@ -9,7 +9,7 @@
 // lanes at a time, an FMA exactly where the reference's AVX2 build fuses (MATH_SIMD_FMA), dpps sums as (p0 + p1) + (p2 + p3),
 // tan / floor from the host libm like the reference. Host code only: no device is needed for these entry points.
 // Pinned against the reference's OWN csm.cpp and math headers (oracle/ref_views.cpp -> oracle/_ref/libgarden_ref_views.so,
-// tests/test_views.py) and against golden vectors made with them (tests/golden/views.npz).
+// tests/test_views.py) and against golden vectors made with them (tests/golden/frows/views.npz).
 #include "../../include/garden_sceneprep.h"
 
 #include <cmath>

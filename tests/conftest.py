@@ -11,6 +11,7 @@ for p in (str(ROOT), str(ROOT / "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "multigpu: needs at least two CUDA devices (run with -m multigpu under gpurun --gpus 2)")
 
 
 def _device_usable() -> bool:
@@ -30,10 +31,24 @@ def _device_usable() -> bool:
         return False
 
 
+def _gpu_count() -> int:
+    try:
+        import subprocess
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except Exception:
+        return 0
+
+
 def pytest_collection_modifyitems(config, items):
-    """A plain `pytest tests` on a box without a usable sm_100 device skips the gpu-marked tests instead of failing them
-    (tests/test_abi.py::test_no_cpu_fallback stays the one place that asserts the loud failure). With `-m gpu` — how the
-    GPU box runs them — nothing is skipped: a missing device must fail there, not pass silently."""
+    """(1) `multigpu` tests are DESELECTED (not skipped) where fewer than two GPUs exist, so the single-GPU run of `-m gpu`
+    carries no skips. (2) A plain `pytest tests` on a box without a usable sm_100 device skips the gpu-marked tests instead
+    of failing them (tests/test_abi.py::test_no_cpu_fallback stays the one place that asserts the loud failure). With
+    `-m gpu` — how the GPU box runs them — nothing is skipped: a missing device must fail there, not pass silently."""
+    multi = [it for it in items if it.get_closest_marker("multigpu")]
+    if multi and _gpu_count() < 2:
+        config.hook.pytest_deselected(items=multi)
+        items[:] = [it for it in items if not it.get_closest_marker("multigpu")]
     markexpr = config.getoption("-m", default="") or ""
     if "gpu" in markexpr and "not gpu" not in markexpr:
         return
