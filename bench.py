@@ -40,6 +40,7 @@ WORKLOADS = {
     # configs[4]: 64M entities over 8 GPUs = 8M per GPU (weak-scaling shard), 16 independent views
     "C5": ("C5", 8_000_000, "64M entities / 8 GPUs (8M per GPU), depth-8, 16 independent views (2 cube probes + 4 split-screen)"),
 }
+SHADOW_DISTANCE = 100.0  # csm.hpp:88 default; --shadow-distance raises it so that the cascades see a larger share of the scene
 CUBE_FACES = [(0.0, 0.0), (1.5707964, 0.0), (3.1415927, 0.0), (-1.5707964, 0.0), (0.0, 1.5), (0.0, -1.5)]  # (yaw, pitch)
 
 
@@ -53,7 +54,7 @@ def frame_views_vps(workload: str):
         b, vb = V.perspective_views([(y + 0.4, p * 0.9) for y, p in CUBE_FACES], 1.5707964, 1.0, 0.01)
         c, vc = V.perspective_views([(0.3, -0.1), (1.9, -0.05), (3.6, -0.12), (5.1, -0.08)], 1.2, 16 / 9, 0.01)
         return np.concatenate([a, b, c]), list(va) + list(vb) + list(vc)
-    return V.camera_and_cascades(0.6, -0.12, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    return V.camera_and_cascades(0.6, -0.12, 1.2, 16 / 9, 0.01, SHADOW_DISTANCE, (0.05, 0.1, 0.25, 1.0))
 
 
 def frame_views(workload: str):
@@ -709,7 +710,7 @@ def run_b200_arm(args):
                        "frames_timed": frames_timed,
                        "timing": f"every one of the {args.steps} steps repeated {reps}x back to back (sustained load, "
                                  f">= {args.min_seconds} s); ms_per_step is per frame",
-                       "views": int(views.size), "visible_total": int(visible_sum),
+                       "views": int(views.size), "visible_total": int(visible_sum), "shadow_distance": SHADOW_DISTANCE,
                        "l2": "inputs larger than L2 (%.2f GB of SoA streams per frame vs 126 MB L2)" % (75 * n / 1e9),
                        "sharding": ("contiguous entity ranges per GPU, all views per GPU; sorted runs exchanged over NCCL by "
                                     "key range (fixed-capacity blocks, no host synchronisation) and k-way merged; "
@@ -755,7 +756,7 @@ def run_b200_arm(args):
 
 def main():
     # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner) is sent to stderr
-    global _JSON_OUT
+    global _JSON_OUT, SHADOW_DISTANCE
     sys.stdout.flush()
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -778,7 +779,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: wait for every frame's exchange before the next frame")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the merged-order check against a single-GPU sort")
+    ap.add_argument("--shadow-distance", type=float, default=0.0,
+                    help="CSM shadow distance of the camera + cascades workloads (default 100: the reference's); larger values "
+                         "let every cascade see 10-15 %% of the scene (SURVEY.md 8d)")
     args = ap.parse_args()
+    if args.shadow_distance > 0:
+        SHADOW_DISTANCE = args.shadow_distance
     if args.impl == "reference":
         run_reference_arm(args)
     else:
