@@ -737,7 +737,7 @@ def run_b200_arm(args):
         if world > 1:
             line["exchange"] = {"frame_latency_ms_serialised": latency_ms, "bytes_received_per_rank": exchange_bytes,
                                 "protocol": "alltoall" if merger.all_to_all else "allgather",
-                                "collectives_per_frame": 3 if merger.all_to_all else 1, "host_syncs_per_frame": 0,
+                                "collectives_per_frame": 2 if merger.all_to_all else 1, "host_syncs_per_frame": 0,
                                 "where": "inside libgarden_sceneprep.so (gsp_exchange_async, NCCL loaded by the library)",
                                 "parts_rank0": exchange_parts}
             line["config"]["merge_check"] = merge_check

@@ -110,6 +110,8 @@ struct Exchange
 	uint64_t frameIndex = 0;
 	bool allToAll = true, timing = false;
 	uint32_t* dScalar = nullptr; // 2 words for the autosize reduction
+	uint32_t* mergeScratch = nullptr; // the two intermediate levels of the merge tree (merges are serialised on `stream`)
+	bool treeMerge = true;            // GSP_MERGE=slice: rank every element in every other run instead (kMergeSlice)
 };
 
 } // namespace gsp
@@ -120,13 +122,12 @@ namespace gsp
 {
 uint32_t launchMergePacked(cudaStream_t stream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
 	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPays, uint8_t* dOutRanks,
-	uint32_t outCapacity, bool preSplit);
+	uint32_t outCapacity, bool preSplit, uint32_t* dTreeScratch, uint32_t smCount);
 uint32_t launchSampleRuns(Context& c, uint32_t* dSamples);
 uint32_t launchSplitAndPack(Context& c, cudaStream_t stream, uint32_t ranks, const uint32_t* dMySamples, const uint32_t* dGatheredSamples,
 	uint32_t* dSplitters, uint32_t* dSendBlocks, uint32_t capacityPerDest);
-uint32_t launchSliceStarts(cudaStream_t stream, uint32_t ranks, uint32_t myRank, uint32_t lists, const uint32_t* dGatheredLengths,
+uint32_t launchSliceStarts(cudaStream_t stream, uint32_t ranks, uint32_t lists, const uint32_t* dReceived, uint32_t capacityPerDest,
 	uint32_t* dSliceInfo);
-uint32_t launchSliceLengths(cudaStream_t stream, uint32_t lists, const uint32_t* dSliceInfo, uint32_t* dLengths);
 }
 
 #define GSP_CUDA(call)                                                                             \
@@ -162,6 +163,8 @@ static void freeSets(Exchange& x)
 		s.outRanks = nullptr;
 		s.used = s.pending = false;
 	}
+	cudaFree(x.mergeScratch);
+	x.mergeScratch = nullptr;
 	x.capacity = x.outCapacity = 0;
 }
 
@@ -199,6 +202,8 @@ static int attachComm(Context& c, ncclComm_t comm, uint32_t ranks, uint32_t rank
 	x->comm = comm; x->ranks = ranks; x->rank = rank;
 	const char* mode = getenv("GSP_EXCHANGE");
 	x->allToAll = !(mode && !strcmp(mode, "allgather"));
+	const char* merge = getenv("GSP_MERGE");
+	x->treeMerge = !(merge && !strcmp(merge, "slice"));
 	c.exchange = x;
 	GSP_CUDA(cudaSetDevice(c.device));
 	GSP_CUDA(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
@@ -220,6 +225,8 @@ static int allocateSets(Context& c, uint32_t capacity)
 	GSP_CUDA(cudaStreamSynchronize(c.stream));
 	freeSets(x);
 	x.lists = (uint32_t)c.segments.size();
+	if (x.allToAll && 2u * x.lists > kExMaxLists)
+		x.allToAll = false; // the sub-block headers carry two words per list: beyond that, the all-gather protocol
 	const uint32_t lists = std::max(1u, x.lists), ranks = x.ranks;
 	const size_t blockWords = kExHeaderWords + 2ull * capacity;
 	// allgather: every rank's slice fits even if one key range swallowed everything; alltoall: what can be received
@@ -244,6 +251,8 @@ static int allocateSets(Context& c, uint32_t capacity)
 		GSP_CUDA(cudaMallocHost((void**)&s.hFlags, 8 * sizeof(uint32_t)));
 		memset(s.hFlags, 0, 8 * sizeof(uint32_t));
 	}
+	if (x.treeMerge)
+		GSP_CUDA(cudaMalloc((void**)&x.mergeScratch, (4ull * outCap + 2ull * ((outCap + 3ull) / 4ull)) * sizeof(uint32_t)));
 	x.capacity = capacity; x.outCapacity = (uint32_t)outCap;
 	return GSP_OK;
 }
@@ -409,7 +418,7 @@ int gsp_exchange_async(gsp_context* ctx)
 		GSP_NCCL(N.AllGather(s.send, s.recv, blockWords, ncclUint32, x.comm, x.stream));
 		if (x.timing) cudaEventRecord(s.t[2], x.stream);
 		launchMergePacked(x.stream, ranks, x.rank, lists, x.capacity, s.recv, s.plan, s.sliceInfo, s.outKeys, s.outPays, s.outRanks,
-			x.outCapacity, false);
+			x.outCapacity, false, x.mergeScratch, c.smCount);
 	}
 	else
 	{
@@ -434,11 +443,9 @@ int gsp_exchange_async(gsp_context* ctx)
 		GSP_NCCL(N.GroupEnd());
 		if (x.timing) cudaEventRecord(s.t[2], x.stream);
 		launchMergePacked(x.stream, ranks, x.rank, lists, x.capacity, s.recv, s.plan, s.sliceInfo, s.outKeys, s.outPays, s.outRanks,
-			x.outCapacity, true);
-		// where my slices start in the merged lists: the lengths of all slices, once around
-		launchSliceLengths(x.stream, lists, s.sliceInfo, s.lengths);
-		GSP_NCCL(N.AllGather(s.lengths, s.lengths + lists, lists, ncclUint32, x.comm, x.stream));
-		launchSliceStarts(x.stream, ranks, x.rank, lists, s.lengths + lists, s.sliceInfo);
+			x.outCapacity, true, x.mergeScratch, c.smCount);
+		// where my slices start in the merged lists: every source put "elements below your range" into its sub-block header
+		launchSliceStarts(x.stream, ranks, lists, s.recv, x.capacity, s.sliceInfo);
 	}
 	if (x.timing) cudaEventRecord(s.t[3], x.stream);
 	const size_t planWords = 2ull * ranks * lists + lists + 2ull * lists * ranks + 8;

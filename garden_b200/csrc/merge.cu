@@ -227,6 +227,218 @@ uint32_t launchMerge(cudaStream_t stream, const MergeArgs& A, uint32_t maxRunLen
 }
 
 
+// ---- pairwise merge tree -------------------------------------------------------------------------------------------------
+// kMergeSlice ranks every element in every other run: ranks - 1 searches per element, which at 8 ranks costs more than the
+// sort that produced the runs. The tree merges the runs of a list two by two with merge-path partitioning instead:
+// ceil(log2 ranks) passes, each reading and writing every element of my slice once (9 bytes in, 9 out), whatever the rank
+// count. Level 1 reads the sub-ranges [lo, hi) of the received runs (the rank is implicit), the later levels read the
+// previous level from a scratch buffer; the groups of a list stay back to back in run order at every level, so the two
+// inputs of a merge are adjacent and its output covers exactly their union — one region per list, the same in the two
+// scratch buffers and in the final output. Ties go to the lower group (lower ranks hold lower global entity indices).
+constexpr uint32_t kTreeThreads = 256, kTreeItems = 8, kTreeTile = kTreeThreads * kTreeItems, kTreeMaxJobs = 1024;
+
+struct TreeArgs
+{
+	MergeArgs M;
+	const uint32_t* __restrict__ srcKeys;   // previous level (levels > 1)
+	const uint32_t* __restrict__ srcPays;
+	const uint8_t* __restrict__ srcRanks;
+	uint32_t* __restrict__ dstKeys;
+	uint32_t* __restrict__ dstPays;
+	uint8_t* __restrict__ dstRanks;
+	uint32_t half;                          // runs per input group: 1, 2, 4 ...
+};
+
+// Merge path: how many of the first `diag` outputs of merge(a, b) come from a (a wins ties). All 32 lanes call it with the
+// same arguments; 32 probes per round like warpBound.
+__device__ __forceinline__ uint32_t warpMergePath(const uint32_t* __restrict__ a, uint32_t na, const uint32_t* __restrict__ b, uint32_t nb,
+	uint32_t diag)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t lo = diag > nb ? diag - nb : 0u, hi = min(diag, na); // the answer lies in [lo, hi]
+	while (hi - lo > 32)
+	{
+		const uint64_t span = hi - lo;
+		const uint32_t p = lo + (uint32_t)(((uint64_t)(lane + 1) * span) / 33); // lo < p < hi
+		const uint32_t taken = __ballot_sync(0xffffffffu, a[p] <= b[diag - 1 - p]); // a prefix of the lanes
+		const uint32_t t = __popc(taken);
+		const uint32_t pPrev = __shfl_sync(0xffffffffu, p, t ? t - 1 : 0), pNext = __shfl_sync(0xffffffffu, p, t < 32 ? t : 31);
+		if (t) lo = pPrev + 1;
+		if (t < 32) hi = pNext;
+	}
+	const uint32_t i = lo + lane;
+	const uint32_t taken = __ballot_sync(0xffffffffu, i < hi && a[i] <= b[diag - 1 - i]);
+	return lo + __popc(taken);
+}
+
+template<bool kFirst>
+__global__ void __launch_bounds__(kTreeThreads) kMergeTree(const __grid_constant__ TreeArgs T)
+{
+	__shared__ uint32_t sTileStart[kTreeMaxJobs + 1];
+	__shared__ uint32_t sKeys[kTreeTile], sSrc[kTreeTile];
+	__shared__ uint32_t sCut[2];
+	const MergeArgs& A = T.M;
+	const uint32_t ranks = A.ranks, half = T.half, pairs = (ranks + 2 * half - 1) / (2 * half), jobs = A.lists * pairs;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	// tiles of every job (list, pair), then their running sum: the grid is sized for the capacity, the lengths live here
+	for (uint32_t job = threadIdx.x; job < jobs; job += kTreeThreads)
+	{
+		const uint32_t list = job / pairs, a0 = (job % pairs) * 2 * half, a2 = min(a0 + 2 * half, ranks);
+		uint32_t n = 0;
+		for (uint32_t r = a0; r < a2; r++)
+			n += A.bounds[(list * ranks + r) * 2 + 1] - A.bounds[(list * ranks + r) * 2 + 0];
+		sTileStart[job + 1] = (n + kTreeTile - 1) / kTreeTile;
+	}
+	if (threadIdx.x == 0)
+		sTileStart[0] = 0;
+	__syncthreads();
+	if (warp == 0)
+	{
+		uint32_t running = 0;
+		for (uint32_t base = 0; base < jobs; base += 32)
+		{
+			uint32_t v = base + lane < jobs ? sTileStart[base + lane + 1] : 0u;
+			#pragma unroll
+			for (uint32_t o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t up = __shfl_up_sync(0xffffffffu, v, o);
+				if (lane >= o) v += up;
+			}
+			if (base + lane < jobs)
+				sTileStart[base + lane + 1] = running + v;
+			running += __shfl_sync(0xffffffffu, v, 31);
+		}
+	}
+	__syncthreads();
+	const uint32_t tiles = sTileStart[jobs];
+
+	for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+	{
+		uint32_t job = 0;
+		{
+			uint32_t lo = 0, hi = jobs; // first job whose tiles end beyond `tile`
+			while (lo < hi)
+			{
+				const uint32_t mid = (lo + hi) >> 1;
+				if (sTileStart[mid + 1] <= tile) lo = mid + 1; else hi = mid;
+			}
+			job = lo;
+		}
+		const uint32_t list = job / pairs, a0 = (job % pairs) * 2 * half, a1 = min(a0 + half, ranks), a2 = min(a0 + 2 * half, ranks);
+		// lengths of the runs before / in the two groups (every warp computes them: 32 runs at most)
+		uint32_t before = 0, nA = 0, nB = 0;
+		{
+			const uint32_t n = lane < ranks ? A.bounds[(list * ranks + lane) * 2 + 1] - A.bounds[(list * ranks + lane) * 2 + 0] : 0u;
+			before = lane < a0 ? n : 0u; nA = lane >= a0 && lane < a1 ? n : 0u; nB = lane >= a1 && lane < a2 ? n : 0u;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+			{
+				before += __shfl_xor_sync(0xffffffffu, before, o);
+				nA += __shfl_xor_sync(0xffffffffu, nA, o);
+				nB += __shfl_xor_sync(0xffffffffu, nB, o);
+			}
+		}
+		const uint32_t region = A.outOffsets[list] + before;
+		const uint32_t *kA, *kB, *pA, *pB;
+		const uint8_t *rA = nullptr, *rB = nullptr;
+		if (kFirst)
+		{
+			const size_t atA = (size_t)a0 * A.rankStride + A.offsets[a0 * A.lists + list] + A.bounds[(list * ranks + a0) * 2 + 0];
+			kA = A.keys + atA; pA = A.payloads + atA;
+			kB = kA; pB = pA;
+			if (a1 < a2)
+			{
+				const size_t atB = (size_t)a1 * A.rankStride + A.offsets[a1 * A.lists + list] + A.bounds[(list * ranks + a1) * 2 + 0];
+				kB = A.keys + atB; pB = A.payloads + atB;
+			}
+		}
+		else
+		{
+			kA = T.srcKeys + region; pA = T.srcPays + region; rA = T.srcRanks + region;
+			kB = kA + nA; pB = pA + nA; rB = rA + nA;
+		}
+		const uint32_t d0 = (tile - sTileStart[job]) * kTreeTile, d1 = min(d0 + kTreeTile, nA + nB);
+		if (warp < 2)
+		{
+			const uint32_t cut = warpMergePath(kA, nA, kB, nB, warp ? d1 : d0);
+			if (lane == 0)
+				sCut[warp] = cut;
+		}
+		__syncthreads();
+		const uint32_t i0 = sCut[0], i1 = sCut[1], j0 = d0 - i0, na = i1 - i0, nb = (d1 - i1) - j0, n = na + nb;
+		for (uint32_t o = threadIdx.x; o < n; o += kTreeThreads)
+			sKeys[o] = o < na ? kA[i0 + o] : kB[j0 + (o - na)];
+		__syncthreads();
+		{
+			// my kTreeItems outputs start at diagonal d of the staged pair
+			const uint32_t d = min(threadIdx.x * kTreeItems, n);
+			uint32_t lo = d > nb ? d - nb : 0u, hi = min(d, na);
+			while (lo < hi)
+			{
+				const uint32_t mid = (lo + hi) >> 1;
+				if (sKeys[mid] <= sKeys[na + (d - 1 - mid)]) lo = mid + 1; else hi = mid;
+			}
+			uint32_t ai = lo, bi = d - lo;
+			uint32_t ka = ai < na ? sKeys[ai] : 0u, kb = bi < nb ? sKeys[na + bi] : 0u;
+			#pragma unroll
+			for (uint32_t u = 0; u < kTreeItems; u++)
+			{
+				if (d + u < n)
+				{
+					const bool takeA = bi >= nb || (ai < na && ka <= kb);
+					sSrc[d + u] = takeA ? ai : (0x80000000u | bi);
+					if (takeA) { ai++; ka = ai < na ? sKeys[ai] : 0u; }
+					else { bi++; kb = bi < nb ? sKeys[na + bi] : 0u; }
+				}
+			}
+		}
+		__syncthreads();
+		for (uint32_t o = threadIdx.x; o < n; o += kTreeThreads)
+		{
+			const uint32_t src = sSrc[o], fromB = src >> 31, idx = src & 0x7FFFFFFFu;
+			const uint32_t g = fromB ? j0 + idx : i0 + idx;
+			const uint32_t at = region + d0 + o;
+			T.dstKeys[at] = sKeys[fromB ? na + idx : idx];
+			T.dstPays[at] = fromB ? pB[g] : pA[g];
+			T.dstRanks[at] = kFirst ? (uint8_t)(fromB ? a1 : a0) : (fromB ? rB[g] : rA[g]);
+		}
+		__syncthreads(); // the next tile reuses the shared arrays
+	}
+}
+
+// scratch words of the tree for an output of outCapacity elements: 2 x (keys | payloads | ranks)
+static inline size_t mergeTreeScratchWords(uint32_t outCapacity)
+{
+	return 4ull * outCapacity + 2ull * ((outCapacity + 3ull) / 4ull);
+}
+
+uint32_t launchMergeTree(cudaStream_t stream, const MergeArgs& A, uint32_t outCapacity, uint32_t* scratch, uint32_t smCount)
+{
+	if (A.lists == 0 || A.ranks == 0)
+		return 0;
+	kMergeBounds<<<A.lists, 32 * A.ranks, 0, stream>>>(A);
+	uint32_t levels = 1;
+	while ((1u << levels) < A.ranks) levels++;
+	uint32_t* tmpK[2] = { scratch, scratch + 2ull * outCapacity };
+	uint32_t* tmpP[2] = { scratch + outCapacity, scratch + 3ull * outCapacity };
+	uint8_t* tmpR[2] = { (uint8_t*)(scratch + 4ull * outCapacity), (uint8_t*)(scratch + 4ull * outCapacity + (outCapacity + 3ull) / 4ull) };
+	const uint32_t worstTiles = outCapacity / kTreeTile + A.lists * ((A.ranks + 1) / 2) + 1;
+	const uint32_t blocks = std::max(1u, std::min(worstTiles, smCount * 8u));
+	for (uint32_t lv = 1; lv <= levels; lv++)
+	{
+		TreeArgs T;
+		T.M = A; T.half = 1u << (lv - 1);
+		T.srcKeys = tmpK[(lv - 1) & 1]; T.srcPays = tmpP[(lv - 1) & 1]; T.srcRanks = tmpR[(lv - 1) & 1];
+		const bool last = lv == levels;
+		T.dstKeys = last ? A.outKeys : tmpK[lv & 1]; T.dstPays = last ? A.outPayloads : tmpP[lv & 1]; T.dstRanks = last ? A.outRanks : tmpR[lv & 1];
+		if (lv == 1) kMergeTree<true><<<blocks, kTreeThreads, 0, stream>>>(T);
+		else kMergeTree<false><<<blocks, kTreeThreads, 0, stream>>>(T);
+	}
+	return 1 + levels;
+}
+
+
 // ---- host-synchronisation-free exchange ---------------------------------------------------------------------------------
 // The per-list lengths only exist on the device when the frame has just been enqueued, so the whole exchange is laid out
 // around a fixed-capacity BLOCK per rank that carries its own description:
@@ -412,7 +624,7 @@ namespace gsp
 // plan + bounds + merge of `ranks` packed blocks (block r at r * (kExHeaderWords + 2 * capacityElems) words)
 uint32_t launchMergePacked(cudaStream_t stream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
 	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPays, uint8_t* dOutRanks,
-	uint32_t outCapacity, bool preSplit)
+	uint32_t outCapacity, bool preSplit, uint32_t* dTreeScratch, uint32_t smCount)
 {
 	const uint32_t blockWords = kExHeaderWords + 2u * capacityElems;
 	kMergePlan<<<1, 32, 0, stream>>>(dGathered, blockWords, ranks, lists, outCapacity, dPlan);
@@ -422,6 +634,8 @@ uint32_t launchMergePacked(cudaStream_t stream, uint32_t ranks, uint32_t myRank,
 	A.outOffsets = dPlan + 2 * ranks * lists; A.bounds = dPlan + 2 * ranks * lists + lists;
 	A.sliceInfo = dSliceInfo; A.outKeys = dOutKeys; A.outPayloads = dOutPays; A.outRanks = dOutRanks;
 	A.rankStride = blockWords; A.ranks = ranks; A.lists = lists; A.myRank = myRank; A.preSplit = preSplit ? 1u : 0u;
+	if (dTreeScratch && lists * ((ranks + 1) / 2) <= kTreeMaxJobs)
+		return 1 + launchMergeTree(stream, A, outCapacity, dTreeScratch, smCount);
 	// (pre-split runs are merged whole: size the grid for a full block per run)
 	return 1 + launchMerge(stream, A, preSplit ? (uint32_t)std::min<uint64_t>((uint64_t)capacityElems * ranks, 0xFFFFFFFFull) : capacityElems);
 }
@@ -545,7 +759,7 @@ __global__ void __launch_bounds__(256) kPackByDestination(const __grid_constant_
 	__syncthreads();
 	if (blockIdx.x == 0)
 	{
-		// headers: { magic, lists, total, capacity, overflow, 0, 0, 0, count[lists] }
+		// headers: { magic, lists, total, capacity, overflow, 0, 0, 0, count[lists], before[lists] }
 		for (uint32_t d = 0; d < A.ranks; d++)
 		{
 			const bool overflow = sTotal[d] > A.capacity;
@@ -560,6 +774,8 @@ __global__ void __launch_bounds__(256) kPackByDestination(const __grid_constant_
 				else if (i == 4) w = overflow ? 1u : 0u;
 				else if (i >= kExHeaderFixed && i < kExHeaderFixed + A.lists && !overflow)
 					w = A.bounds[(i - kExHeaderFixed) * (A.ranks + 1) + d + 1] - A.bounds[(i - kExHeaderFixed) * (A.ranks + 1) + d];
+				else if (i >= kExHeaderFixed + A.lists && i < kExHeaderFixed + 2 * A.lists)
+					w = A.bounds[(i - kExHeaderFixed - A.lists) * (A.ranks + 1) + d]; // elements of my run BEFORE d's key range
 				h[i] = w;
 			}
 		}
@@ -591,21 +807,17 @@ __global__ void __launch_bounds__(256) kPackByDestination(const __grid_constant_
 	}
 }
 
-__global__ void kSliceLengths(uint32_t lists, const uint32_t* __restrict__ sliceInfo, uint32_t* __restrict__ lengths)
-{
-	const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-	if (l < lists)
-		lengths[l] = sliceInfo[l * 2 + 1];
-}
-__global__ void kSliceStarts(uint32_t ranks, uint32_t myRank, uint32_t lists, const uint32_t* __restrict__ gathered,
+// Where my slice of every list starts in the merged list: the elements every rank holds below my key range. Each source
+// wrote that number into the header of the sub-block it sent me, so no further exchange is needed.
+__global__ void kSliceStarts(uint32_t ranks, uint32_t lists, const uint32_t* __restrict__ received, size_t blockWords,
 	uint32_t* __restrict__ sliceInfo)
 {
 	const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
 	if (l >= lists)
 		return;
 	uint32_t start = 0;
-	for (uint32_t r = 0; r < myRank; r++)
-		start += gathered[r * lists + l];
+	for (uint32_t r = 0; r < ranks; r++)
+		start += received[r * blockWords + kExHeaderFixed + lists + l];
 	sliceInfo[l * 2 + 0] = start;
 }
 
@@ -629,15 +841,10 @@ uint32_t launchSplitAndPack(Context& c, cudaStream_t stream, uint32_t ranks, con
 	kPackByDestination<<<c.smCount * 4, 256, 0, stream>>>(P);
 	return 2;
 }
-uint32_t launchSliceLengths(cudaStream_t stream, uint32_t lists, const uint32_t* dSliceInfo, uint32_t* dLengths)
-{
-	kSliceLengths<<<(lists + 127) / 128, 128, 0, stream>>>(lists, dSliceInfo, dLengths);
-	return 1;
-}
-uint32_t launchSliceStarts(cudaStream_t stream, uint32_t ranks, uint32_t myRank, uint32_t lists, const uint32_t* dGatheredLengths,
+uint32_t launchSliceStarts(cudaStream_t stream, uint32_t ranks, uint32_t lists, const uint32_t* dReceived, uint32_t capacityPerDest,
 	uint32_t* dSliceInfo)
 {
-	kSliceStarts<<<(lists + 127) / 128, 128, 0, stream>>>(ranks, myRank, lists, dGatheredLengths, dSliceInfo);
+	kSliceStarts<<<(lists + 127) / 128, 128, 0, stream>>>(ranks, lists, dReceived, kExHeaderWords + 2ull * capacityPerDest, dSliceInfo);
 	return 1;
 }
 } // namespace gsp
@@ -650,6 +857,26 @@ extern "C" int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint3
 		!dOutKeys || !dOutPayloads || !dOutRanks)
 		return GSP_ERR_INVALID;
 	gsp::launchMergePacked((cudaStream_t)cudaStream, ranks, myRank, lists, capacityElems, dGathered, dPlan, dSliceInfo, dOutKeys,
-		dOutPayloads, dOutRanks, outCapacity, false);
+		dOutPayloads, dOutRanks, outCapacity, false, nullptr, 0);
+	return cudaGetLastError() == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
+}
+
+extern "C" uint64_t gsp_merge_tree_scratch_words(uint32_t outCapacity)
+{
+	return gsp::mergeTreeScratchWords(outCapacity);
+}
+
+extern "C" int gsp_merge_gathered_packed_tree(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
+	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
+	uint8_t* dOutRanks, uint32_t outCapacity, uint32_t* dScratch)
+{
+	if (ranks == 0 || ranks > 32 || myRank >= ranks || lists == 0 || lists > kExMaxLists || !dGathered || !dPlan || !dSliceInfo ||
+		!dOutKeys || !dOutPayloads || !dOutRanks || !dScratch || lists * ((ranks + 1) / 2) > 1024u)
+		return GSP_ERR_INVALID;
+	int device = 0, sms = 148;
+	cudaGetDevice(&device);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	gsp::launchMergePacked((cudaStream_t)cudaStream, ranks, myRank, lists, capacityElems, dGathered, dPlan, dSliceInfo, dOutKeys,
+		dOutPayloads, dOutRanks, outCapacity, false, dScratch, (uint32_t)sms);
 	return cudaGetLastError() == cudaSuccess ? GSP_OK : GSP_ERR_CUDA;
 }

@@ -183,6 +183,13 @@ int gsp_export_runs_packed(gsp_context* ctx, uint32_t* dBlock, uint32_t capacity
 int gsp_merge_gathered_packed(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
 	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
 	uint8_t* dOutRanks, uint32_t outCapacity);
+/* The same merge as a pairwise merge-path tree (ceil(log2 ranks) passes over my slice instead of ranks - 1 searches per
+ * element; what gsp_exchange_async uses). dScratch = gsp_merge_tree_scratch_words(outCapacity) 32-bit words. Refused
+ * (GSP_ERR_INVALID) when lists * ceil(ranks / 2) exceeds 1024. */
+uint64_t gsp_merge_tree_scratch_words(uint32_t outCapacity);
+int gsp_merge_gathered_packed_tree(void* cudaStream, uint32_t ranks, uint32_t myRank, uint32_t lists, uint32_t capacityElems,
+	const uint32_t* dGathered, uint32_t* dPlan, uint32_t* dSliceInfo, uint32_t* dOutKeys, uint32_t* dOutPayloads,
+	uint8_t* dOutRanks, uint32_t outCapacity, uint32_t* dScratch);
 
 /* ---- the same exchange with NCCL inside the library: one context per GPU, any host language ------------------------------------
  * ("one context may drive 1-8 GPUs" — here: n contexts, one per device, joined by one communicator.)

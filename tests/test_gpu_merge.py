@@ -117,8 +117,8 @@ def _shards(whole, ranks, chains, depth):
     return out, starts
 
 
-@pytest.mark.parametrize("ranks", [2, 4, 8])
-def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks):
+@pytest.mark.parametrize("ranks,tree", [(2, False), (4, False), (8, False), (1, True), (2, True), (3, True), (4, True), (5, True), (8, True)])
+def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks, tree):
     """The host-synchronisation-free exchange (gsp_export_runs_packed -> [all-gather] -> gsp_merge_gathered_packed):
     blocks are exported right after gsp_run_async (no gsp_sync), laid out as the all-gather would, merged per rank, and
     checked against the numpy merge and against a single sort of the whole scene. Then the overflow protocol."""
@@ -164,8 +164,13 @@ def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks):
         out_k = torch.zeros(total, dtype=torch.int32, device="cuda"); out_p = torch.zeros_like(out_k)
         out_r = torch.zeros(total, dtype=torch.uint8, device="cuda")
         sinfo = torch.zeros(lists * 2, dtype=torch.int32, device="cuda")
-        rc = lib.gsp_merge_gathered_packed(0, ranks, me, lists, cap, gathered.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
-                                           out_k.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total)
+        if tree:  # the pairwise merge-path tree gsp_exchange_async uses; scratch poisoned so stale reads would show
+            scratch = torch.full((int(lib.gsp_merge_tree_scratch_words(total)),), -1, dtype=torch.int32, device="cuda")
+            rc = lib.gsp_merge_gathered_packed_tree(0, ranks, me, lists, cap, gathered.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
+                                                    out_k.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total, scratch.data_ptr())
+        else:
+            rc = lib.gsp_merge_gathered_packed(0, ranks, me, lists, cap, gathered.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
+                                               out_k.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total)
         assert rc == 0
         torch.cuda.synchronize()
         pl = plan.cpu().numpy().view(np.uint32)
@@ -203,8 +208,13 @@ def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks):
     sentinel = torch.full((total,), 0x5a5a5a5a, dtype=torch.int32, device="cuda")
     out_p = sentinel.clone(); out_r = torch.zeros(total, dtype=torch.uint8, device="cuda")
     sinfo = torch.zeros(lists * 2, dtype=torch.int32, device="cuda")
-    rc = lib.gsp_merge_gathered_packed(0, ranks, 0, lists, small, g2.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
-                                       sentinel.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total)
+    if tree:
+        scratch = torch.zeros(int(lib.gsp_merge_tree_scratch_words(total)), dtype=torch.int32, device="cuda")
+        rc = lib.gsp_merge_gathered_packed_tree(0, ranks, 0, lists, small, g2.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
+                                                sentinel.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total, scratch.data_ptr())
+    else:
+        rc = lib.gsp_merge_gathered_packed(0, ranks, 0, lists, small, g2.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
+                                           sentinel.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total)
     assert rc == 0
     sp.sync()
     torch.cuda.synchronize()
@@ -214,3 +224,65 @@ def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks):
     assert bool((sentinel == 0x5a5a5a5a).all()), "nothing may be merged from an overflowed exchange"
     assert int(sinfo.cpu().numpy().reshape(lists, 2)[:, 1].sum()) == 0
     sp.close()
+
+
+@pytest.mark.parametrize("ranks,key_bits", [(2, 32), (3, 6), (4, 20), (7, 3), (8, 32), (16, 10)])
+def test_merge_tree_synthetic_runs(sceneprep_lib, ranks, key_bits):
+    """The merge-path tree on hand-made blocks: runs of very different lengths (some empty, some spanning many 2048-element
+    tiles), few distinct keys (ties decide by rank, then by position in the run) or 32-bit keys. Every rank's slice has to
+    equal the numpy merge, and the slices together have to tile every list."""
+    import torch
+    from garden_b200.binding import load_library
+    lib = load_library()
+    rng = np.random.default_rng(1000 * ranks + key_bits)
+    lists = 3
+    lengths = rng.integers(0, 60000, size=(ranks, lists))
+    lengths[rng.integers(0, ranks), 0] = 0            # an empty run
+    lengths[:, 2] = rng.integers(0, 40, size=ranks)   # a list shorter than one tile
+    if ranks >= 3:
+        lengths[1, 1] = 150000                        # one rank dominates a list
+    cap = int(lengths.sum(axis=1).max()) + 17
+    words = lib.gsp_exchange_block_words(cap)
+    blocks = np.zeros((ranks, words), np.uint32)
+    runs = [[None] * lists for _ in range(ranks)]
+    for r in range(ranks):
+        blocks[r, :5] = (0x47535031, lists, int(lengths[r].sum()), cap, 0)
+        at = 0
+        for l in range(lists):
+            n = int(lengths[r, l])
+            k = np.sort(rng.integers(0, 1 << key_bits, size=n, dtype=np.uint64).astype(np.uint32))
+            p = rng.integers(0, 1 << 28, size=n, dtype=np.uint64).astype(np.uint32)
+            p = p[np.lexsort((p, k))]  # runs are tie-ordered by payload, as the stable device sort leaves them
+            blocks[r, 8 + l] = n
+            blocks[r, 256 + at:256 + at + n] = k
+            blocks[r, 256 + cap + at:256 + cap + at + n] = p
+            runs[r][l] = (k, p)
+            at += n
+    total = int(lengths.sum())
+    gathered = torch.from_numpy(blocks.view(np.int32).reshape(-1)).cuda()
+    plan = torch.zeros(lib.gsp_merge_plan_words(ranks, lists), dtype=torch.int32, device="cuda")
+    out_offsets = np.concatenate([[0], np.cumsum(lengths.sum(axis=0))[:-1]])
+    covered = np.zeros(total, bool)
+    for me in range(ranks):
+        out_k = torch.full((total,), -1, dtype=torch.int32, device="cuda"); out_p = out_k.clone()
+        out_r = torch.full((total,), 255, dtype=torch.uint8, device="cuda")
+        sinfo = torch.zeros(lists * 2, dtype=torch.int32, device="cuda")
+        scratch = torch.full((int(lib.gsp_merge_tree_scratch_words(total)),), -1, dtype=torch.int32, device="cuda")
+        rc = lib.gsp_merge_gathered_packed_tree(0, ranks, me, lists, cap, gathered.data_ptr(), plan.data_ptr(), sinfo.data_ptr(),
+                                                out_k.data_ptr(), out_p.data_ptr(), out_r.data_ptr(), total, scratch.data_ptr())
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert plan.cpu().numpy().view(np.uint32)[-8] == 0
+        info = sinfo.cpu().numpy().reshape(lists, 2)
+        ok, op, orr = out_k.cpu().numpy().view(np.uint32), out_p.cpu().numpy().view(np.uint32), out_r.cpu().numpy()
+        for l in range(lists):
+            ek, ep, er, estart = merge_reference([runs[r][l][0] for r in range(ranks)], [runs[r][l][1] for r in range(ranks)], my_rank=me)
+            start, length = int(info[l, 0]), int(info[l, 1])
+            assert (start, length) == (estart, ek.size), f"rank {me} list {l}: slice bounds"
+            o = int(out_offsets[l])
+            assert np.array_equal(ok[o:o + length], ek), f"rank {me} list {l}: keys"
+            assert np.array_equal(op[o:o + length], ep), f"rank {me} list {l}: payloads"
+            assert np.array_equal(orr[o:o + length], er), f"rank {me} list {l}: ranks"
+            assert not covered[o + start:o + start + length].any()
+            covered[o + start:o + start + length] = True
+    assert covered.all()
