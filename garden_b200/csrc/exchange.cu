@@ -11,7 +11,9 @@
 //   allgather  every rank receives every run (one ncclAllGather of equal blocks) and cuts out its key range itself;
 //   alltoall   the runs are cut by common splitters BEFORE they travel: a small all-gather of samples gives every rank the
 //              same weighted quantiles, each rank packs one sub-block per destination, grouped ncclSend/ncclRecv move them,
-//              and a rank receives only what it merges: 1/ranks of the all-gather's volume, 1/ranks of the merge windows.
+//              and a rank receives only what it merges: 1/ranks of the all-gather's volume. Sub-block headers also carry
+//              "elements of the sender's run below your key range", whose sum is where the slice starts in the merged list.
+// The merge is a pairwise merge-path tree (merge.cu: kMergeTree; GSP_MERGE=slice selects round 1's rank-in-every-run merge).
 // The block capacity is speculative: an overflow is flagged in the header and in the plan flags, nothing is merged for
 // that frame, and the host — which reads the flags from pinned memory — grows the blocks and repeats the frame.
 #include "sceneprep_internal.h"
@@ -90,7 +92,6 @@ struct ExchangeSet
 	uint32_t* outKeys = nullptr; uint32_t* outPays = nullptr; uint8_t* outRanks = nullptr;
 	uint32_t* samples = nullptr;    // alltoall: [lists][kExSampleWords] mine, then [ranks][lists][kExSampleWords] gathered
 	uint32_t* splitters = nullptr;  // alltoall: [lists][ranks - 1] common splitters, then per-rank scratch
-	uint32_t* lengths = nullptr;    // alltoall: [lists] my slice lengths, then [ranks][lists] gathered
 	uint32_t* hFlags = nullptr;     // pinned: the 8 plan flags of the frame
 	cudaEvent_t exported = nullptr, done = nullptr;
 	cudaEvent_t t[4] = {};          // optional timing: export | collective | merge
@@ -158,8 +159,8 @@ static void freeSets(Exchange& x)
 	for (auto& s : x.sets)
 	{
 		cudaFree(s.send); cudaFree(s.recv); cudaFree(s.plan); cudaFree(s.sliceInfo); cudaFree(s.outKeys); cudaFree(s.outPays);
-		cudaFree(s.outRanks); cudaFree(s.samples); cudaFree(s.splitters); cudaFree(s.lengths); cudaFreeHost(s.hFlags);
-		s.send = s.recv = s.plan = s.sliceInfo = s.outKeys = s.outPays = s.samples = s.splitters = s.lengths = s.hFlags = nullptr;
+		cudaFree(s.outRanks); cudaFree(s.samples); cudaFree(s.splitters); cudaFreeHost(s.hFlags);
+		s.send = s.recv = s.plan = s.sliceInfo = s.outKeys = s.outPays = s.samples = s.splitters = s.hFlags = nullptr;
 		s.outRanks = nullptr;
 		s.used = s.pending = false;
 	}
@@ -247,7 +248,6 @@ static int allocateSets(Context& c, uint32_t capacity)
 		GSP_CUDA(cudaMalloc((void**)&s.outRanks, outCap));
 		GSP_CUDA(cudaMalloc((void**)&s.samples, (size_t)(ranks + 1) * lists * kExSampleWords * sizeof(uint32_t)));
 		GSP_CUDA(cudaMalloc((void**)&s.splitters, (size_t)lists * (ranks + 1) * 2 * sizeof(uint32_t)));
-		GSP_CUDA(cudaMalloc((void**)&s.lengths, (size_t)(ranks + 1) * lists * sizeof(uint32_t)));
 		GSP_CUDA(cudaMallocHost((void**)&s.hFlags, 8 * sizeof(uint32_t)));
 		memset(s.hFlags, 0, 8 * sizeof(uint32_t));
 	}

@@ -210,21 +210,20 @@ def _gloo_alltoall_worker(rank, world, port, out_dir):
         sp = common_splitters(samples[:, l, :])
         b = split_bounds(keys[l], sp)
         for d in range(world):
-            pieces[d][l] = (keys[l][b[d]:b[d + 1]], pays[l][b[d]:b[d + 1]])
+            # what a sub-block carries: keys, payloads and "elements of my run below your key range" (kPackByDestination's header)
+            pieces[d][l] = (keys[l][b[d]:b[d + 1]], pays[l][b[d]:b[d + 1]], int(b[d]))
     received = [None] * world
     # (gloo has no all_to_all: the object channel stands in for ncclSend / ncclRecv)
     everyone = [None] * world
     dist.all_gather_object(everyone, pieces)
     for src in range(world):
         received[src] = everyone[src][rank]
-    lengths = np.zeros(lists, np.int64)
+    start = np.zeros(lists, np.int64)
     for l in range(lists):
         k, p, s = merge_reference([received[src][l][0] for src in range(world)], [received[src][l][1] for src in range(world)])
         out[f"k{l}"], out[f"p{l}"], out[f"s{l}"] = k, p, s
-        lengths[l] = k.size
-    all_len = [None] * world
-    dist.all_gather_object(all_len, lengths)
-    out["start"] = np.sum(np.stack(all_len)[:rank], axis=0) if rank else np.zeros(lists, np.int64)
+        start[l] = sum(received[src][l][2] for src in range(world))  # kSliceStarts: no further collective
+    out["start"] = start
     np.savez(os.path.join(out_dir, f"a{rank}.npz"), **out)
     dist.barrier()
     dist.destroy_process_group()
