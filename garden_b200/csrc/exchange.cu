@@ -252,7 +252,7 @@ static int allocateSets(Context& c, uint32_t capacity)
 		memset(s.hFlags, 0, 8 * sizeof(uint32_t));
 	}
 	if (x.treeMerge)
-		GSP_CUDA(cudaMalloc((void**)&x.mergeScratch, (4ull * outCap + 2ull * ((outCap + 3ull) / 4ull)) * sizeof(uint32_t)));
+		GSP_CUDA(cudaMalloc((void**)&x.mergeScratch, gsp_merge_tree_scratch_words((uint32_t)outCap) * sizeof(uint32_t)));
 	x.capacity = capacity; x.outCapacity = (uint32_t)outCap;
 	return GSP_OK;
 }

@@ -236,6 +236,10 @@ uint32_t launchMerge(cudaStream_t stream, const MergeArgs& A, uint32_t maxRunLen
 // inputs of a merge are adjacent and its output covers exactly their union — one region per list, the same in the two
 // scratch buffers and in the final output. Ties go to the lower group (lower ranks hold lower global entity indices).
 constexpr uint32_t kTreeThreads = 256, kTreeItems = 8, kTreeTile = kTreeThreads * kTreeItems, kTreeMaxJobs = 1024;
+// shared arrays skip one word in 33: a thread's outputs are kTreeItems apart from its neighbour's, which would put
+// every fourth lane into the same bank
+constexpr uint32_t kTreePadded = kTreeTile + kTreeTile / 32, kTreeBlocksPerSM = 4;
+__device__ __forceinline__ uint32_t treePad(uint32_t i) { return i + (i >> 5); }
 
 struct TreeArgs
 {
@@ -271,17 +275,21 @@ __device__ __forceinline__ uint32_t warpMergePath(const uint32_t* __restrict__ a
 	return lo + __popc(taken);
 }
 
+// One launch per level cuts the level's merges into tiles: the tiles of every (list, pair) job are numbered through, two
+// warps per tile search the two diagonals that bound it, and a 32-byte record tells kMergeTree all it needs — the merge
+// kernel itself then has no dependent global searches left, only streaming loads and stores.
+//   record = { dst, na, nb, rankA | rankB << 8, srcA, 0, srcB, 0 }   (element indices into the level's key array)
+constexpr uint32_t kTreeRecordWords = 8, kPartitionTilesPerBlock = kTreeThreads / 64;
 template<bool kFirst>
-__global__ void __launch_bounds__(kTreeThreads) kMergeTree(const __grid_constant__ TreeArgs T)
+__global__ void __launch_bounds__(kTreeThreads) kTreePartition(const __grid_constant__ TreeArgs T, uint32_t* __restrict__ records /* [0] = tiles, records from word 8 */)
 {
 	__shared__ uint32_t sTileStart[kTreeMaxJobs + 1];
-	__shared__ uint32_t sKeys[kTreeTile], sSrc[kTreeTile];
-	__shared__ uint32_t sCut[2];
+	__shared__ uint32_t sCut[kTreeThreads / 32];
 	const MergeArgs& A = T.M;
 	const uint32_t ranks = A.ranks, half = T.half, pairs = (ranks + 2 * half - 1) / (2 * half), jobs = A.lists * pairs;
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-	// tiles of every job (list, pair), then their running sum: the grid is sized for the capacity, the lengths live here
+	// tiles of every job (list, pair), then their running sum
 	for (uint32_t job = threadIdx.x; job < jobs; job += kTreeThreads)
 	{
 		const uint32_t list = job / pairs, a0 = (job % pairs) * 2 * half, a2 = min(a0 + 2 * half, ranks);
@@ -312,8 +320,14 @@ __global__ void __launch_bounds__(kTreeThreads) kMergeTree(const __grid_constant
 	}
 	__syncthreads();
 	const uint32_t tiles = sTileStart[jobs];
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		records[0] = tiles;
 
-	for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+	const uint32_t tile = blockIdx.x * kPartitionTilesPerBlock + (warp >> 1);
+	const bool live = tile < tiles; // (uniform per warp pair; the barrier below is reached by everyone)
+	uint32_t region = 0, nA = 0, nB = 0, a0 = 0, a1 = 0, d0 = 0, d1 = 0;
+	size_t baseA = 0, baseB = 0;
+	if (live)
 	{
 		uint32_t job = 0;
 		{
@@ -325,9 +339,10 @@ __global__ void __launch_bounds__(kTreeThreads) kMergeTree(const __grid_constant
 			}
 			job = lo;
 		}
-		const uint32_t list = job / pairs, a0 = (job % pairs) * 2 * half, a1 = min(a0 + half, ranks), a2 = min(a0 + 2 * half, ranks);
-		// lengths of the runs before / in the two groups (every warp computes them: 32 runs at most)
-		uint32_t before = 0, nA = 0, nB = 0;
+		const uint32_t list = job / pairs;
+		a0 = (job % pairs) * 2 * half; a1 = min(a0 + half, ranks);
+		const uint32_t a2 = min(a0 + 2 * half, ranks);
+		uint32_t before = 0;
 		{
 			const uint32_t n = lane < ranks ? A.bounds[(list * ranks + lane) * 2 + 1] - A.bounds[(list * ranks + lane) * 2 + 0] : 0u;
 			before = lane < a0 ? n : 0u; nA = lane >= a0 && lane < a1 ? n : 0u; nB = lane >= a1 && lane < a2 ? n : 0u;
@@ -339,36 +354,96 @@ __global__ void __launch_bounds__(kTreeThreads) kMergeTree(const __grid_constant
 				nB += __shfl_xor_sync(0xffffffffu, nB, o);
 			}
 		}
-		const uint32_t region = A.outOffsets[list] + before;
-		const uint32_t *kA, *kB, *pA, *pB;
-		const uint8_t *rA = nullptr, *rB = nullptr;
+		region = A.outOffsets[list] + before;
+		const uint32_t* keys;
 		if (kFirst)
 		{
-			const size_t atA = (size_t)a0 * A.rankStride + A.offsets[a0 * A.lists + list] + A.bounds[(list * ranks + a0) * 2 + 0];
-			kA = A.keys + atA; pA = A.payloads + atA;
-			kB = kA; pB = pA;
+			keys = A.keys;
+			baseA = (size_t)a0 * A.rankStride + A.offsets[a0 * A.lists + list] + A.bounds[(list * ranks + a0) * 2 + 0];
+			baseB = baseA;
 			if (a1 < a2)
-			{
-				const size_t atB = (size_t)a1 * A.rankStride + A.offsets[a1 * A.lists + list] + A.bounds[(list * ranks + a1) * 2 + 0];
-				kB = A.keys + atB; pB = A.payloads + atB;
-			}
+				baseB = (size_t)a1 * A.rankStride + A.offsets[a1 * A.lists + list] + A.bounds[(list * ranks + a1) * 2 + 0];
 		}
 		else
 		{
-			kA = T.srcKeys + region; pA = T.srcPays + region; rA = T.srcRanks + region;
-			kB = kA + nA; pB = pA + nA; rB = rA + nA;
+			keys = T.srcKeys;
+			baseA = region; baseB = (size_t)region + nA;
 		}
-		const uint32_t d0 = (tile - sTileStart[job]) * kTreeTile, d1 = min(d0 + kTreeTile, nA + nB);
-		if (warp < 2)
+		d0 = (tile - sTileStart[job]) * kTreeTile; d1 = min(d0 + kTreeTile, nA + nB);
+		const uint32_t cut = warpMergePath(keys + baseA, nA, keys + baseB, nB, (warp & 1) ? d1 : d0);
+		if (lane == 0)
+			sCut[warp] = cut;
+	}
+	__syncthreads();
+	if (live && !(warp & 1) && lane == 0)
+	{
+		const uint32_t i0 = sCut[warp], i1 = sCut[warp + 1], j0 = d0 - i0;
+		const size_t srcA = baseA + i0, srcB = baseB + j0;
+		uint4* rec = (uint4*)(records + kTreeRecordWords * (1 + (size_t)tile));
+		rec[0] = make_uint4(region + d0, i1 - i0, (d1 - i1) - j0, a0 | a1 << 8);
+		rec[1] = make_uint4((uint32_t)srcA, 0u, (uint32_t)srcB, 0u);
+	}
+}
+
+template<bool kFirst>
+__global__ void __launch_bounds__(kTreeThreads, kTreeBlocksPerSM) kMergeTree(const __grid_constant__ TreeArgs T, const uint32_t* __restrict__ records)
+{
+	__shared__ uint32_t sKeys[kTreePadded], sPays[kTreePadded];
+	__shared__ uint16_t sSrc[kTreePadded];
+	__shared__ uint8_t sRanks[kTreePadded];
+	const uint32_t* __restrict__ keys = kFirst ? T.M.keys : T.srcKeys;
+	const uint32_t* __restrict__ pays = kFirst ? T.M.payloads : T.srcPays;
+	const uint32_t tiles = records[0];
+	// padded positions of what this thread touches: o = threadIdx.x + u * kTreeThreads -> oBase + u * (kTreeThreads + kTreeThreads / 32),
+	// d + u = threadIdx.x * kTreeItems + u -> dBase + u   (kTreeItems divides 32)
+	const uint32_t oBase = treePad(threadIdx.x), dBase = threadIdx.x * kTreeItems + (threadIdx.x * kTreeItems >> 5);
+	constexpr uint32_t oStep = kTreeThreads + kTreeThreads / 32;
+	uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+	if (blockIdx.x < tiles)
+	{
+		r0 = ((const uint4*)(records + kTreeRecordWords * (1 + (size_t)blockIdx.x)))[0];
+		r1 = ((const uint4*)(records + kTreeRecordWords * (1 + (size_t)blockIdx.x)))[1];
+	}
+	for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+	{
+		const uint32_t dst = r0.x, na = r0.y, nb = r0.z, n = na + nb, rankA = r0.w & 255u, rankB = r0.w >> 8;
+		// 32-bit element indices relative to the key array (the launcher refuses layouts beyond 2^32 elements); b's index is
+		// biased by -na so that position o of the staged pair reads index (o < na ? srcA : srcB) + o
+		const uint32_t srcA = r1.x, srcB = r1.z - na;
+		// the next tile's record travels while this one is merged
+		if (tile + gridDim.x < tiles)
 		{
-			const uint32_t cut = warpMergePath(kA, nA, kB, nB, warp ? d1 : d0);
-			if (lane == 0)
-				sCut[warp] = cut;
+			r0 = ((const uint4*)(records + kTreeRecordWords * (1 + (size_t)tile + gridDim.x)))[0];
+			r1 = ((const uint4*)(records + kTreeRecordWords * (1 + (size_t)tile + gridDim.x)))[1];
 		}
-		__syncthreads();
-		const uint32_t i0 = sCut[0], i1 = sCut[1], j0 = d0 - i0, na = i1 - i0, nb = (d1 - i1) - j0, n = na + nb;
-		for (uint32_t o = threadIdx.x; o < n; o += kTreeThreads)
-			sKeys[o] = o < na ? kA[i0 + o] : kB[j0 + (o - na)];
+		// stage both ranges, [a | b] (keys, payloads, source ranks): coalesced, every load of the thread in flight at once
+		{
+			uint32_t k[kTreeItems], q[kTreeItems], r[kTreeItems];
+			#pragma unroll
+			for (uint32_t u = 0; u < kTreeItems; u++)
+			{
+				const uint32_t o = threadIdx.x + u * kTreeThreads;
+				if (o < n)
+				{
+					const bool fromB = o >= na;
+					const uint32_t g = (fromB ? srcB : srcA) + o;
+					k[u] = keys[g];
+					q[u] = pays[g];
+					r[u] = kFirst ? (fromB ? rankB : rankA) : (uint32_t)T.srcRanks[g];
+				}
+			}
+			#pragma unroll
+			for (uint32_t u = 0; u < kTreeItems; u++)
+			{
+				const uint32_t o = threadIdx.x + u * kTreeThreads;
+				if (o < n)
+				{
+					sKeys[oBase + u * oStep] = k[u];
+					sPays[oBase + u * oStep] = q[u];
+					sRanks[oBase + u * oStep] = (uint8_t)r[u];
+				}
+			}
+		}
 		__syncthreads();
 		{
 			// my kTreeItems outputs start at diagonal d of the staged pair
@@ -377,40 +452,51 @@ __global__ void __launch_bounds__(kTreeThreads) kMergeTree(const __grid_constant
 			while (lo < hi)
 			{
 				const uint32_t mid = (lo + hi) >> 1;
-				if (sKeys[mid] <= sKeys[na + (d - 1 - mid)]) lo = mid + 1; else hi = mid;
+				if (sKeys[treePad(mid)] <= sKeys[treePad(na + (d - 1 - mid))]) lo = mid + 1; else hi = mid;
 			}
-			uint32_t ai = lo, bi = d - lo;
-			uint32_t ka = ai < na ? sKeys[ai] : 0u, kb = bi < nb ? sKeys[na + bi] : 0u;
+			uint32_t ai = lo, bi = na + (d - lo); // positions in the staged array
+			bool hasA = ai < na, hasB = bi < n;
+			uint32_t ka = hasA ? sKeys[treePad(ai)] : 0u, kb = hasB ? sKeys[treePad(bi)] : 0u;
+			// (no divergent branches: one shared load per step whichever side advances)
 			#pragma unroll
 			for (uint32_t u = 0; u < kTreeItems; u++)
 			{
+				const bool takeA = !hasB || (hasA && ka <= kb);
+				const uint32_t taken = takeA ? ai : bi, next = taken + 1;
 				if (d + u < n)
-				{
-					const bool takeA = bi >= nb || (ai < na && ka <= kb);
-					sSrc[d + u] = takeA ? ai : (0x80000000u | bi);
-					if (takeA) { ai++; ka = ai < na ? sKeys[ai] : 0u; }
-					else { bi++; kb = bi < nb ? sKeys[na + bi] : 0u; }
-				}
+					sSrc[dBase + u] = (uint16_t)taken;
+				const bool has = next < (takeA ? na : n);
+				const uint32_t v = has ? sKeys[treePad(next)] : 0u;
+				ai = takeA ? next : ai; bi = takeA ? bi : next;
+				ka = takeA ? v : ka; kb = takeA ? kb : v;
+				hasA = takeA ? has : hasA; hasB = takeA ? hasB : has;
 			}
 		}
 		__syncthreads();
-		for (uint32_t o = threadIdx.x; o < n; o += kTreeThreads)
+		#pragma unroll
+		for (uint32_t u = 0; u < kTreeItems; u++)
 		{
-			const uint32_t src = sSrc[o], fromB = src >> 31, idx = src & 0x7FFFFFFFu;
-			const uint32_t g = fromB ? j0 + idx : i0 + idx;
-			const uint32_t at = region + d0 + o;
-			T.dstKeys[at] = sKeys[fromB ? na + idx : idx];
-			T.dstPays[at] = fromB ? pB[g] : pA[g];
-			T.dstRanks[at] = kFirst ? (uint8_t)(fromB ? a1 : a0) : (fromB ? rB[g] : rA[g]);
+			const uint32_t o = threadIdx.x + u * kTreeThreads;
+			if (o < n)
+			{
+				const uint32_t src = treePad(sSrc[oBase + u * oStep]);
+				T.dstKeys[dst + o] = sKeys[src];
+				T.dstPays[dst + o] = sPays[src];
+				T.dstRanks[dst + o] = sRanks[src];
+			}
 		}
 		__syncthreads(); // the next tile reuses the shared arrays
 	}
 }
 
-// scratch words of the tree for an output of outCapacity elements: 2 x (keys | payloads | ranks)
+// scratch words of the tree for an output of outCapacity elements: 2 x (keys | payloads | ranks), then the tile records
+static inline size_t mergeTreeDataWords(uint32_t outCapacity)
+{
+	return (4ull * outCapacity + 2ull * ((outCapacity + 3ull) / 4ull) + 3ull) & ~3ull; // (records are read as uint4)
+}
 static inline size_t mergeTreeScratchWords(uint32_t outCapacity)
 {
-	return 4ull * outCapacity + 2ull * ((outCapacity + 3ull) / 4ull);
+	return mergeTreeDataWords(outCapacity) + kTreeRecordWords * (2ull + outCapacity / kTreeTile + kTreeMaxJobs);
 }
 
 uint32_t launchMergeTree(cudaStream_t stream, const MergeArgs& A, uint32_t outCapacity, uint32_t* scratch, uint32_t smCount)
@@ -423,8 +509,10 @@ uint32_t launchMergeTree(cudaStream_t stream, const MergeArgs& A, uint32_t outCa
 	uint32_t* tmpK[2] = { scratch, scratch + 2ull * outCapacity };
 	uint32_t* tmpP[2] = { scratch + outCapacity, scratch + 3ull * outCapacity };
 	uint8_t* tmpR[2] = { (uint8_t*)(scratch + 4ull * outCapacity), (uint8_t*)(scratch + 4ull * outCapacity + (outCapacity + 3ull) / 4ull) };
+	uint32_t* records = scratch + mergeTreeDataWords(outCapacity);
 	const uint32_t worstTiles = outCapacity / kTreeTile + A.lists * ((A.ranks + 1) / 2) + 1;
-	const uint32_t blocks = std::max(1u, std::min(worstTiles, smCount * 8u));
+	const uint32_t blocks = std::max(1u, std::min(worstTiles, smCount * kTreeBlocksPerSM));
+	const uint32_t partitionBlocks = (worstTiles + kPartitionTilesPerBlock - 1) / kPartitionTilesPerBlock;
 	for (uint32_t lv = 1; lv <= levels; lv++)
 	{
 		TreeArgs T;
@@ -432,10 +520,18 @@ uint32_t launchMergeTree(cudaStream_t stream, const MergeArgs& A, uint32_t outCa
 		T.srcKeys = tmpK[(lv - 1) & 1]; T.srcPays = tmpP[(lv - 1) & 1]; T.srcRanks = tmpR[(lv - 1) & 1];
 		const bool last = lv == levels;
 		T.dstKeys = last ? A.outKeys : tmpK[lv & 1]; T.dstPays = last ? A.outPayloads : tmpP[lv & 1]; T.dstRanks = last ? A.outRanks : tmpR[lv & 1];
-		if (lv == 1) kMergeTree<true><<<blocks, kTreeThreads, 0, stream>>>(T);
-		else kMergeTree<false><<<blocks, kTreeThreads, 0, stream>>>(T);
+		if (lv == 1)
+		{
+			kTreePartition<true><<<partitionBlocks, kTreeThreads, 0, stream>>>(T, records);
+			kMergeTree<true><<<blocks, kTreeThreads, 0, stream>>>(T, records);
+		}
+		else
+		{
+			kTreePartition<false><<<partitionBlocks, kTreeThreads, 0, stream>>>(T, records);
+			kMergeTree<false><<<blocks, kTreeThreads, 0, stream>>>(T, records);
+		}
 	}
-	return 1 + levels;
+	return 1 + 2 * levels;
 }
 
 
@@ -634,7 +730,7 @@ uint32_t launchMergePacked(cudaStream_t stream, uint32_t ranks, uint32_t myRank,
 	A.outOffsets = dPlan + 2 * ranks * lists; A.bounds = dPlan + 2 * ranks * lists + lists;
 	A.sliceInfo = dSliceInfo; A.outKeys = dOutKeys; A.outPayloads = dOutPays; A.outRanks = dOutRanks;
 	A.rankStride = blockWords; A.ranks = ranks; A.lists = lists; A.myRank = myRank; A.preSplit = preSplit ? 1u : 0u;
-	if (dTreeScratch && lists * ((ranks + 1) / 2) <= kTreeMaxJobs)
+	if (dTreeScratch && lists * ((ranks + 1) / 2) <= kTreeMaxJobs && (uint64_t)blockWords * ranks < 0xFFFFFFFFull)
 		return 1 + launchMergeTree(stream, A, outCapacity, dTreeScratch, smCount);
 	// (pre-split runs are merged whole: size the grid for a full block per run)
 	return 1 + launchMerge(stream, A, preSplit ? (uint32_t)std::min<uint64_t>((uint64_t)capacityElems * ranks, 0xFFFFFFFFull) : capacityElems);
