@@ -114,6 +114,51 @@ __device__ __forceinline__ bool boxesCulled(const CullParams& P, float cx, float
 	return outside;
 }
 
+// The prepass' view loop: true if the sphere (c, reach) may touch some enabled view. The box views of the group share the
+// three dot products with their common axes, so each of them costs six comparisons against its own extents
+// (CullParams::boxViewLo / boxViewHi) instead of six plane equations; when every lane of the warp is outside the union of
+// the boxes they are skipped altogether. All lanes of the warp call it (`test` masks lanes that have nothing to test).
+template<uint32_t kViews>
+__device__ __forceinline__ bool sphereMaySurvive(const CullParams& P, bool test, float cx, float cy, float cz, float reach)
+{
+	float rm[3] = { 0.f, 0.f, 0.f }, rp[3] = { 0.f, 0.f, 0.f };
+	bool outsideBoxes = false;
+	if (P.boxMask != 0) // (uniform)
+	{
+		const float r = reach + P.boxSlack;
+		#pragma unroll
+		for (int j = 0; j < 3; j++)
+		{
+			const float t = fmaf(P.boxAxis[j][0], cx, fmaf(P.boxAxis[j][1], cy, P.boxAxis[j][2] * cz));
+			rm[j] = t - r; rp[j] = t + r;
+			outsideBoxes = outsideBoxes | (rm[j] > P.boxHi[j]) | (rp[j] < P.boxLo[j]);
+		}
+	}
+	const uint32_t skipViews = __all_sync(0xffffffffu, outsideBoxes || !test) ? P.boxMask : 0u;
+	bool maybe = false;
+	if (test)
+	{
+		#pragma unroll
+		for (uint32_t v = 0; v < kViews; v++)
+		{
+			if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
+			{
+				const ViewConst& V = P.views[v];
+				bool behind; // false for NaN / infinite bounds in both forms
+				// (no short-circuit evaluation: the lanes of a warp rarely agree, and a chain of predicated compares
+				// is cheaper than the reconvergence of early exits)
+				if ((P.boxMask >> v) & 1u) // (uniform)
+					behind = (rm[0] > P.boxViewHi[v][0]) | (rp[0] < P.boxViewLo[v][0]) | (rm[1] > P.boxViewHi[v][1]) | (rp[1] < P.boxViewLo[v][1]) |
+						(rm[2] > P.boxViewHi[v][2]) | (rp[2] < P.boxViewLo[v][2]);
+				else
+					behind = minPlaneDistance(V, cx, cy, cz) < -(reach + V.slack);
+				maybe = maybe | ((V.enabled != 0) & !behind);
+			}
+		}
+	}
+	return maybe;
+}
+
 // ---- prepass: filter + hierarchical conservative culling + ordered compaction of the survivors ---------------------------
 // In a large scene most entities are outside every view, and the expensive part of the path — the leaf-first product of the
 // parent chain (transform.hpp:197-214) — is only needed for entities that might be visible. The prepass bounds the world box
@@ -258,26 +303,9 @@ __global__ void __launch_bounds__(kPreThreads) kPrepass(const __grid_constant__ 
 		const float cx = rec[k].x - P.cam[0], cy = rec[k].y - P.cam[1], cz = rec[k].z - P.cam[2];
 		const float magnitude = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + u);
 		const float reach = fmaf(magnitude, kBandR, u * 1.0001f);
-		// box views (cascades) are skipped by the whole warp when every lane is certainly outside all of them
-		const bool outsideBoxes = P.boxMask != 0 && boxesCulled(P, cx, cy, cz, reach);
-		const uint32_t skipViews = __all_sync(0xffffffffu, outsideBoxes || !test) ? P.boxMask : 0u;
+		const bool maybe = sphereMaySurvive<kViews>(P, test, cx, cy, cz, reach);
 		if (test)
-		{
-			bool maybe = false;
-			#pragma unroll
-			for (uint32_t v = 0; v < kViews; v++)
-			{
-				if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
-				{
-					const ViewConst& V = P.views[v];
-					const float dmin = minPlaneDistance(V, cx, cy, cz);
-					const bool behind = dmin < -(reach + V.slack); // false for NaN / infinite bounds
-					if (V.enabled && !behind && !(outsideBoxes && ((P.boxMask >> v) & 1u)))
-						maybe = true;
-				}
-			}
 			survive = maybe;
-		}
 		// slots of a block are ordered (round, warp, lane): word k * kPreWarps + warp holds 32 consecutive slots
 		const uint32_t votes = __ballot_sync(0xffffffffu, survive);
 		if (lane == 0)
@@ -319,26 +347,8 @@ __global__ void __launch_bounds__(kPreThreads) kPrepassT(const __grid_constant__
 		const float magnitude = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + u);
 		const float reach = fmaf(magnitude, kBandR, u * 1.0001f);
 		const bool test = live && A.prepassCull != 0;
-		const bool outsideBoxes = P.boxMask != 0 && boxesCulled(P, cx, cy, cz, reach);
-		const uint32_t skipViews = __all_sync(0xffffffffu, outsideBoxes || !test) ? P.boxMask : 0u;
-		bool survive = live;
-		if (test)
-		{
-			bool maybe = false;
-			#pragma unroll
-			for (uint32_t v = 0; v < kViews; v++)
-			{
-				if (v < P.viewCount && !((skipViews >> v) & 1u)) // warp-uniform
-				{
-					const ViewConst& V = P.views[v];
-					const float dmin = minPlaneDistance(V, cx, cy, cz);
-					const bool behind = dmin < -(reach + V.slack);
-					if (V.enabled && !behind && !(outsideBoxes && ((P.boxMask >> v) & 1u)))
-						maybe = true;
-				}
-			}
-			survive = maybe;
-		}
+		const bool maybe = sphereMaySurvive<kViews>(P, test, cx, cy, cz, reach);
+		const bool survive = test ? maybe : live;
 		const uint32_t votes = __ballot_sync(0xffffffffu, survive);
 		if (lane == 0)
 			A.surBits[(size_t)blockIdx.x * kPreWords + k * kPreWarps + warp] = votes;
@@ -1380,6 +1390,7 @@ static void prepareBoxGroup(CullParams& P)
 {
 	P.boxMask = 0; P.boxSlack = 0.0f;
 	double axis[3][3] = {}, glo[3] = {}, ghi[3] = {}, slack = 0.0;
+	bool groupBroken = false;
 	for (uint32_t v = 0; v < P.viewCount; v++)
 	{
 		double n[3][3], lo[3], hi[3];
@@ -1404,7 +1415,17 @@ static void prepareBoxGroup(CullParams& P)
 		}
 		P.boxMask |= 1u << v;
 		slack = std::max(slack, (double)P.views[v].slack);
+		for (int j = 0; j < 3; j++)
+		{
+			// rounded outwards like the union below
+			P.boxViewLo[v][j] = (float)(lo[j] - std::fabs(lo[j]) * 1e-5 - 1e-30);
+			P.boxViewHi[v][j] = (float)(hi[j] + std::fabs(hi[j]) * 1e-5 + 1e-30);
+			if (!std::isfinite(P.boxViewLo[v][j]) || !std::isfinite(P.boxViewHi[v][j]))
+				groupBroken = true;
+		}
 	}
+	if (groupBroken)
+		P.boxMask = 0;
 	if (!P.boxMask)
 		return;
 	for (int j = 0; j < 3; j++)

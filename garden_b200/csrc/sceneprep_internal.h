@@ -127,6 +127,7 @@ struct CullParams
 	float boxAxis[3][3];
 	float boxLo[3], boxHi[3];
 	float boxSlack;
+	float boxViewLo[kMaxViews][3], boxViewHi[kMaxViews][3]; // each group view's own extents along boxAxis (the prepass)
 };
 
 // A segment = one output list of one view: (view, canonical pool). Unsorted buffers own a segment each;

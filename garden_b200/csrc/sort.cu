@@ -74,6 +74,20 @@ __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* sWa
 	return offset + inc - v;
 }
 
+// One step of the peer search: keeps in `peers` the lanes whose digit agrees with mine in the bit `mask`. Four SASS
+// instructions (test, vote, and / and-not under the predicate); the plain C++ form compiled to nine.
+__device__ __forceinline__ uint32_t ballotPeers(uint32_t peers, uint32_t digit, uint32_t mask)
+{
+	asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 v, w;\n\t"
+		"and.b32 v, %1, %2;\n\tsetp.ne.u32 p, v, 0;\n\t"
+		"vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+		"not.b32 w, v;\n\t"
+		"selp.b32 v, v, w, p;\n\t"
+		"and.b32 %0, %0, v;\n\t}"
+		: "+r"(peers) : "r"(digit), "r"(mask));
+	return peers;
+}
+
 constexpr uint32_t kSortBlocksPerSM = kSortItems >= 16 ? 3 : 5; // resident blocks the pass is sized for
 constexpr uint32_t kLookbackBatch = 4; // predecessor tiles inspected per step (independent loads in flight; 16 measured slower, 8 / 4 / 2 within 2 %)
 
@@ -165,10 +179,7 @@ __global__ void __launch_bounds__(kSortThreads, kSortBlocksPerSM) kSortPass(cons
 			{
 				#pragma unroll
 				for (uint32_t b = 0; b < kRadixBits; b++)
-				{
-					const uint32_t vote = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
-					peers &= ((dg >> b) & 1u) ? vote : ~vote;
-				}
+					peers = ballotPeers(peers, dg, 1u << b);
 			}
 			peerMask[i] = peers;
 		}
