@@ -266,14 +266,18 @@ __global__ void __launch_bounds__(kSortThreads, kSortBlocksPerSM) kSortPass(cons
 		__syncthreads();
 		uint32_t* kout = keysOut + seg.offset;
 		uint32_t* pout = payOut + seg.offset;
-		#pragma unroll 4
-		for (uint32_t j = threadIdx.x; j < n; j += kSortThreads)
+		#pragma unroll
+		for (uint32_t u = 0; u < kSortItems; u++)
 		{
-			const uint32_t k = sKeys[j];
-			const uint32_t dg = (k >> shift) & (kRadix - 1);
-			const uint32_t pos = (uint32_t)(sGlobal[dg] + (int32_t)j);
-			kout[pos] = k;
-			pout[pos] = sPay[j];
+			const uint32_t j = threadIdx.x + u * kSortThreads;
+			if (j < n)
+			{
+				const uint32_t k = sKeys[j];
+				const uint32_t dg = (k >> shift) & (kRadix - 1);
+				const uint32_t pos = (uint32_t)(sGlobal[dg] + (int32_t)j);
+				kout[pos] = k;
+				pout[pos] = sPay[j];
+			}
 		}
 	}
 }
