@@ -161,6 +161,9 @@ def pinned_like(arr: np.ndarray):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+REF_BUDGET_S = float(os.environ.get("GSP_REF_BUDGET_S", "240"))  # wall-clock bound of the reference arm's timed frames
+
+
 def reference_engine_run(workload: str, sample_n: int, steps: int, warmup: int, seed: int):
     """Times the reference's own prepareMeshes (oracle/_ref stock build; falls back to the C port) on `sample_n`
     entities of the workload. Returns dict(value, ms_per_step, cores, kind, sample, visible)."""
@@ -171,11 +174,23 @@ def reference_engine_run(workload: str, sample_n: int, steps: int, warmup: int, 
     scene.camera_pos = camera_pos()
     views = frame_views(workload)
     if reflib.ref_available("stock"):
-        with reflib.RefEngine("stock", threads=-1) as ref:
-            ref.load_scene(scene)
-            threads = ref.thread_count
-            ref.time_frames(views, max(warmup, 1))
-            ms, vis = ref.time_frames(views, steps)
+        ms = None
+        while ms is None:
+            with reflib.RefEngine("stock", threads=-1) as ref:
+                ref.load_scene(scene)
+                threads = ref.thread_count
+                warm, _ = ref.time_frames(views, max(warmup, 1))
+                # EXACTLY `steps` timed frames; if that many frames of the whole workload would not end within a few
+                # minutes (REF_BUDGET_S), every step runs on a smaller scene of the same generator instead (the metric
+                # is per entity). One retry at most: the second scene is sized from the first one's measured frame time.
+                need_s = float(np.min(warm)) * 1e-3 * steps
+                if need_s > REF_BUDGET_S and sample_n > 200_000:
+                    chain = scenes.CONFIGS[cfg]["depth"] + 1
+                    sample_n = max(int(sample_n * REF_BUDGET_S / need_s), 200_000) // chain * chain
+                    scene = scenes.config_scene(cfg, n=sample_n, seed=seed)
+                    scene.camera_pos = camera_pos()
+                    continue
+                ms, vis = ref.time_frames(views, steps)
         kind = "reference"
         cores = threads
     else:
@@ -195,7 +210,7 @@ def reference_engine_run(workload: str, sample_n: int, steps: int, warmup: int, 
         kind, cores = "port", 1
     mean_ms = float(np.mean(ms))
     return {"value": sample_n / (mean_ms * 1e-3), "ms_per_step": mean_ms, "best_ms": float(np.min(ms)), "cores": int(cores),
-            "kind": kind, "visible": int(vis[-1]),
+            "kind": kind, "visible": int(vis[-1]), "entities": int(sample_n),
             "sample": f"{sample_n} entities of workload {workload} (same generator, same {views.size} views), "
                       f"{len(ms)} frames, mean"}
 
@@ -204,8 +219,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = args.ref_sample or WORKLOADS[args.workload][1]
-    res = reference_engine_run(args.workload, sample, args.steps, args.warmup, args.seed)
+    whole = WORKLOADS[args.workload][1]
+    res = reference_engine_run(args.workload, args.ref_sample or whole, args.steps, args.warmup, args.seed)
+    sample = res["entities"]
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
@@ -213,8 +229,10 @@ def run_reference_arm(args):
         "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][2]}", "entities_per_gpu": sample,
                    "entities_total": sample, "entities_per_step": sample,
                    "views": int(frame_views(args.workload).size), "visible_total": res["visible"],
-                   "note": "the reference's own prepareMeshes (thread pool on all host cores) over the WHOLE workload, "
-                           "one call per view per step as mesh.cpp:795-847,893-903 does"},
+                   "same_config": sample == whole,
+                   "note": ("the reference's own prepareMeshes (thread pool on all host cores) over "
+                            + ("the WHOLE workload" if sample == whole else f"a {sample}-entity sample of the workload (time budget {REF_BUDGET_S:.0f} s for {args.steps} steps)")
+                            + ", one call per view per step as mesh.cpp:795-847,893-903 does")},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
