@@ -199,6 +199,9 @@ class RunMerger:
         send_k = self._ensure("send_keys", stride, torch.int32)
         send_p = self._ensure("send_pays", stride, torch.int32)
         sp.export_runs(send_k.data_ptr(), send_p.data_ptr(), stride)
+        # the export runs on the context's stream, the all-gathers below on torch's current stream: this (already
+        # host-synchronous) path simply waits for the export, whatever stream the context was given
+        sp.sync()
         gk = self._ensure("gk", stride * self.world, torch.int32)
         gp = self._ensure("gp", stride * self.world, torch.int32)
         dist.all_gather_into_tensor(gk[: stride * self.world], send_k[:stride])

@@ -201,7 +201,9 @@ int gsp_merge_gathered_packed_tree(void* cudaStream, uint32_t ranks, uint32_t my
  * runs do not fit is flagged, nothing of it is merged, gsp_exchange_poll / _finish report it with the capacity that would
  * have sufficed; the caller then calls gsp_exchange_configure (same value on every rank) and repeats the frame.
  * GSP_EXCHANGE=allgather|alltoall selects the protocol (default alltoall: runs are cut by common, sample-based splitters
- * before they travel, every rank receives only the key range it merges). */
+ * before they travel, every rank receives only the key range it merges: two collectives per frame — a small all-gather of
+ * samples and grouped send/recv of the sub-blocks, whose headers also carry where each slice starts; falls back to allgather
+ * beyond 124 lists). GSP_MERGE=slice selects gsp_merge_gathered's rank-in-every-run merge instead of the merge-path tree. */
 #define GSP_COMM_ID_BYTES 128
 int gsp_comm_unique_id(uint8_t id[GSP_COMM_ID_BYTES]);
 int gsp_comm_init(gsp_context* ctx, const uint8_t id[GSP_COMM_ID_BYTES], uint32_t ranks, uint32_t rank);
