@@ -135,7 +135,7 @@ void gsp_destroy(gsp_context* ctx)
 	for (auto& p : c.pools)
 	{
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
-		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.visBits);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.worldPos); cudaFree(p.visible); cudaFree(p.visBits);
 		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount);
 	}
 	cudaFree(c.frameZero);
@@ -399,11 +399,11 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		if (cap == 0) cap = 1;
 		GSP_CUDA(cudaStreamSynchronize(c.stream));
 		cudaFree(p.aabbA); cudaFree(p.aabbB); cudaFree(p.entity); cudaFree(p.tslot); cudaFree(p.flags);
-		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.visible); cudaFree(p.visBits);
+		cudaFree(p.ready); cudaFree(p.world); cudaFree(p.worldPos); cudaFree(p.visible); cudaFree(p.visBits);
 		cudaFree(p.radius); cudaFree(p.surList); cudaFree(p.surTs); cudaFree(p.surBits); cudaFree(p.blockCount);
 		p.visBits = nullptr; p.radius = nullptr; p.surList = nullptr; p.surTs = nullptr; p.surBits = nullptr; p.blockCount = nullptr; p.bucketCount = nullptr;
 		p.aabbA = nullptr; p.aabbB = nullptr; p.entity = nullptr; p.tslot = nullptr; p.flags = nullptr; p.ready = nullptr;
-		p.world = nullptr; p.visible = nullptr; p.cullStatus = nullptr; p.capacity = 0;
+		p.world = nullptr; p.worldPos = nullptr; p.visible = nullptr; p.cullStatus = nullptr; p.capacity = 0;
 		GSP_CUDA(cudaMalloc((void**)&p.aabbA, (size_t)cap * sizeof(float4)));
 		GSP_CUDA(cudaMalloc((void**)&p.aabbB, (size_t)cap * sizeof(float2)));
 		GSP_CUDA(cudaMalloc((void**)&p.entity, (size_t)cap * sizeof(uint32_t)));
@@ -411,6 +411,7 @@ int gsp_set_mesh_pool(gsp_context* ctx, uint32_t pool, uint32_t renderType, uint
 		GSP_CUDA(cudaMalloc((void**)&p.flags, (size_t)cap));
 		GSP_CUDA(cudaMalloc((void**)&p.ready, (size_t)cap));
 		GSP_CUDA(cudaMalloc((void**)&p.world, (size_t)cap * kWorldStride * sizeof(float4)));
+		GSP_CUDA(cudaMalloc((void**)&p.worldPos, (size_t)cap * sizeof(float4)));
 		GSP_CUDA(cudaMalloc((void**)&p.visible, (size_t)cap));
 		GSP_CUDA(cudaMalloc((void**)&p.radius, (size_t)cap * sizeof(float)));
 		GSP_CUDA(cudaMalloc((void**)&p.surList, (size_t)cap * sizeof(uint32_t)));

@@ -35,6 +35,7 @@ struct CullArgs
 	uint32_t* __restrict__ surList;  // survivor index -> slot (written by kCompactSurvivors in slot order)
 	uint32_t* __restrict__ surTs;    // survivor index -> transform slot of the owning entity
 	float4* __restrict__ world;      // [survivor][kWorldStride]
+	float4* __restrict__ worldPos;   // [survivor] translation column of the same matrix (what the sort key is made of)
 	uint8_t* __restrict__ visible;
 	uint32_t* __restrict__ visBits;  // [kMaxViews][tiles * 8] one ballot word per 32 SURVIVORS and view
 	uint32_t* __restrict__ chunkCount; // [kMaxViews][chunks] visible survivors per chunk and view; scanned in place to list offsets
@@ -396,6 +397,14 @@ __global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __
 		return; // (whole warps; nothing below synchronises across warps)
 	uint32_t before = 0;
 	const uint32_t bucket = b / kPreBucket;
+	// everything this warp reads before it can write is requested up front: its own word of survivor bits, the counts of the
+	// earlier blocks of its bucket, the earlier buckets
+	const uint32_t bits = A.bits[(size_t)b * kPreWords + lane];
+	{
+		const uint32_t i0 = bucket * kPreBucket + lane, i1 = i0 + 32; // (kPreBucket == 64: two blocks per lane)
+		const uint32_t v0 = i0 < b ? A.blockCount[i0] : 0u, v1 = i1 < b ? A.blockCount[i1] : 0u;
+		before = v0 + v1;
+	}
 	for (uint32_t j0 = lane; j0 < bucket; j0 += 32 * 8) // 8 independent loads in flight per lane
 	{
 		uint32_t v[8];
@@ -406,13 +415,7 @@ __global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __
 		for (uint32_t q = 0; q < 8; q++)
 			before += v[q];
 	}
-	{
-		const uint32_t i0 = bucket * kPreBucket + lane, i1 = i0 + 32; // (kPreBucket == 64: two blocks per lane)
-		const uint32_t v0 = i0 < b ? A.blockCount[i0] : 0u, v1 = i1 < b ? A.blockCount[i1] : 0u;
-		before += v0 + v1;
-	}
 	before = __reduce_add_sync(0xffffffffu, before);
-	const uint32_t bits = A.bits[(size_t)b * kPreWords + lane];
 	const uint32_t c = __popc(bits);
 	uint32_t inc = c;
 	#pragma unroll
@@ -431,14 +434,30 @@ __global__ void __launch_bounds__(kCompactWarps * 32) kCompactSurvivors(const __
 		}
 	}
 	__syncwarp();
-	for (uint32_t j = lane; j < total; j += 32)
+	// four list positions per lane and round: the transform links are gathered with four loads in flight
+	for (uint32_t j0 = lane; j0 < total; j0 += 32 * 4)
 	{
-		const uint32_t slot = b * kPreTile + sOffsets[warp][j];
-		A.list[before + j] = slot;
-		if (kTransforms)
-			A.aux[slot] = before + j;
-		else
-			A.aux[before + j] = A.tslot[slot];
+		uint32_t slot[4], link[4];
+		#pragma unroll
+		for (uint32_t q = 0; q < 4; q++)
+		{
+			const uint32_t j = j0 + 32 * q;
+			slot[q] = b * kPreTile + (j < total ? sOffsets[warp][j] : 0u);
+			link[q] = (!kTransforms && j < total) ? A.tslot[slot[q]] : 0u;
+		}
+		#pragma unroll
+		for (uint32_t q = 0; q < 4; q++)
+		{
+			const uint32_t j = j0 + 32 * q;
+			if (j < total)
+			{
+				A.list[before + j] = slot[q];
+				if (kTransforms)
+					A.aux[slot[q]] = before + j;
+				else
+					A.aux[before + j] = link[q];
+			}
+		}
 	}
 	if (b == preBlocks - 1 && lane == 0)
 		A.counters[A.counterIndex] = before + total;
@@ -979,6 +998,7 @@ __global__ void __launch_bounds__(kCullThreads, kCullBlocksPerSM) kCull(const __
 			w[0] = make_float4(M.c[0][0], M.c[0][1], M.c[0][2], M.c[1][0]);
 			w[1] = make_float4(M.c[1][1], M.c[1][2], M.c[2][0], M.c[2][1]);
 			w[2] = make_float4(M.c[2][2], M.c[3][0], M.c[3][1], M.c[3][2]);
+			A.worldPos[tileBase + owner] = make_float4(M.c[3][0], M.c[3][1], M.c[3][2], 0.f);
 			if (P.hasReady)
 			{
 				for (uint32_t v = 0; v < P.viewCount; v++)
@@ -1109,6 +1129,7 @@ __global__ void __launch_bounds__(kClassifyThreads) kClassify(const __grid_const
 			w[0] = make_float4(M.c[0][0], M.c[0][1], M.c[0][2], M.c[1][0]);
 			w[1] = make_float4(M.c[1][1], M.c[1][2], M.c[2][0], M.c[2][1]);
 			w[2] = make_float4(M.c[2][2], M.c[3][0], M.c[3][1], M.c[3][2]);
+			A.worldPos[idx] = make_float4(M.c[3][0], M.c[3][1], M.c[3][2], 0.f);
 			if (A.visibleView != kNone && ((mask >> A.visibleView) & 1u))
 				A.visible[slot] = 1; // (the prepass stored 0 for every slot)
 		}
@@ -1272,7 +1293,7 @@ __global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constan
 			{
 				const uint32_t j = j0 + 32 * b;
 				slot[b] = chunk * kChunkItems + (j < total ? sList[warp][j] : sList[warp][j0]); // (a survivor index)
-				w2[b] = A.world[(size_t)slot[b] * kWorldStride + 2]; // (c2.z, c3.x, c3.y, c3.z) of the float4x3 world matrix
+				w2[b] = A.worldPos[slot[b]]; // (c3.x, c3.y, c3.z, 0): the dense copy of the world matrices' translation
 			}
 			#pragma unroll
 			for (uint32_t b = 0; b < kGatherBatch; b++)
@@ -1282,9 +1303,9 @@ __global__ void __launch_bounds__(kScatterThreads) kScatter(const __grid_constan
 					break;
 				float key;
 				if (P.key2D)
-					key = __fadd_rn(w2[b].w, 1.0f); // mesh.cpp:250
+					key = __fadd_rn(w2[b].z, 1.0f); // mesh.cpp:250
 				else
-					key = lengthSq3(__fadd_rn(w2[b].y, ox), __fadd_rn(w2[b].z, oy), __fadd_rn(w2[b].w, oz)); // mesh.cpp:172,251
+					key = lengthSq3(__fadd_rn(w2[b].x, ox), __fadd_rn(w2[b].y, oy), __fadd_rn(w2[b].z, oz)); // mesh.cpp:172,251
 				uint32_t k = floatToOrdered(key);
 				if (P.descending)
 					k = ~k;
@@ -1596,7 +1617,7 @@ uint32_t launchCull(Context& c, uint32_t pool, cudaEvent_t afterPrepass, cudaEve
 
 	commonArgs(c, A);
 	A.aabbA = p.aabbA; A.aabbB = p.aabbB; A.tslot = p.tslot; A.mflags = p.flags; A.ready = p.ready;
-	A.surList = p.surList; A.surTs = p.surTs; A.world = p.world; A.visible = p.visible;
+	A.surList = p.surList; A.surTs = p.surTs; A.world = p.world; A.worldPos = p.worldPos; A.visible = p.visible;
 	A.visBits = p.visBits; A.chunkCount = p.cullStatus;
 	A.keys = c.keys[0]; A.payloads = c.payloads[0]; A.sortHist = c.sortHist;
 	A.surBits = p.surBits; A.blockCount = p.blockCount; A.bucketCount = p.bucketCount;

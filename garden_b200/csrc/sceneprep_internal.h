@@ -86,6 +86,7 @@ struct PoolDev
 	uint32_t* surList = nullptr;  // survivor index -> slot
 	uint32_t* surTs = nullptr;    // survivor index -> transform slot
 	float4* world = nullptr;   // kWorldStride x float4 per SURVIVOR: float4x3 world matrix (c0..c3 lanes xyz), written when visible anywhere
+	float4* worldPos = nullptr; // (c3.x, c3.y, c3.z, 0) of the same matrices, dense: all the key computation (kScatter) reads
 	uint8_t* visible = nullptr; // isVisible of the last main view, per slot
 	uint32_t* cullStatus = nullptr; // [kMaxViews][chunks] visible count per chunk of survivors and view, scanned in place to list offsets
 	uint32_t* visBits = nullptr;    // [kMaxViews][tiles * 8] visibility ballot words over survivor indices

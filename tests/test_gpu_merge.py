@@ -226,21 +226,23 @@ def test_packed_exchange_emulated_ranks(sceneprep_lib, ranks, tree):
     sp.close()
 
 
-@pytest.mark.parametrize("ranks,key_bits", [(2, 32), (3, 6), (4, 20), (7, 3), (8, 32), (16, 10)])
-def test_merge_tree_synthetic_runs(sceneprep_lib, ranks, key_bits):
+@pytest.mark.parametrize("ranks,key_bits,lists", [(2, 32, 3), (3, 6, 3), (4, 20, 3), (7, 3, 3), (8, 32, 3), (16, 10, 3), (8, 12, 40), (5, 4, 97)])
+def test_merge_tree_synthetic_runs(sceneprep_lib, ranks, key_bits, lists):
     """The merge-path tree on hand-made blocks: runs of very different lengths (some empty, some spanning many 2048-element
     tiles), few distinct keys (ties decide by rank, then by position in the run) or 32-bit keys. Every rank's slice has to
     equal the numpy merge, and the slices together have to tile every list."""
     import torch
     from garden_b200.binding import load_library
     lib = load_library()
-    rng = np.random.default_rng(1000 * ranks + key_bits)
-    lists = 3
-    lengths = rng.integers(0, 60000, size=(ranks, lists))
+    rng = np.random.default_rng(1000 * ranks + key_bits + lists)
+    # (many lists: the (list, pair) job table spans several warp-scan rounds; some lists are empty on every rank)
+    lengths = rng.integers(0, 60000 if lists <= 3 else 5000, size=(ranks, lists))
     lengths[rng.integers(0, ranks), 0] = 0            # an empty run
     lengths[:, 2] = rng.integers(0, 40, size=ranks)   # a list shorter than one tile
     if ranks >= 3:
         lengths[1, 1] = 150000                        # one rank dominates a list
+    if lists > 3:
+        lengths[:, 5::7] = 0                          # lists nobody has anything in
     cap = int(lengths.sum(axis=1).max()) + 17
     words = lib.gsp_exchange_block_words(cap)
     blocks = np.zeros((ranks, words), np.uint32)
