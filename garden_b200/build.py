@@ -48,7 +48,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         if not (CSRC / src).exists():
             continue
         obj = obj_dir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        # GSP_NVCC_EXTRA: extra flags for experiments (e.g. "-DGSP_SORT_BLOCKS_PER_SM=4"); never set in normal builds
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("GSP_NVCC_EXTRA", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

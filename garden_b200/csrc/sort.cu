@@ -88,7 +88,10 @@ __device__ __forceinline__ uint32_t ballotPeers(uint32_t peers, uint32_t digit, 
 	return peers;
 }
 
-constexpr uint32_t kSortBlocksPerSM = kSortItems >= 16 ? 3 : 5; // resident blocks the pass is sized for
+#ifndef GSP_SORT_BLOCKS_PER_SM
+#define GSP_SORT_BLOCKS_PER_SM (kSortItems >= 16 ? 3 : 5)
+#endif
+constexpr uint32_t kSortBlocksPerSM = GSP_SORT_BLOCKS_PER_SM; // resident blocks the pass is sized for
 constexpr uint32_t kLookbackBatch = 4; // predecessor tiles inspected per step (independent loads in flight; 16 measured slower, 8 / 4 / 2 within 2 %)
 
 template<bool kUseMatch>
