@@ -375,10 +375,16 @@ int gsp_set_pool_count(gsp_context* ctx, uint32_t poolCount)
 	Context& c = ctx->c;
 	if (poolCount > (uint32_t)kMaxPools)
 		return fail(c, GSP_ERR_INVALID, "gsp_set_pool_count: too many pools");
+	bool changed = c.poolCount != poolCount;
 	for (uint32_t i = poolCount; i < (uint32_t)kMaxPools; i++)
+	{
+		changed = changed || c.pools[i].set;
 		c.pools[i].set = false;
+	}
 	c.poolCount = poolCount;
-	c.layoutDirty = true; c.resultsValid = false; c.frameEnqueued = false;
+	if (changed) // (re-stating the same count every frame, as a caller without dirty tracking does, keeps the list layout)
+		c.layoutDirty = true;
+	c.resultsValid = false; c.frameEnqueued = false;
 	return GSP_OK;
 }
 
@@ -703,6 +709,7 @@ int gsp_run_async(gsp_context* ctx)
 	if (!c.viewsSet)
 		return fail(c, GSP_ERR_STATE, "gsp_run: gsp_set_views has not been called");
 	GSP_CUDA(cudaSetDevice(c.device));
+	c.fetchedValid = false; // the record arena and the counters are about to be rewritten
 	if (c.fetchInFlight) // the previous frame's lists are still travelling out of the record arena
 	{
 		int rc = fetchWait(c);
@@ -819,7 +826,10 @@ static uint32_t poolInstanceCount(Context& c, uint32_t view, uint32_t pool)
 
 static int checkResults(Context& c, uint32_t view)
 {
-	if (!c.resultsValid)
+	// valid: a completed frame nobody has touched since — or the snapshot gsp_fetch_all_async took of one, which survives the
+	// staging of the next frame's inputs (the lists of frame k travel to the host while frame k+1 is uploaded); a layout
+	// change or the next gsp_run_async ends it
+	if (!c.resultsValid && !(c.fetchedValid && !c.layoutDirty))
 		return fail(c, GSP_ERR_STATE, "results requested before a completed gsp_run");
 	if (view >= c.views.size())
 		return fail(c, GSP_ERR_INVALID, "view index out of range");
@@ -886,6 +896,7 @@ static int fetchAllAsync(Context& c)
 		c.segDownloaded[seg] = 2; // in flight
 	}
 	c.fetchInFlight = c.fetchInFlight || any;
+	c.fetchedValid = true;
 	return GSP_OK;
 }
 

@@ -164,6 +164,8 @@ struct Context
 	cudaStream_t ownStream = nullptr, stream = nullptr;
 	cudaStream_t copyStream = nullptr; cudaEvent_t copyEvent = nullptr; // list downloads overlap the caller / the write-back
 	bool fetchInFlight = false;
+	bool fetchedValid = false; // gsp_fetch_all_async took a snapshot of the frame's lists: the list getters keep serving it while the
+	                           // NEXT frame's inputs are staged (until gsp_run_async or a layout change)
 	std::string error;
 
 	TransformsDev tf;

@@ -137,7 +137,12 @@ int gsp_get_unsorted(gsp_context* ctx, uint32_t view, uint32_t buffer, const gsp
  * synchronisation (gsp_get_unsorted / gsp_get_sorted afterwards return pointers without further copies). */
 int gsp_fetch_all(gsp_context* ctx);
 /* Same, but only enqueues the copies (on the context's copy stream, ordered after the frame): the transfer overlaps whatever
- * the caller does next, e.g. gsp_writeback_visible. The first gsp_get_unsorted / gsp_get_sorted (or gsp_fetch_all) waits. */
+ * the caller does next, e.g. gsp_writeback_visible. The first gsp_get_unsorted / gsp_get_sorted (or gsp_fetch_all) waits.
+ * The call also takes a SNAPSHOT of the frame's lists: the list getters keep serving it while the inputs of the NEXT frame are
+ * staged (gsp_set_transforms / gsp_update_transforms* / gsp_set_mesh_pool / gsp_set_views with the same shape), so the lists
+ * of frame k travel to the host while frame k+1 is uploaded — the renderer consumes frame k meanwhile, as the reference's
+ * render passes do after prepareMeshes. The snapshot ends with the next gsp_run[_async] or any change of the list layout
+ * (pool count, a pool's capacity or render type, the number or kind of views). */
 int gsp_fetch_all_async(gsp_context* ctx);
 /* sortedBuffers[buffer]->{drawCount, instanceCount} */
 int gsp_get_sorted_counts(gsp_context* ctx, uint32_t view, uint32_t buffer, uint32_t* drawCount, uint32_t* instanceCount);

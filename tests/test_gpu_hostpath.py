@@ -190,3 +190,47 @@ def test_sync_and_writeback_follow_the_frame_state(oracle_built, sceneprep_lib):
     sp.writeback_visible(0, m, 48)
     assert int(m["isVisible"].sum()) == seen
     sp.close()
+
+
+def test_fetched_lists_survive_the_staging_of_the_next_frame(oracle_built, sceneprep_lib):
+    """gsp_fetch_all_async takes a snapshot: the list getters keep serving frame k while frame k+1's inputs are staged (the
+    pipelined end-to-end loop of bench.py), until the next run or a layout change."""
+    from garden_b200.binding import GSP_ERR_STATE, ScenePrep, ScenePrepError
+    scene = scenes.config_scene("C2", n=30_000)
+    t, pools = aos_inputs(scene)
+    views, _ = V.camera_and_cascades(0.3, -0.1, 1.2, 16 / 9, 0.01, 100.0, (0.05, 0.1, 0.25, 1.0))
+    sp = ScenePrep(0)
+
+    def stage(tr, vw):
+        sp.set_transforms(tr, tr.dtype.itemsize, tr.size)
+        sp.set_pool_count(1)
+        sp.set_mesh_pool(0, RT_OPAQUE, pools[0], 48, pools[0].size)
+        sp.set_views(vw, scene.camera_pos)
+
+    stage(t, views)
+    sp.run()
+    before = [sp.get_unsorted(v, 0)[0].copy() for v in range(views.size)]
+    assert sum(b.size for b in before) > 0
+    # frame k+1 = the same scene moved: staged while frame k's snapshot is still being read
+    moved = t.copy()
+    moved["position"][:, 0] += 3.0
+    sp.run()
+    sp.fetch_all_async()
+    stage(moved, views)
+    during = [sp.get_unsorted(v, 0)[0].copy() for v in range(views.size)]
+    for a, b in zip(before, during):
+        assert a.tobytes() == b.tobytes(), "the snapshot must still be frame k"
+    assert sp.get_sorted(0, 0)[1] == 0
+    with pytest.raises(ScenePrepError) as e:
+        sp.sync()  # ... but nothing of the NEW inputs has run yet
+    assert e.value.code == GSP_ERR_STATE
+    sp.run()
+    after = [sp.get_unsorted(v, 0)[0] for v in range(views.size)]
+    assert any(a.tobytes() != b.tobytes() for a, b in zip(before, after)), "the next run replaces the snapshot"
+    # a layout change ends the snapshot at once
+    sp.fetch_all_async()
+    sp.set_views(views[:4], scene.camera_pos)
+    with pytest.raises(ScenePrepError) as e:
+        sp.get_unsorted(0, 0)
+    assert e.value.code == GSP_ERR_STATE
+    sp.close()
