@@ -1,14 +1,17 @@
 """Multi-GPU plumbing for the sharded scene preparation (one process per GPU, torch.distributed).
 
-Sharding: every rank owns a contiguous entity range (all views), culls and sorts it with the single-GPU path, then
-  1. all-gather of the per-list lengths              (tiny; tells every rank the layout of the gathered runs)
-  2. all-gather of the sorted (key, payload) runs    (NCCL over NVLink; 8 bytes per visible entity and view)
-  3. k-way merge on the device: each rank merges ITS key range of every list (gsp_merge_gathered)
-The merged draw order equals a single sort over all entities with ties broken by global entity order, because ranks hold
-contiguous ranges in rank order and the merge breaks ties by (rank, payload).
+Sharding: every rank owns a contiguous entity range (all views), culls and sorts it with the single-GPU path; the sorted
+(key, payload) runs are then exchanged by key range and merged so that the result equals a single sort over all entities,
+ties broken by global entity order (ranks hold contiguous ranges in rank order, the merge breaks ties by (rank, payload)).
 
-`plan_gather` and `merge_reference` are pure numpy (they define the layout / the expected result) and are what the CPU
-tests check, including a world_size-2 gloo run of `exchange_counts`.
+The exchange itself lives in libgarden_sceneprep.so (csrc/exchange.cu, csrc/merge.cu: NCCL loaded by the library, no host
+synchronisation, key-range all-to-all + merge-path tree) — `PipelinedRunMerger` below only carries the NCCL unique id over
+torch.distributed and forwards to gsp_exchange_*. `RunMerger` is round 1's host-synchronous path (lengths to the host, two
+all-gathers through torch.distributed, gsp_merge_gathered), kept for tools/dist_parity.py's cross-check.
+
+`plan_gather`, `pack_block`, `plan_from_blocks`, `sample_run`, `common_splitters`, `split_bounds` and `merge_reference` are
+pure numpy statements of what the device kernels compute (layouts, splitters, expected merges); the CPU tests check them,
+including world_size-2 gloo runs of the count exchange, the one-block all-gather and the all-to-all.
 """
 from __future__ import annotations
 
@@ -287,8 +290,11 @@ class PipelinedRunMerger:
         info = [C.c_uint32() for _ in range(4)]
         sp._check(lib.gsp_comm_info(sp.h, *[C.byref(i) for i in info]))
         self.all_to_all = bool(info[3].value)
-        # kernels per frame on top of the single-GPU frame
-        self.launches_per_frame = 8 if self.all_to_all else 4
+        # kernels of this library per frame on top of the single-GPU frame (NCCL's own kernels are not counted):
+        # alltoall: kSampleRuns, kSplitRuns, kPackByDestination, kMergePlan, kMergeBounds, kSliceStarts + (kTreePartition,
+        # kMergeTree) per merge level; allgather: kExportPacked, kMergePlan, kMergeBounds + the same per level
+        levels = max(1, int(np.ceil(np.log2(max(self.world, 2)))))
+        self.launches_per_frame = (6 if self.all_to_all else 3) + 2 * levels
         self.timing = None
         self.frame_index = 0
 
