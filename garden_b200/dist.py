@@ -152,6 +152,51 @@ def merge_reference(runs_keys, runs_payloads, my_rank: int | None = None):
     return keys[lo:hi], pays[lo:hi], src[lo:hi], lo
 
 
+def merge_path_cut(a: np.ndarray, b: np.ndarray, diag: int) -> int:
+    """How many of the first `diag` outputs of merge(a, b) come from a, a winning ties — the binary search kTreePartition's
+    warps run (csrc/merge.cu: warpMergePath, 32 probes per round there)."""
+    lo, hi = max(0, diag - len(b)), min(diag, len(a))
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if a[mid] <= b[diag - 1 - mid]:
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo
+
+
+def merge_tree_reference(runs_keys, runs_payloads, tile: int = 2048):
+    """numpy statement of the pairwise merge tree (kTreePartition + kMergeTree) for ONE list: the runs are merged two by
+    two in rank order, level by level, every merge cut into tiles of `tile` outputs by merge-path diagonals and each tile
+    merged on its own (a wins ties). Returns (keys, payloads, ranks) — equal to merge_reference(...) of the same runs."""
+    groups = [(np.asarray(k, np.uint32), np.asarray(p, np.uint32), np.full(len(k), r, np.uint8))
+              for r, (k, p) in enumerate(zip(runs_keys, runs_payloads))]
+    if not groups:
+        return np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint8)
+    while len(groups) > 1:
+        merged = []
+        for g in range(0, len(groups), 2):
+            if g + 1 == len(groups):
+                merged.append(groups[g])  # (an odd group is copied through: a merge with an empty partner)
+                continue
+            (ka, pa, ra), (kb, pb, rb) = groups[g], groups[g + 1]
+            n = len(ka) + len(kb)
+            out_k, out_p, out_r = np.empty(n, np.uint32), np.empty(n, np.uint32), np.empty(n, np.uint8)
+            for d0 in range(0, n, tile):
+                d1 = min(d0 + tile, n)
+                i0, i1 = merge_path_cut(ka, kb, d0), merge_path_cut(ka, kb, d1)
+                j0, j1 = d0 - i0, d1 - i1
+                ta, tb = ka[i0:i1], kb[j0:j1]
+                # inside the tile: an element of a goes after the b's that are smaller, an element of b after the a's <= it
+                pos_a = np.arange(len(ta)) + np.searchsorted(tb, ta, side="left")
+                pos_b = np.arange(len(tb)) + np.searchsorted(ta, tb, side="right")
+                out_k[d0 + pos_a], out_p[d0 + pos_a], out_r[d0 + pos_a] = ta, pa[i0:i1], ra[i0:i1]
+                out_k[d0 + pos_b], out_p[d0 + pos_b], out_r[d0 + pos_b] = tb, pb[j0:j1], rb[j0:j1]
+            merged.append((out_k, out_p, out_r))
+        groups = merged
+    return groups[0]
+
+
 def exchange_counts(counts: np.ndarray, group=None) -> np.ndarray:
     """All-gather of the per-list lengths. Works with any backend (tensors live where the backend needs them)."""
     import torch

@@ -245,3 +245,29 @@ def test_alltoall_exchange_gloo_world2(tmp_path):
             assert np.array_equal(res[r][f"s{l}"], full_r[pos:pos + n])
             pos += n
         assert pos == full_k.size
+
+
+@pytest.mark.parametrize("ranks,key_bits", [(1, 8), (2, 32), (3, 4), (5, 6), (8, 10), (8, 2)])
+def test_merge_tree_statement_equals_the_full_merge(ranks, key_bits):
+    """The pairwise merge-path tree (what kTreePartition + kMergeTree compute, stated in numpy with the same tile cuts and
+    the same tie rule) equals the (key, rank, payload) sort of all runs, for runs with many ties and of very different
+    lengths; every diagonal cut is consistent with the merged order."""
+    from garden_b200.dist import merge_path_cut, merge_reference, merge_tree_reference
+    rng = np.random.default_rng(17 * ranks + key_bits)
+    lengths = rng.integers(0, 9000, size=ranks)
+    lengths[rng.integers(0, ranks)] = 0
+    runs_k, runs_p = [], []
+    for n in lengths:
+        k = np.sort(rng.integers(0, 1 << key_bits, size=int(n), dtype=np.uint64).astype(np.uint32))
+        p = rng.integers(0, 1 << 28, size=int(n), dtype=np.uint64).astype(np.uint32)
+        p = p[np.lexsort((p, k))]
+        runs_k.append(k); runs_p.append(p)
+    ek, ep, er = merge_reference(runs_k, runs_p)
+    for tile in (2048, 7):
+        tk, tp, tr = merge_tree_reference(runs_k, runs_p, tile=tile)
+        assert np.array_equal(tk, ek) and np.array_equal(tp, ep) and np.array_equal(tr, er)
+    if ranks >= 2:
+        a, b = runs_k[0], runs_k[1]
+        mk, _, mr = merge_reference([a, b], [runs_p[0], runs_p[1]])
+        for diag in rng.integers(0, len(a) + len(b) + 1, size=20):
+            assert merge_path_cut(a, b, int(diag)) == int((mr[:diag] == 0).sum())
