@@ -249,12 +249,9 @@ int gsp_light_view_proj(const float* view, const float* lightDir, float fieldOfV
 
 // Camera without a parent: view = rotate(normalize(q)) * translate(scale(s), -p) with its translation zeroed, projection =
 // calcPerspProjInfRevZ, viewProj = projection * view (graphics.cpp:168-172,198-203,241; camera.hpp:111-121).
-int gsp_camera_view_proj(const float* position, const float* rotation, const float* scale, float fieldOfView, float aspectRatio,
-	float nearPlane, float* view, float* projection, float* viewProj)
+// rotate(normalize(q)), matrix/transform.hpp:128-140 (scalar float code on the normalised lanes)
+static M4 rotationOf(const float* rotation)
 {
-	if (!position || !rotation || !scale || !view || !projection || !viewProj)
-		return GSP_ERR_INVALID;
-	// rotate(quat), matrix/transform.hpp:128-140 (scalar float code)
 	const L4 q = normalize4(make(rotation[0], rotation[1], rotation[2], rotation[3]));
 	const float x = q.v[0], y = q.v[1], z = q.v[2], w = q.v[3];
 	const float xx = rnd(x * x), yy = rnd(y * y), zz = rnd(z * z), xz = rnd(x * z), xy = rnd(x * y), yz = rnd(y * z);
@@ -264,24 +261,73 @@ int gsp_camera_view_proj(const float* position, const float* rotation, const flo
 	R.c[1] = make(rnd(2.0f * rnd(xy - wz)), rnd(1.0f - rnd(2.0f * rnd(xx + zz))), rnd(2.0f * rnd(yz + wx)), 0.0f);
 	R.c[2] = make(rnd(2.0f * rnd(xz + wy)), rnd(2.0f * rnd(yz - wx)), rnd(1.0f - rnd(2.0f * rnd(xx + yy))), 0.0f);
 	R.c[3] = make(0.0f, 0.0f, 0.0f, 1.0f);
-	// translate(scale(s), -p) (matrix/transform.hpp:59-62,80-84)
+	return R;
+}
+static M4 scaleOf(const float* scale) // scale(s), matrix/transform.hpp:80-84
+{
 	M4 S;
 	S.c[0] = make(scale[0], 0.0f, 0.0f, 0.0f); S.c[1] = make(0.0f, scale[1], 0.0f, 0.0f);
 	S.c[2] = make(0.0f, 0.0f, scale[2], 0.0f); S.c[3] = make(0.0f, 0.0f, 0.0f, 1.0f);
+	return S;
+}
+// calcView (graphics.cpp:168-172): rotate(normalize(q)) * translate(scale(s), -p)
+static M4 cameraView(const float* position, const float* rotation, const float* scale)
+{
+	const M4 R = rotationOf(rotation);
+	M4 S = scaleOf(scale);
 	const L4 t = neg(make(position[0], position[1], position[2], 0.0f));
 	{
-		// c3 = (c3 + dot3x3(m, t)).xyz, lane W kept; dot3x3 = mul, fma, fma over the first three columns (simd/matrix/float.hpp:372-378)
+		// translate(m, t): c3 = (c3 + dot3x3(m, t)).xyz, lane W kept; dot3x3 = mul, fma, fma over the first three columns
+		// (matrix/transform.hpp:59-62, simd/matrix/float.hpp:372-378)
 		L4 r = mul(S.c[0], splat(t.v[0]));
 		r = fma4(S.c[1], splat(t.v[1]), r);
 		r = fma4(S.c[2], splat(t.v[2]), r);
 		const L4 sum = add(S.c[3], r);
 		S.c[3] = make(sum.v[0], sum.v[1], sum.v[2], S.c[3].v[3]);
 	}
-	M4 V = mulMat(R, S);
+	return mulMat(R, S);
+}
+// math::calcModel, general branch (matrix/transform.hpp:255): translate(position) * rotate(normalize(q)) * scale(s). The
+// `scale == f32x4::one` shortcut compares all four lanes and lane W of a component's scale holds childCapacity bits
+// (transform.hpp:40,52,84), which never read as 1.0f: components always take this branch.
+static M4 localModel(const float* position, const float* rotation, const float* scale)
+{
+	M4 T;
+	T.c[0] = make(1.0f, 0.0f, 0.0f, 0.0f); T.c[1] = make(0.0f, 1.0f, 0.0f, 0.0f);
+	T.c[2] = make(0.0f, 0.0f, 1.0f, 0.0f); T.c[3] = make(position[0], position[1], position[2], 1.0f);
+	return mulMat(mulMat(T, rotationOf(rotation)), scaleOf(scale));
+}
+
+static int cameraViewProj(M4 V, float fieldOfView, float aspectRatio, float nearPlane, float* view, float* projection, float* viewProj)
+{
 	V.c[3] = make(0.0f, 0.0f, 0.0f, V.c[3].v[3]); // setTranslation(view, zero): the camera-relative view keeps lane W
 	const M4 P = perspInfRevZ(fieldOfView, aspectRatio, nearPlane);
 	store(view, V); store(projection, P); store(viewProj, mulMat(P, V));
 	return GSP_OK;
+}
+
+int gsp_camera_view_proj(const float* position, const float* rotation, const float* scale, float fieldOfView, float aspectRatio,
+	float nearPlane, float* view, float* projection, float* viewProj)
+{
+	if (!position || !rotation || !scale || !view || !projection || !viewProj)
+		return GSP_ERR_INVALID;
+	return cameraViewProj(cameraView(position, rotation, scale), fieldOfView, aspectRatio, nearPlane, view, projection, viewProj);
+}
+
+// calcRelativeView (graphics.cpp:173-189): view = calcView(camera); for every ancestor, nearest first:
+// view = calcModel(ancestor) * view. parents[i] = { position xyz, rotation xyzw, scale xyz } (10 floats).
+int gsp_camera_view_proj_chain(const float* position, const float* rotation, const float* scale, const float* parents,
+	uint32_t parentCount, float fieldOfView, float aspectRatio, float nearPlane, float* view, float* projection, float* viewProj)
+{
+	if (!position || !rotation || !scale || !view || !projection || !viewProj || (parentCount && !parents))
+		return GSP_ERR_INVALID;
+	M4 V = cameraView(position, rotation, scale);
+	for (uint32_t i = 0; i < parentCount; i++)
+	{
+		const float* a = parents + (size_t)i * 10;
+		V = mulMat(localModel(a, a + 3, a + 7), V);
+	}
+	return cameraViewProj(V, fieldOfView, aspectRatio, nearPlane, view, projection, viewProj);
 }
 
 // The shadow passes of a frame the way CsmRenderSystem::prepareShadowRender produces them (csm.cpp:311-329): pass i covers

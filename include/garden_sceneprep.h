@@ -254,9 +254,12 @@ void gsp_frustum_planes(const float* viewProj, float* planes);
 int gsp_view_from_viewproj(const float* viewProj, const float* cameraOffset, int32_t shadowPass, gsp_view* view);
 /* The matrices themselves, in the reference's float operation order (host code; csrc/viewsetup.cu), so that a caller that hands
  * over camera parameters instead of planes gets the reference's planes bit for bit. All matrices: 16 floats, column-major.
- *   gsp_camera_view_proj   GraphicsSystem::prepareCommonConstants for a perspective camera without a parent
+ *   gsp_camera_view_proj   GraphicsSystem::prepareCommonConstants for a perspective camera without a parent entity
  *                          (source/system/graphics.cpp:168-172,192-203,241; camera.hpp:111-121): the camera-relative view
  *                          (translation zeroed), calcPerspProjInfRevZ, viewProj = projection * view
+ *   gsp_camera_view_proj_chain  the same for a camera WITH ancestors: calcRelativeView (graphics.cpp:173-189) multiplies
+ *                          calcModel(ancestor) onto the view, nearest ancestor first; parents[i] = { position xyz, rotation
+ *                          xyzw, scale xyz } (10 floats per ancestor)
  *   gsp_light_view_proj    calcLightViewProj (source/system/render/csm.cpp:260-308): cascade viewProj + cameraOffset for the
  *                          camera sub-frustum [nearPlane, farPlane]
  *   gsp_cascade_views      CsmRenderSystem::prepareShadowRender for passes 0 .. cascadeCount-1 (csm.cpp:311-329): `splits`
@@ -264,6 +267,8 @@ int gsp_view_from_viewproj(const float* viewProj, const float* cameraOffset, int
  *                          shadowPass = i) and, if not NULL, viewProjs[i][16] */
 int gsp_camera_view_proj(const float* position, const float* rotation, const float* scale, float fieldOfView, float aspectRatio,
 	float nearPlane, float* view, float* projection, float* viewProj);
+int gsp_camera_view_proj_chain(const float* position, const float* rotation, const float* scale, const float* parents,
+	uint32_t parentCount, float fieldOfView, float aspectRatio, float nearPlane, float* view, float* projection, float* viewProj);
 int gsp_light_view_proj(const float* view, const float* lightDir, float fieldOfView, float aspectRatio, float nearPlane, float farPlane,
 	float zCoeff, uint32_t shadowMapSize, float* viewProj, float* cameraOffset);
 int gsp_cascade_views(const float* view, const float* lightDir, float fieldOfView, float aspectRatio, float cameraNear,
