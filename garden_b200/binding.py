@@ -76,6 +76,7 @@ SYMBOLS = {
     "gsp_view_from_viewproj": (_i32, [_vp, _vp, _i32, _vp]),
     "gsp_camera_view_proj": (_i32, [_vp, _vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp]),
     "gsp_camera_view_proj_chain": (_i32, [_vp, _vp, _vp, _vp, _u32, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "gsp_camera_view_proj_ortho": (_i32, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsp_light_view_proj": (_i32, [_vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _u32, _vp, _vp]),
     "gsp_cascade_views": (_i32, [_vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _u32, C.c_float, _u32, _vp, _vp]),
     "gsp_set_active": (_i32, [_vp, _vp, _u32, _i32]),

@@ -330,6 +330,26 @@ int gsp_camera_view_proj_chain(const float* position, const float* rotation, con
 	return cameraViewProj(V, fieldOfView, aspectRatio, nearPlane, view, projection, viewProj);
 }
 
+// The same for an ORTHOGRAPHIC CameraComponent (camera.hpp:119-120: calcOrthoProjRevZ(width, height, depth)); ancestors as in
+// gsp_camera_view_proj_chain (parentCount may be 0).
+int gsp_camera_view_proj_ortho(const float* position, const float* rotation, const float* scale, const float* parents,
+	uint32_t parentCount, const float width[2], const float height[2], const float depth[2], float* view, float* projection,
+	float* viewProj)
+{
+	if (!position || !rotation || !scale || !width || !height || !depth || !view || !projection || !viewProj || (parentCount && !parents))
+		return GSP_ERR_INVALID;
+	M4 V = cameraView(position, rotation, scale);
+	for (uint32_t i = 0; i < parentCount; i++)
+	{
+		const float* a = parents + (size_t)i * 10;
+		V = mulMat(localModel(a, a + 3, a + 7), V);
+	}
+	V.c[3] = make(0.0f, 0.0f, 0.0f, V.c[3].v[3]);
+	const M4 P = orthoRevZ(width[0], width[1], height[0], height[1], depth[0], depth[1]);
+	store(view, V); store(projection, P); store(viewProj, mulMat(P, V));
+	return GSP_OK;
+}
+
 // The shadow passes of a frame the way CsmRenderSystem::prepareShadowRender produces them (csm.cpp:311-329): pass i covers
 // [i == 0 ? cameraNear : distance * splits[i - 1],  i == count - 1 ? distance : distance * splits[i]].
 int gsp_cascade_views(const float* view, const float* lightDir, float fieldOfView, float aspectRatio, float cameraNear,

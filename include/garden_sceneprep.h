@@ -260,6 +260,8 @@ int gsp_view_from_viewproj(const float* viewProj, const float* cameraOffset, int
  *   gsp_camera_view_proj_chain  the same for a camera WITH ancestors: calcRelativeView (graphics.cpp:173-189) multiplies
  *                          calcModel(ancestor) onto the view, nearest ancestor first; parents[i] = { position xyz, rotation
  *                          xyzw, scale xyz } (10 floats per ancestor)
+ *   gsp_camera_view_proj_ortho  the same for an orthographic CameraComponent: calcOrthoProjRevZ(width, height, depth)
+ *                          (camera.hpp:119-120, matrix/projection.hpp:92-99); ancestors as above (parentCount may be 0)
  *   gsp_light_view_proj    calcLightViewProj (source/system/render/csm.cpp:260-308): cascade viewProj + cameraOffset for the
  *                          camera sub-frustum [nearPlane, farPlane]
  *   gsp_cascade_views      CsmRenderSystem::prepareShadowRender for passes 0 .. cascadeCount-1 (csm.cpp:311-329): `splits`
@@ -269,6 +271,9 @@ int gsp_camera_view_proj(const float* position, const float* rotation, const flo
 	float nearPlane, float* view, float* projection, float* viewProj);
 int gsp_camera_view_proj_chain(const float* position, const float* rotation, const float* scale, const float* parents,
 	uint32_t parentCount, float fieldOfView, float aspectRatio, float nearPlane, float* view, float* projection, float* viewProj);
+int gsp_camera_view_proj_ortho(const float* position, const float* rotation, const float* scale, const float* parents,
+	uint32_t parentCount, const float width[2], const float height[2], const float depth[2], float* view, float* projection,
+	float* viewProj);
 int gsp_light_view_proj(const float* view, const float* lightDir, float fieldOfView, float aspectRatio, float nearPlane, float farPlane,
 	float zCoeff, uint32_t shadowMapSize, float* viewProj, float* cameraOffset);
 int gsp_cascade_views(const float* view, const float* lightDir, float fieldOfView, float aspectRatio, float cameraNear,

@@ -57,3 +57,23 @@ REF_EXPORT void ref_camera_view_proj_chain(const float* position, const float* r
 	auto viewProj = projection * view;
 	memcpy(viewOut, &view, 64); memcpy(projectionOut, &projection, 64); memcpy(viewProjOut, &viewProj, 64);
 }
+
+// The same with the projection of an orthographic CameraComponent (camera.hpp:119-120).
+REF_EXPORT void ref_camera_view_proj_ortho(const float* position, const float* rotation, const float* scaling, const float* parents,
+	uint32_t parentCount, const float* width, const float* height, const float* depth, float* viewOut, float* projectionOut,
+	float* viewProjOut)
+{
+	f32x4 p(position[0], position[1], position[2], 0.0f), s(scaling[0], scaling[1], scaling[2], 0.0f);
+	quat q(rotation[0], rotation[1], rotation[2], rotation[3]);
+	auto view = rotate(normalize(q)) * translate(scale(s), -p);
+	for (uint32_t i = 0; i < parentCount; i++)
+	{
+		const float* a = parents + (size_t)i * 10;
+		auto parentModel = calcModel(f32x4(a[0], a[1], a[2], 0.0f), quat(a[3], a[4], a[5], a[6]), f32x4(a[7], a[8], a[9], 0.0f));
+		view = parentModel * view;
+	}
+	setTranslation(view, f32x4::zero);
+	auto projection = (f32x4x4)calcOrthoProjRevZ(float2(width[0], width[1]), float2(height[0], height[1]), float2(depth[0], depth[1]));
+	auto viewProj = projection * view;
+	memcpy(viewOut, &view, 64); memcpy(projectionOut, &projection, 64); memcpy(viewProjOut, &viewProj, 64);
+}
